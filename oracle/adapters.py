@@ -1,0 +1,58 @@
+"""Oracle objects with the duck-typed surfaces the reference pipeline calls.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+``OracleTransformer`` quacks like ``pipe.transformer`` (call signature at
+pipeline_wan_i2v_clean.py:593-610), ``OracleVAE`` like ``pipe.vae``
+(``encode(x).latent_dist.mode()`` :348 / scheduling...:1384,
+``decode(z, return_dict=False)[0]`` :743 / :1285, ``config.{z_dim,latents_mean,
+latents_std}`` :333-340).  Batch size is 1, as in the entry script.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import torch
+
+from . import wan_dit, wan_vae
+
+
+class OracleTransformer:
+    def __init__(self, params, cfg: wan_dit.DitConfig, amp: bool = True, out_dtype=torch.bfloat16):
+        self.P, self.cfg, self.amp = params, cfg, amp
+        self.dtype = out_dtype
+        self.config = SimpleNamespace(patch_size=cfg.patch)
+        self.calls = 0
+
+    def __call__(self, hidden_states, timestep, encoder_hidden_states, encoder_hidden_states_image=None,
+                 attention_kwargs=None, return_dict=False):
+        assert hidden_states.shape[0] == 1
+        self.calls += 1
+        y = wan_dit.dit_forward(self.P, self.cfg, hidden_states[0].cpu(), timestep.reshape(-1)[:1].cpu(),
+                                encoder_hidden_states[0].cpu(), encoder_hidden_states_image[0].cpu(), amp=self.amp)
+        return (y.unsqueeze(0).to(self.dtype).to(hidden_states.device),)
+
+
+class _Dist:
+    def __init__(self, mean):
+        self._m = mean
+
+    def mode(self):
+        return self._m
+
+
+class OracleVAE:
+    def __init__(self, params, cfg: wan_vae.VaeConfig = wan_vae.WAN_VAE):
+        self.P, self.cfg = params, cfg
+        self.dtype = torch.float32
+        self.config = SimpleNamespace(z_dim=cfg.z_dim, latents_mean=list(wan_vae.LATENTS_MEAN[:cfg.z_dim]),
+                                      latents_std=list(wan_vae.LATENTS_STD[:cfg.z_dim]))
+        self.temperal_downsample = list(cfg.temporal_downsample)
+
+    def encode(self, x):
+        assert x.shape[0] == 1
+        return SimpleNamespace(latent_dist=_Dist(wan_vae.encode_mode(self.P, self.cfg, x[0].cpu()).unsqueeze(0).to(x.device)))
+
+    def decode(self, z, return_dict=False):
+        assert z.shape[0] == 1
+        return (wan_vae.decode(self.P, self.cfg, z[0].cpu()).unsqueeze(0).to(z.device),)

@@ -1,0 +1,189 @@
+"""Import the UNMODIFIED reference modules from /root/reference (build container only).
+
+TEST INFRASTRUCTURE ONLY.  Used by ``oracle/make_golden.py`` and by the
+``not gpu`` tests that pin the oracle against the reference when
+``/root/reference`` exists (it does not exist on the GPU box, where the
+committed fixtures in ``tests/golden/`` stand in).
+
+``diffusers`` is not installed here, and the reference's model / scheduler files
+import four things from it (model.py:7-8, scheduling_unipc_multistep_clean.py:22-24).
+A minimal stand-in for exactly those names is registered in ``sys.modules``;
+nothing of the reference is copied or edited.  ``flash_attention`` asserts CUDA
+(attention.py:54), so on the CPU it is replaced by an equivalent SDPA call.
+"""
+from __future__ import annotations
+
+import functools
+import importlib
+import inspect
+import os
+import sys
+import types
+from enum import Enum
+
+import torch
+
+REF_ROOT = "/root/reference"
+REF_WAN = os.path.join(REF_ROOT, "wan_for_worldforge")
+
+
+def available() -> bool:
+    return os.path.isdir(REF_WAN)
+
+
+class _Cfg(dict):
+    __getattr__ = dict.__getitem__
+
+
+def _register_to_config(init):
+    @functools.wraps(init)
+    def wrapped(self, *a, **kw):
+        sig = inspect.signature(init)
+        bound = sig.bind(self, *a, **kw)
+        bound.apply_defaults()
+        cfg = {k: v for k, v in bound.arguments.items() if k != "self"}
+        prev = getattr(self, "_shim_cfg", None)
+        self._shim_cfg = _Cfg(cfg if prev is None else {**prev, **cfg})
+        init(self, *a, **kw)
+    return wrapped
+
+
+class _ConfigMixin:
+    @property
+    def config(self):
+        return self._shim_cfg
+
+    def register_to_config(self, **kw):
+        self._shim_cfg.update(kw)
+
+    @classmethod
+    def from_config(cls, config, **kw):
+        return cls(**{**dict(config), **kw})
+
+
+class _ModelMixin(torch.nn.Module):
+    pass
+
+
+class _SchedulerMixin:
+    pass
+
+
+class _BaseOutput(dict):
+    pass
+
+
+class _Karras(Enum):
+    UniPCMultistepScheduler = 1
+
+
+def install_diffusers_shim() -> None:
+    if "diffusers" in sys.modules and not getattr(sys.modules["diffusers"], "_wf_shim", False):
+        return  # a real diffusers is present: use it
+    def mod(name):
+        m = types.ModuleType(name)
+        sys.modules[name] = m
+        return m
+    d = mod("diffusers"); d._wf_shim = True
+    cu = mod("diffusers.configuration_utils")
+    cu.ConfigMixin = _ConfigMixin
+    cu.register_to_config = _register_to_config
+    mm = mod("diffusers.models"); mu = mod("diffusers.models.modeling_utils")
+    mu.ModelMixin = _ModelMixin
+    ut = mod("diffusers.utils")
+    ut.deprecate = lambda *a, **k: None
+    ut.is_scipy_available = lambda: True
+    ut.BaseOutput = _BaseOutput
+    sc = mod("diffusers.schedulers"); su = mod("diffusers.schedulers.scheduling_utils")
+    su.KarrasDiffusionSchedulers = _Karras
+    su.SchedulerMixin = _SchedulerMixin
+    su.SchedulerOutput = _BaseOutput
+    d.configuration_utils, d.models, d.utils, d.schedulers = cu, mm, ut, sc
+    mm.modeling_utils = mu
+    sc.scheduling_utils = su
+
+
+def _sdpa_flash_attention(q, k, v, q_lens=None, k_lens=None, dropout_p=0., softmax_scale=None,
+                          q_scale=None, causal=False, window_size=(-1, -1), deterministic=False,
+                          dtype=torch.bfloat16, version=None):
+    """CPU stand-in with flash_attention's dtype contract (attention.py:54-130):
+    inputs that are not half are cast to ``dtype``; the result is cast back to q's dtype."""
+    assert q_lens is None and not causal
+    if k_lens is not None:   # self-attention passes the (full) sequence length
+        assert all(int(n) == k.size(1) for n in k_lens)
+    out_dtype = q.dtype
+    half = (torch.float16, torch.bfloat16)
+    cast = (lambda x: x if x.dtype in half else x.to(dtype)) if _FLASH_CAST[0] else (lambda x: x)
+    q, k, v = cast(q), cast(k), cast(v)
+    q = q.to(v.dtype); k = k.to(v.dtype)
+    o = torch.nn.functional.scaled_dot_product_attention(
+        q.transpose(1, 2).float(), k.transpose(1, 2).float(), v.transpose(1, 2).float(),
+        scale=softmax_scale).transpose(1, 2)
+    if _FLASH_CAST[0]:
+        o = o.to(v.dtype)
+    return o.contiguous().type(out_dtype)
+
+
+_FLASH_CAST = [False]   # False: keep fp32 end to end (fp32 pinning); True: flash-attn's bf16 casts
+
+
+def _add_path():
+    if REF_WAN not in sys.path:
+        sys.path.insert(0, REF_WAN)
+
+
+def load_wan_model_module(cpu_autocast: bool = False):
+    """Returns wan.modules.model with flash_attention replaced for the CPU.
+
+    cpu_autocast=True additionally maps the ``torch.cuda.amp.autocast`` the
+    module uses for its fp32 islands (model.py:31,42,297,305,312,344,546) onto
+    CPU autocast, so that running the module under
+    ``torch.autocast('cpu', dtype=torch.bfloat16)`` reproduces the dtype flow it
+    has on a GPU under ``torch.autocast('cuda', dtype=torch.bfloat16)``.
+    """
+    assert available()
+    install_diffusers_shim()
+    _add_path()
+    if cpu_autocast:
+        import torch.cuda.amp as camp
+        if not getattr(camp, "_wf_patched", False):
+            camp._orig_autocast = camp.autocast
+            camp.autocast = lambda *a, **kw: torch.autocast("cpu", *a, **kw)
+            camp._wf_patched = True
+    for name in [m for m in sys.modules if m == "wan" or m.startswith("wan.")]:
+        del sys.modules[name]
+    # import the sub-modules directly; wan/__init__ pulls in pipelines we do not need
+    pkg = types.ModuleType("wan"); pkg.__path__ = [os.path.join(REF_WAN, "wan")]
+    sys.modules["wan"] = pkg
+    mods = types.ModuleType("wan.modules"); mods.__path__ = [os.path.join(REF_WAN, "wan", "modules")]
+    sys.modules["wan.modules"] = mods
+    att = importlib.import_module("wan.modules.attention")
+    att.flash_attention = _sdpa_flash_attention
+    model = importlib.import_module("wan.modules.model")
+    model.flash_attention = _sdpa_flash_attention
+    _FLASH_CAST[0] = cpu_autocast
+    return model
+
+
+def load_wan_vae_module():
+    assert available()
+    _add_path()
+    if "wan" not in sys.modules:
+        pkg = types.ModuleType("wan"); pkg.__path__ = [os.path.join(REF_WAN, "wan")]
+        sys.modules["wan"] = pkg
+        mods = types.ModuleType("wan.modules"); mods.__path__ = [os.path.join(REF_WAN, "wan", "modules")]
+        sys.modules["wan.modules"] = mods
+    return importlib.import_module("wan.modules.vae")
+
+
+def load_scheduler_module():
+    assert available()
+    install_diffusers_shim()
+    _add_path()
+    if "utils" in sys.modules and not hasattr(sys.modules["utils"], "__path__"):
+        del sys.modules["utils"]
+    spec = importlib.util.spec_from_file_location(
+        "wf_ref_scheduling_unipc", os.path.join(REF_WAN, "utils", "scheduling_unipc_multistep_clean.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
