@@ -1,0 +1,134 @@
+/* worldforge_b200 - C ABI of libwf_b200.so (sm_100a kernels for the WorldForge sampling hot path).
+ *
+ * The reference (Westlake-AGI-Lab/WorldForge) is 100% Python and has no FFI: its hot path sits
+ * behind duck-typed objects (pipe.transformer / pipe.vae / pipe.scheduler).  This
+ * header is therefore the boundary a maintainer would bind with ctypes from those objects; every
+ * entry point names the reference expression it replaces (paths relative to
+ * wan_for_worldforge/).  INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions: plain C, raw device pointers (tensor.data_ptr()), sizes in elements unless a name
+ * says bytes; every function returns 0 (WF_OK) or a negative WF_E* code and never throws; the
+ * message is available from wf_last_error() (thread-local).  All device work is asynchronous on
+ * the cudaStream_t passed as `stream` (0 = legacy default stream).  The library owns no memory:
+ * callers allocate inputs, outputs and the workspaces whose sizes the *_workspace_bytes functions
+ * report.  `*_bf16` / `is_bf16` flags say whether a buffer holds bf16 (1) or fp32 (0) elements.
+ */
+#ifndef WF_B200_H
+#define WF_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WF_ABI_VERSION 1
+
+#define WF_OK 0
+#define WF_EINVAL (-1) /* bad argument (shape, alignment, null pointer) */
+#define WF_ECUDA (-2)  /* CUDA runtime / driver error */
+
+const char* wf_last_error(void);
+int wf_abi_version(void);
+int wf_sm_count(void);
+
+/* ---- DiT tensor-core kernels (tcgen05 / TMEM / TMA) ------------------------------------------- */
+
+/* epilogues of wf_gemm_bf16 */
+#define WF_EPI_BF16 0        /* out bf16 [M,ldo]   = bf16(acc + bias)                                   */
+#define WF_EPI_GELU_BF16 1   /* out bf16           = bf16(gelu_tanh(bf16(acc + bias)))                  */
+#define WF_EPI_RESID_F32 2   /* out fp32 (in place) += float(bf16(acc + bias)) * gate[n]  (gate NULL: 1) */
+#define WF_EPI_F32_OF_BF16 3 /* out fp32           = float(bf16(acc + bias))                            */
+
+/* nn.Linear under autocast(bf16): out = a[M,K] . w[N,K]^T + bias, fused epilogue.
+ * Replaces every F.linear of WanAttentionBlock / text_embedding / img_emb / patch_embedding
+ * (wan/modules/model.py:123-126,197-198,271-273,456-460) together with the elementwise op that
+ * follows it (GELU :272; gated residual :306,:313; residual :310).
+ * a, w: bf16 row-major, K contiguous (lda, ldw in elements, multiples of 8); bias: bf16 [N] or NULL. */
+int wf_gemm_bf16(const void* a, int lda, const void* w, int ldw, const void* bias, void* out, int ldo,
+                 const float* gate, int M, int N, int K, int epilogue, void* stream);
+
+/* flash_attention(q, k, v) for head_dim 128, non-causal (wan/modules/attention.py:24-130; call sites
+ * model.py:149-154 self-attention, :220-222 cross-attention).  q [Lq, heads*128], k/v [Lk, heads*128],
+ * out [Lq, heads*128], all bf16 row-major with the given leading dimensions (multiples of 8).
+ * add_in (bf16, same shape as out, or NULL): out = bf16(float(bf16(attn)) + add_in), the
+ * "x = x + img_x" of WanI2VCrossAttention (model.py:227). */
+int wf_attention_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
+                      const void* add_in, int ld_add, int Lq, int Lk, int heads, float softmax_scale,
+                      void* stream);
+
+/* ---- DiT HBM-bound kernels ------------------------------------------------------------------------ */
+
+/* WanLayerNorm (+ modulation or affine), model.py:97-102 with :303/:311 (scale,shift = e[1],e[0] /
+ * e[4],e[3]) or norm3's weight,bias (:262-264).  round_norm_bf16 = 1 reproduces .type_as(x) for the
+ * bf16 token stream of block 0. */
+int wf_layer_norm(const void* x, int ldx, int x_is_bf16, void* out, int ldo, int out_is_bf16, const float* scale,
+                  const float* shift, const float* weight, const float* bias, int rows, int D, float eps,
+                  int round_norm_bf16, void* stream);
+
+/* WanRMSNorm over the full model dim (model.py:81-89) followed by rope_apply (:43-70), in place on a
+ * bf16 [rows, D] slice (leading dimension ldx).  rope: fp64 [rows, 64, 2] (cos, sin) per token and
+ * complex pair, or NULL for the cross-attention q/k, which carry no RoPE. */
+int wf_rms_norm_rope(void* x, int ldx, const float* weight, const double* rope, int rows, int D, float eps,
+                     void* stream);
+
+/* im2col of patch_embedding = Conv3d(k = s = (1,2,2)) (model.py:456-457,534-537):
+ * hidden bf16 [C,F,H,W] -> cols bf16 [F*(H/2)*(W/2), 4*C]. */
+int wf_patchify(const void* hidden, void* cols, int C, int F, int H, int W, void* stream);
+
+/* Head.forward + unpatchify (model.py:337-347, 584-607): fp32 LN, modulation, fp32 Linear(D -> 4*Cout),
+ * scatter to out fp32 [Cout, F, 2*GH, 2*GW]. */
+int wf_dit_head(const float* x, int ldx, int L, int D, const float* scale, const float* shift, const float* w,
+                const float* b, int Cout, float* out, int F, int GH, int GW, float eps, void* stream);
+
+/* fp32 matrix-vector product with optional SiLU on the input and/or output: the time_embedding /
+ * time_projection MLPs at batch 1 (model.py:546-550). */
+int wf_gemv_f32(const float* w, const float* x, const float* b, float* out, int N, int K, int silu_in,
+                int silu_out, void* stream);
+
+/* sinusoidal_embedding_1d (model.py:18-28) of the int64 timestep held on the device, float64 math: out fp32 [freq_dim] */
+int wf_time_sinusoid(const long long* timestep, float* out, int freq_dim, void* stream);
+
+/* out[r,:] = a[r,:] + b[:] - "self.modulation + e" for all blocks at once (model.py:298, 345) */
+int wf_add_bcast_f32(const float* a, const float* b, float* out, long long rows, int inner, void* stream);
+
+/* nn.GELU() (erf form) in place on bf16 - the MLPProj activation (model.py:355-358). */
+int wf_gelu_erf_bf16(void* x, long long n, void* stream);
+
+/* ---- WorldForge sampler ops (utils/pipeline_wan_i2v_clean.py, utils/scheduling_unipc_multistep_clean.py) */
+
+/* noise_pred + s*(noise_pred - noise_uncond), pipeline :611 */
+int wf_cfg_combine(const void* cond, const void* uncond, void* out, int is_bf16, float scale, long long n,
+                   void* stream);
+/* x0 = sample - sigma*model_output, scheduler :952-958; out dtype = bf16 iff both inputs are bf16 */
+int wf_x0_convert(const void* sample, int sample_bf16, const void* v, int v_bf16, void* out, float sigma,
+                  long long n, void* stream);
+/* multistep_uni_p_bh_update, scheduler :1084-1099, with the scalar coefficients evaluated by the host:
+ * c_x = sigma_t/sigma_s0, c_m0 = alpha_t*expm1(-h), rk = r_1, c_res = alpha_t*B_h; out has x's dtype. */
+int wf_unip_update(const void* x, int x_bf16, const void* m0, int m0_bf16, const void* m1, int m1_bf16, void* out,
+                   int order, float c_x, float c_m0, float rk, float c_res, long long n, void* stream);
+/* add_noise, scheduler :1584: out fp32 = (1-sigma)*x0 + sigma*noise, sigma held in x0's dtype */
+int wf_renoise(const void* x0, int x0_bf16, const float* noise, float* out, float one_minus_sigma, float sigma,
+               long long n, void* stream);
+/* DSG, pipeline :664-681: two passes (three reductions, then the guided combination).
+ * stats (device float[3], may be NULL) receives cos, sin, magnitude ratio. */
+long long wf_dsg_workspace_bytes(void);
+int wf_dsg(const void* g, const void* w, void* out, int is_bf16, float omega, long long n, void* workspace,
+           float* stats, void* stream);
+/* FLF pixel blend, scheduler :1375-1381: out = (2*ref-1)*mask + decoded*(1-mask); fp32;
+ * decoded/ref/out [channels, plane], mask [plane] broadcast over channels. */
+int wf_flf_blend(const float* decoded, const float* ref, const float* mask, float* out, int channels,
+                 long long plane, void* stream);
+/* scheduler :1281-1282: out fp32 = x0/inv_std + mean evaluated in x0's dtype ([channels, per_channel]) */
+int wf_latent_denorm(const void* x0, int is_bf16, float* out, const float* mean, const float* inv_std, int channels,
+                     long long per_channel, void* stream);
+/* scheduler :1385 + :1410-1417: out (x0's dtype) = replace_mask bit c ? x0[c] : (enc[c]-mean[c])*inv_std[c] */
+int wf_latent_norm_replace(const float* enc, const void* x0, int is_bf16, void* out, const float* mean,
+                           const float* inv_std, unsigned replace_mask, int channels, long long per_channel,
+                           void* stream);
+/* FLF scoring front end, scheduler :376-378 + :175-176: global min-max normalise, *255, truncate to uint8 */
+long long wf_quantise_workspace_bytes(void);
+int wf_quantise_u8(const void* x, int is_bf16, unsigned char* out, long long n, void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WF_B200_H */

@@ -1,0 +1,322 @@
+// worldforge_b200 - non-causal multi-head attention (head_dim 128) on tcgen05 / TMEM / TMA.
+//
+//   O[q, h, :] = softmax_k( Q[q,h,:] . K[k,h,:] / sqrt(128) ) V[k,h,:]
+//
+// This is flash_attention() of the reference (wan/modules/attention.py:24-130) for both call
+// sites of the Wan DiT block: the 3-D spatio-temporal self-attention (model.py:149-154;
+// Lq = Lk = 32 760 tokens at 480p/81f) and the text / image cross-attention (model.py:220-222;
+// Lk = 512 and 257).  bf16 q,k,v in, fp32 scores and softmax statistics, bf16 probabilities
+// into the PV product, fp32 accumulation, bf16 out.  ``add_in`` fuses the reference's
+// "x = x + img_x" (model.py:227): out = bf16(float(bf16(o)) + float(add_in)).
+//
+// Layout: q,k,v,out are the [tokens, heads*128] row-major matrices the q/k/v projections
+// produce - head h is the 128-column slice at h*128; nothing is transposed or re-packed.
+//
+// One CTA owns TWO 128-row query tiles of one head and walks the keys in blocks of 64:
+//   warp 0   TMA producer   (Q once; K/V blocks through a 4-stage mbarrier ring)
+//   warp 1   MMA issuer     S_t = Q_t K^T (128x64, K=128)  and  O_t += P_t V (128x128, K=64)
+//   warp 2   TMEM allocator (S_0,S_1: 64 columns each; O_0,O_1: 128 columns each)
+//   warps 4-7 / 8-11  softmax for tile 0 / tile 1: one thread per query row
+// The issuer alternates the two tiles so that while tile 0's rows are in softmax the tensor
+// core runs tile 1's MMAs (and vice versa).  V is consumed as an MN-major UMMA operand
+// straight from its TMA box; P goes through 128-byte-swizzled shared memory.  O stays in
+// TMEM for the whole key loop; it is rescaled there only when a row maximum grows by more
+// than 2^8 (lazy rescaling), so the common path never touches O.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace wf {
+
+constexpr int AT_BM = 128, AT_BN = 64, AT_D = 128, AT_STAGES = 4;
+constexpr int AT_Q_BYTES = AT_BM * AT_D * 2;    // 32 KB per query tile
+constexpr int AT_K_BYTES = AT_BN * AT_D * 2;    // 16 KB
+constexpr int AT_KV_BYTES = 2 * AT_K_BYTES;     // K + V of one stage
+constexpr int AT_P_BYTES = AT_BM * AT_BN * 2;   // 16 KB per query tile
+constexpr int AT_OFF_KV = 2 * AT_Q_BYTES;
+constexpr int AT_OFF_P = AT_OFF_KV + AT_STAGES * AT_KV_BYTES;
+constexpr int AT_OFF_BAR = AT_OFF_P + 2 * AT_P_BYTES;
+constexpr int AT_SMEM = AT_OFF_BAR + 256 + 1024;
+constexpr int AT_THREADS = 384;
+constexpr uint32_t AT_TMEM_S = 0, AT_TMEM_O = 128;
+constexpr float AT_RESCALE_THRESHOLD = 8.0f;
+
+struct AttnArgs {
+  int Lq, Lk;
+  bf16* out; int ldo;
+  const bf16* add_in; int ld_add;
+  float scale_log2;     // softmax scale * log2(e)
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attention_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, AttnArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_OFF_BAR);
+  uint64_t* q_full = bars;                 // 1
+  uint64_t* kv_full = bars + 1;            // AT_STAGES
+  uint64_t* kv_empty = kv_full + AT_STAGES;
+  uint64_t* s_full = kv_empty + AT_STAGES; // 2
+  uint64_t* p_full = s_full + 2;           // 2
+  uint64_t* o_done = p_full + 2;           // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int head = blockIdx.y;
+  const int q0 = blockIdx.x * (2 * AT_BM);
+  const int nblk = (p.Lk + AT_BN - 1) / AT_BN;
+  const int col0 = head * AT_D;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && elect_one()) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < AT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 4); mbar_init(&o_done[t], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, 2 * AT_Q_BYTES);
+      for (int t = 0; t < 2; ++t)
+        for (int half = 0; half < 2; ++half)
+          tma_load_2d(smem + t * AT_Q_BYTES + half * (AT_Q_BYTES / 2), &tmQ, q_full, col0 + half * 64, q0 + t * AT_BM);
+    }
+    __syncwarp();
+    for (int j = 0; j < nblk; ++j) {
+      const int stage = j % AT_STAGES;
+      const uint32_t phase = (j / AT_STAGES) & 1;
+      mbar_wait(&kv_empty[stage], phase ^ 1);
+      if (elect_one()) {
+        uint8_t* kdst = smem + AT_OFF_KV + stage * AT_KV_BYTES;
+        uint8_t* vdst = kdst + AT_K_BYTES;
+        mbar_arrive_expect_tx(&kv_full[stage], AT_KV_BYTES);
+        for (int half = 0; half < 2; ++half) {
+          tma_load_2d(kdst + half * (AT_K_BYTES / 2), &tmK, &kv_full[stage], col0 + half * 64, j * AT_BN);
+          tma_load_2d(vdst + half * (AT_K_BYTES / 2), &tmV, &kv_full[stage], col0 + half * 64, j * AT_BN);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc_s = umma_idesc(1, AT_BM, AT_BN, 0, 0);   // S = Q K^T : both K-major
+    constexpr uint32_t idesc_o = umma_idesc(1, AT_BM, AT_D, 0, 1);    // O += P V  : V is MN-major
+    const uint32_t q_addr = smem_u32(smem);
+    const uint32_t p_addr = smem_u32(smem + AT_OFF_P);
+    auto issue_s = [&](int t, int stage) {
+      const uint32_t k_addr = smem_u32(smem + AT_OFF_KV + stage * AT_KV_BYTES);
+#pragma unroll
+      for (int ks = 0; ks < AT_D / 16; ++ks) {
+        uint64_t da = umma_desc_sw128(q_addr + t * AT_Q_BYTES + (ks >> 2) * (AT_Q_BYTES / 2) + (ks & 3) * 32, 16, 1024);
+        uint64_t db = umma_desc_sw128(k_addr + (ks >> 2) * (AT_K_BYTES / 2) + (ks & 3) * 32, 16, 1024);
+        umma_f16_ss(tmem_base + AT_TMEM_S + t * AT_BN, da, db, idesc_s, ks != 0);
+      }
+      umma_commit(&s_full[t]);
+    };
+    auto issue_pv = [&](int t, int stage, int j) {
+      const uint32_t v_addr = smem_u32(smem + AT_OFF_KV + stage * AT_KV_BYTES + AT_K_BYTES);
+#pragma unroll
+      for (int ks = 0; ks < AT_BN / 16; ++ks) {
+        uint64_t da = umma_desc_sw128(p_addr + t * AT_P_BYTES + ks * 32, 16, 1024);
+        uint64_t db = umma_desc_sw128(v_addr + ks * 2048, AT_K_BYTES / 2, 1024);
+        umma_f16_ss(tmem_base + AT_TMEM_O + t * AT_D, da, db, idesc_o, (j | ks) != 0);
+      }
+      umma_commit(&o_done[t]);
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    if (elect_one()) { issue_s(0, 0); issue_s(1, 0); }
+    __syncwarp();
+    for (int j = 0; j < nblk; ++j) {
+      const int stage = j % AT_STAGES;
+      const int nstage = (j + 1) % AT_STAGES;
+      const bool more = (j + 1 < nblk);
+      if (more) mbar_wait(&kv_full[nstage], ((j + 1) / AT_STAGES) & 1);
+      mbar_wait(&p_full[0], j & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        issue_pv(0, stage, j);
+        if (more) issue_s(0, nstage);
+      }
+      __syncwarp();
+      mbar_wait(&p_full[1], j & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        issue_pv(1, stage, j);
+        umma_commit(&kv_empty[stage]);      // both tiles have consumed this K/V block
+        if (more) issue_s(1, nstage);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ softmax + epilogue
+    const int t = (warp - 4) >> 2;          // which query tile
+    const int qd = warp & 3;                // TMEM lane quarter
+    const int row = qd * 32 + lane_id();    // row within the tile
+    const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t s_tmem = tmem_base + lane_addr + AT_TMEM_S + t * AT_BN;
+    const uint32_t o_tmem = tmem_base + lane_addr + AT_TMEM_O + t * AT_D;
+    uint8_t* p_row = smem + AT_OFF_P + t * AT_P_BYTES + row * 128;
+    float m_ref = 0.f, l = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32b_x32(s_tmem, r0);
+      tmem_ld_32x32b_x32(s_tmem + 32, r1);
+      tmem_ld_wait();
+      float s[64];
+      const int valid = p.Lk - j * AT_BN;   // keys of this block that exist
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        s[c] = __uint_as_float(r0[c]) * p.scale_log2;
+        s[c + 32] = __uint_as_float(r1[c]) * p.scale_log2;
+      }
+      if (valid < AT_BN) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) if (c >= valid) s[c] = -INFINITY;
+      }
+      float m_blk = s[0];
+#pragma unroll
+      for (int c = 1; c < 64; ++c) m_blk = fmaxf(m_blk, s[c]);
+      float alpha = 1.0f;
+      bool grow = false;
+      if (j == 0) {
+        m_ref = m_blk;
+      } else if (m_blk - m_ref > AT_RESCALE_THRESHOLD) {
+        alpha = ex2(m_ref - m_blk);
+        m_ref = m_blk;
+        grow = true;
+      }
+      float sum = 0.f;
+      uint32_t pk[32];
+#pragma unroll
+      for (int c = 0; c < 64; c += 2) {
+        float e0 = ex2(s[c] - m_ref), e1 = ex2(s[c + 1] - m_ref);
+        sum += e0 + e1;
+        pk[c >> 1] = pack_bf16x2(e0, e1);
+      }
+      l = l * alpha + sum;
+      // P_t smem and O_t TMEM are free once PV_t(j-1) has retired
+      if (j > 0) {
+        mbar_wait(&o_done[t], (j - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll 1
+          for (int c = 0; c < AT_D; c += 32) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(o_tmem + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x32(o_tmem + c, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      // row-major 128-byte rows, 16-byte chunks XOR-swizzled by (row & 7): the SWIZZLE_128B K-major layout
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        uint4 v = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+        *reinterpret_cast<uint4*>(p_row + ((ch ^ (row & 7)) << 4)) = v;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&p_full[t]);
+    }
+    // epilogue: O / l -> bf16 -> global
+    mbar_wait(&o_done[t], (nblk - 1) & 1);
+    tc_fence_after();
+    const int q = q0 + t * AT_BM + row;
+    const float inv_l = 1.0f / l;
+#pragma unroll 1
+    for (int c = 0; c < AT_D; c += 32) {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(o_tmem + c, o);
+      tmem_ld_wait();
+      if (q < p.Lq) {
+        bf16* dst = p.out + static_cast<size_t>(q) * p.ldo + col0 + c;
+        const bf16* add = p.add_in ? p.add_in + static_cast<size_t>(q) * p.ld_add + col0 + c : nullptr;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          float w[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) w[u] = __uint_as_float(o[i + u]) * inv_l;
+          if (add) {
+            uint4 a = *reinterpret_cast<const uint4*>(add + i);
+            const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float2 f = __bfloat1622float2(a2[u]);
+              w[2 * u] = __fadd_rn(bf16_round(w[2 * u]), f.x);
+              w[2 * u + 1] = __fadd_rn(bf16_round(w[2 * u + 1]), f.y);
+            }
+          }
+          uint4 v = make_uint4(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]), pack_bf16x2(w[4], w[5]),
+                               pack_bf16x2(w[6], w[7]));
+          *reinterpret_cast<uint4*>(dst + i) = v;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace wf
+
+extern "C" int wf_attention_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out,
+                                 int ldo, const void* add_in, int ld_add, int Lq, int Lk, int heads,
+                                 float softmax_scale, void* stream) {
+  using namespace wf;
+  WF_REQUIRE(q && k && v && out, "wf_attention_bf16: null pointer");
+  WF_REQUIRE(Lq > 0 && Lk > 0 && heads > 0, "wf_attention_bf16: empty problem");
+  WF_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && ld_add % 8 == 0,
+             "wf_attention_bf16: leading dimensions must be multiples of 8");
+  WF_REQUIRE(ldq >= heads * AT_D && ldk >= heads * AT_D && ldv >= heads * AT_D && ldo >= heads * AT_D,
+             "wf_attention_bf16: leading dimension smaller than heads*128");
+  CUtensorMap tmQ, tmK, tmV;
+  auto mk = [&](CUtensorMap* m, const void* base, int ld, int rows, uint32_t box_rows) {
+    uint64_t dims[2] = {static_cast<uint64_t>(heads) * AT_D, static_cast<uint64_t>(rows)};
+    uint64_t strides[1] = {static_cast<uint64_t>(ld) * 2};
+    uint32_t box[2] = {64, box_rows};
+    return make_tmap(m, base, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  };
+  int rc;
+  if ((rc = mk(&tmQ, q, ldq, Lq, AT_BM))) return rc;
+  if ((rc = mk(&tmK, k, ldk, Lk, AT_BN))) return rc;
+  if ((rc = mk(&tmV, v, ldv, Lk, AT_BN))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    WF_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    attr_set = true;
+  }
+  AttnArgs args{Lq, Lk, static_cast<bf16*>(out), ldo, static_cast<const bf16*>(add_in), ld_add,
+                softmax_scale * 1.4426950408889634f};
+  dim3 grid((Lq + 2 * AT_BM - 1) / (2 * AT_BM), heads);
+  attention_tcgen05<<<grid, AT_THREADS, AT_SMEM, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, args);
+  WF_LAUNCH_OK();
+  return WF_OK;
+}

@@ -1,0 +1,401 @@
+// worldforge_b200 - the HBM-bound kernels around the tensor-core GEMMs / attention of the Wan DiT block.
+//
+// Each kernel is one fused pass over a [tokens, dim] activation; the reference spends ~10
+// separate elementwise passes per block on these.  Rounding points follow
+// wan/modules/model.py so results match the oracle value for value:
+//   layer-norm + modulate   norm1/norm2: LN(x.float()).type_as(x).float()*(1+e_scale)+e_shift  (:303,:311)
+//                           norm3:       LN with affine weight/bias                             (:262-264,:310)
+//   rms-norm + RoPE         (x.float()*rsqrt(mean(x^2)+eps)).type_as(x) * w                     (:86-89)
+//                           complex rotation in float64, rounded to fp32                        (:55-70)
+//   patchify                Conv3d(k=s=(1,2,2)) written as im2col rows for the GEMM             (:534-537)
+//   head                    LN, modulate, fp32 Linear(dim -> 64), un-patchify                   (:337-347, :600-607)
+//   gemv (fp32)             the time-embedding MLPs, batch 1, fp32 weights                      (:546-550)
+#include <algorithm>
+
+#include "common.cuh"
+#include "host_util.h"
+
+namespace wf {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int THREADS>
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (threadIdx.x < THREADS / 32) ? red[threadIdx.x] : 0.f;
+  if (w == 0) {
+    t = warp_sum(t);
+    if (l == 0) red[0] = t;
+  }
+  __syncthreads();
+  return red[0];
+}
+
+// ------------------------------------------------------------------ layer norm (+ modulate / affine)
+constexpr int LN_THREADS = 256;
+constexpr int LN_MAXV = 8;   // float4 per thread cached in registers: dim <= 8192
+
+struct LnArgs {
+  const void* x; int ldx; int x_is_bf16;
+  void* out; int ldo; int out_is_bf16;
+  const float* scale;   // modulate: y*(1+scale)+shift ; may be null
+  const float* shift;
+  const float* weight;  // affine:   y*weight+bias      ; may be null
+  const float* bias;
+  int D; float eps; int round_norm_bf16;
+};
+
+__global__ void __launch_bounds__(LN_THREADS) layer_norm_kernel(LnArgs p) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  const int nvec = p.D >> 2;
+  float4 v[LN_MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int idx = threadIdx.x + i * LN_THREADS;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (idx < nvec) {
+      if (p.x_is_bf16) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(static_cast<const bf16*>(p.x) + static_cast<size_t>(row) * p.ldx + idx * 4);
+        float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+        float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+        v[i] = make_float4(a.x, a.y, b.x, b.y);
+      } else {
+        v[i] = *reinterpret_cast<const float4*>(static_cast<const float*>(p.x) + static_cast<size_t>(row) * p.ldx + idx * 4);
+      }
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = block_sum<LN_THREADS>(sum, red) / p.D;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int idx = threadIdx.x + i * LN_THREADS;
+    if (idx < nvec) {
+      float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(block_sum<LN_THREADS>(sq, red) / p.D + p.eps);
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int idx = threadIdx.x + i * LN_THREADS;
+    if (idx < nvec) {
+      float y[4] = {(v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd, (v[i].w - mean) * rstd};
+      const int c = idx * 4;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (p.weight) y[u] = y[u] * p.weight[c + u] + p.bias[c + u];
+        if (p.round_norm_bf16) y[u] = bf16_round(y[u]);
+        if (p.scale) y[u] = __fadd_rn(__fmul_rn(y[u], __fadd_rn(1.0f, p.scale[c + u])), p.shift[c + u]);
+      }
+      if (p.out_is_bf16) {
+        uint2 o = make_uint2(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]));
+        *reinterpret_cast<uint2*>(static_cast<bf16*>(p.out) + static_cast<size_t>(row) * p.ldo + c) = o;
+      } else {
+        *reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + c) = make_float4(y[0], y[1], y[2], y[3]);
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------- rms norm (+ RoPE)
+constexpr int RMS_THREADS = 256;
+constexpr int RMS_MAXV = 4;   // 8 bf16 per vector: dim <= 8192
+
+struct RmsArgs {
+  bf16* x; int ldx;             // in place: [rows, D] slice of a wider matrix
+  const float* weight;          // [D]
+  const double* rope;           // [rows, 64, 2] (cos, sin) per token and complex pair, or null
+  int D; float eps;
+};
+
+__global__ void __launch_bounds__(RMS_THREADS) rms_norm_rope_kernel(RmsArgs p) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  const int nvec = p.D >> 3;
+  bf16* xr = p.x + static_cast<size_t>(row) * p.ldx;
+  uint4 raw[RMS_MAXV];
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < RMS_MAXV; ++i) {
+    const int idx = threadIdx.x + i * RMS_THREADS;
+    if (idx < nvec) {
+      raw[i] = *reinterpret_cast<const uint4*>(xr + idx * 8);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float2 f = __bfloat1622float2(h[u]);
+        sq += f.x * f.x + f.y * f.y;
+      }
+    }
+  }
+  const float rstd = rsqrtf(block_sum<RMS_THREADS>(sq, red) / p.D + p.eps);
+#pragma unroll
+  for (int i = 0; i < RMS_MAXV; ++i) {
+    const int idx = threadIdx.x + i * RMS_THREADS;
+    if (idx < nvec) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
+      const int c = idx * 8;
+      uint32_t o[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float2 f = __bfloat1622float2(h[u]);
+        // (x.float() * rstd).type_as(x) * weight
+        float a = __fmul_rn(bf16_round(__fmul_rn(f.x, rstd)), p.weight[c + 2 * u]);
+        float b = __fmul_rn(bf16_round(__fmul_rn(f.y, rstd)), p.weight[c + 2 * u + 1]);
+        if (p.rope) {
+          const int pair = ((c + 2 * u) & 127) >> 1;                 // complex pair index inside the head
+          const double2 cs = *reinterpret_cast<const double2*>(p.rope + (static_cast<size_t>(row) * 64 + pair) * 2);
+          const double da = a, db = b;
+          const float re = static_cast<float>(da * cs.x - db * cs.y);
+          const float im = static_cast<float>(da * cs.y + db * cs.x);
+          a = re; b = im;
+        }
+        o[u] = pack_bf16x2(a, b);
+      }
+      *reinterpret_cast<uint4*>(xr + c) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------- patchify
+// hidden [C, F, H, W] bf16 -> rows [F*(H/2)*(W/2), C*4] bf16, column = c*4 + ph*2 + pw
+__global__ void patchify_kernel(const bf16* __restrict__ x, bf16* __restrict__ cols, int C, int F, int H, int W) {
+  const int gh = H >> 1, gw = W >> 1;
+  const size_t total = static_cast<size_t>(F) * gh * gw * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const size_t tok = i / C;
+    const int w = static_cast<int>(tok % gw), h = static_cast<int>((tok / gw) % gh), f = static_cast<int>(tok / (static_cast<size_t>(gw) * gh));
+    const bf16* src = x + ((static_cast<size_t>(c) * F + f) * H + 2 * h) * W + 2 * w;
+    const __nv_bfloat162 top = *reinterpret_cast<const __nv_bfloat162*>(src);
+    const __nv_bfloat162 bot = *reinterpret_cast<const __nv_bfloat162*>(src + W);
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&top);
+    o.y = *reinterpret_cast<const uint32_t*>(&bot);
+    *reinterpret_cast<uint2*>(cols + tok * (static_cast<size_t>(C) * 4) + c * 4) = o;
+  }
+}
+
+// --------------------------------------------------------------------------------------- head
+// out[c, f, 2h+ph, 2w+pw] = sum_k W[(ph*2+pw)*Cout + c, k] * mod(LN(x[tok,:]))[k] + b
+constexpr int HEAD_THREADS = 256;
+constexpr int HEAD_TOK = 4;
+
+struct HeadArgs {
+  const float* x; int ldx; int L; int D;
+  const float* scale; const float* shift;   // [D]
+  const float* w; const float* b;           // [NO, D], [NO]
+  int NO;                                   // 4 * Cout
+  float* out; int Cout, F, GH, GW;          // out [Cout, F, 2*GH, 2*GW]
+  float eps;
+};
+
+__global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadArgs p) {
+  extern __shared__ float sh[];             // HEAD_TOK * D normalised + modulated rows
+  __shared__ float red[32];
+  const int tok0 = blockIdx.x * HEAD_TOK;
+  for (int t = 0; t < HEAD_TOK; ++t) {
+    const int tok = tok0 + t;
+    float* row = sh + t * p.D;
+    if (tok >= p.L) { for (int i = threadIdx.x; i < p.D; i += HEAD_THREADS) row[i] = 0.f; continue; }
+    const float* xr = p.x + static_cast<size_t>(tok) * p.ldx;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < p.D; i += HEAD_THREADS) { float v = xr[i]; row[i] = v; s += v; }
+    const float mean = block_sum<HEAD_THREADS>(s, red) / p.D;
+    float sq = 0.f;
+    for (int i = threadIdx.x; i < p.D; i += HEAD_THREADS) { float d = row[i] - mean; sq += d * d; }
+    const float rstd = rsqrtf(block_sum<HEAD_THREADS>(sq, red) / p.D + p.eps);
+    for (int i = threadIdx.x; i < p.D; i += HEAD_THREADS) {
+      float y = (row[i] - mean) * rstd;
+      row[i] = __fadd_rn(__fmul_rn(y, __fadd_rn(1.0f, p.scale[i])), p.shift[i]);
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int o = warp; o < p.NO; o += HEAD_THREADS / 32) {
+    const float* wr = p.w + static_cast<size_t>(o) * p.D;
+    float acc[HEAD_TOK];
+#pragma unroll
+    for (int t = 0; t < HEAD_TOK; ++t) acc[t] = 0.f;
+    for (int k = lane * 4; k < p.D; k += 128) {
+      const float4 wv = *reinterpret_cast<const float4*>(wr + k);
+#pragma unroll
+      for (int t = 0; t < HEAD_TOK; ++t) {
+        const float4 xv = *reinterpret_cast<const float4*>(sh + t * p.D + k);
+        acc[t] += wv.x * xv.x + wv.y * xv.y + wv.z * xv.z + wv.w * xv.w;
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < HEAD_TOK; ++t) {
+      float v = warp_sum(acc[t]);
+      const int tok = tok0 + t;
+      if (lane == 0 && tok < p.L) {
+        v += p.b[o];
+        const int c = o % p.Cout, pq = o / p.Cout, ph = pq >> 1, pw = pq & 1;
+        const int gw = tok % p.GW, gh = (tok / p.GW) % p.GH, f = tok / (p.GW * p.GH);
+        p.out[((static_cast<size_t>(c) * p.F + f) * (2 * p.GH) + 2 * gh + ph) * (2 * p.GW) + 2 * gw + pw] = v;
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------- fp32 GEMV
+// out[n] = act_out( sum_k W[n,k] * act_in(x[k]) + b[n] );  act: 0 none, 1 SiLU
+__global__ void __launch_bounds__(256) gemv_f32_kernel(const float* __restrict__ w, const float* __restrict__ x,
+                                                       const float* __restrict__ b, float* __restrict__ out, int N,
+                                                       int K, int silu_in, int silu_out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  const float* wr = w + static_cast<size_t>(warp) * K;
+  float acc = 0.f;
+  for (int k = lane * 4; k < K; k += 128) {
+    const float4 wv = *reinterpret_cast<const float4*>(wr + k);
+    float4 xv = *reinterpret_cast<const float4*>(x + k);
+    if (silu_in) {
+      xv.x = xv.x / (1.0f + expf(-xv.x)); xv.y = xv.y / (1.0f + expf(-xv.y));
+      xv.z = xv.z / (1.0f + expf(-xv.z)); xv.w = xv.w / (1.0f + expf(-xv.w));
+    }
+    acc += wv.x * xv.x + wv.y * xv.y + wv.z * xv.z + wv.w * xv.w;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    float v = acc + (b ? b[warp] : 0.f);
+    if (silu_out) v = v / (1.0f + expf(-v));
+    out[warp] = v;
+  }
+}
+
+// ------------------------------------------------------------- bf16 elementwise GELU (erf form)
+__global__ void gelu_erf_bf16_kernel(bf16* x, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float v = __bfloat162float(x[i]);
+    x[i] = __float2bfloat16_rn(0.5f * v * (1.0f + erff(v * 0.7071067811865476f)));
+  }
+}
+
+
+// ------------------------------------------------- sinusoidal timestep embedding (model.py:18-28)
+// out[0:half] = cos(t * 10000^(-i/half)), out[half:] = sin(...), evaluated in float64 like the reference
+__global__ void time_sinusoid_kernel(const long long* __restrict__ t, float* __restrict__ out, int half) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= half) return;
+  const double pos = static_cast<double>(t[0]);
+  const double ang = pos * pow(10000.0, -static_cast<double>(i) / half);
+  out[i] = static_cast<float>(cos(ang));
+  out[half + i] = static_cast<float>(sin(ang));
+}
+
+// out[r, :] = a[r, :] + b[:]  (modulation tables + time projection, model.py:298,345)
+__global__ void add_bcast_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                                     size_t rows, int inner) {
+  const size_t total = rows * inner;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    out[i] = __fadd_rn(a[i], b[i % inner]);
+}
+
+}  // namespace wf
+
+using namespace wf;
+
+extern "C" int wf_layer_norm(const void* x, int ldx, int x_is_bf16, void* out, int ldo, int out_is_bf16,
+                             const float* scale, const float* shift, const float* weight, const float* bias,
+                             int rows, int D, float eps, int round_norm_bf16, void* stream) {
+  WF_REQUIRE(x && out && rows > 0, "wf_layer_norm: bad arguments");
+  WF_REQUIRE(D % 4 == 0 && D <= 4 * LN_THREADS * LN_MAXV, "wf_layer_norm: dim must be a multiple of 4 and <= 8192");
+  WF_REQUIRE(ldx % 4 == 0 && ldo % 4 == 0, "wf_layer_norm: leading dimensions must be multiples of 4");
+  WF_REQUIRE((scale == nullptr) == (shift == nullptr) && (weight == nullptr) == (bias == nullptr),
+             "wf_layer_norm: scale/shift and weight/bias come in pairs");
+  LnArgs a{x, ldx, x_is_bf16, out, ldo, out_is_bf16, scale, shift, weight, bias, D, eps, round_norm_bf16};
+  layer_norm_kernel<<<rows, LN_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  WF_LAUNCH_OK();
+  return WF_OK;
+}
+
+extern "C" int wf_rms_norm_rope(void* x, int ldx, const float* weight, const double* rope, int rows, int D, float eps,
+                                void* stream) {
+  WF_REQUIRE(x && weight && rows > 0, "wf_rms_norm_rope: bad arguments");
+  WF_REQUIRE(D % 8 == 0 && D <= 8 * RMS_THREADS * RMS_MAXV && ldx % 8 == 0, "wf_rms_norm_rope: dim must be a multiple of 8 and <= 8192");
+  WF_REQUIRE(rope == nullptr || D % 128 == 0, "wf_rms_norm_rope: RoPE needs head_dim 128");
+  RmsArgs a{static_cast<bf16*>(x), ldx, weight, rope, D, eps};
+  rms_norm_rope_kernel<<<rows, RMS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  WF_LAUNCH_OK();
+  return WF_OK;
+}
+
+extern "C" int wf_patchify(const void* hidden, void* cols, int C, int F, int H, int W, void* stream) {
+  WF_REQUIRE(hidden && cols && C > 0 && F > 0, "wf_patchify: bad arguments");
+  WF_REQUIRE(H % 2 == 0 && W % 2 == 0, "wf_patchify: H and W must be even (patch 1x2x2)");
+  const size_t total = static_cast<size_t>(F) * (H / 2) * (W / 2) * C;
+  const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(sm_count()) * 16));
+  patchify_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(hidden),
+                                                                         static_cast<bf16*>(cols), C, F, H, W);
+  WF_LAUNCH_OK();
+  return WF_OK;
+}
+
+extern "C" int wf_dit_head(const float* x, int ldx, int L, int D, const float* scale, const float* shift,
+                           const float* w, const float* b, int Cout, float* out, int F, int GH, int GW, float eps,
+                           void* stream) {
+  WF_REQUIRE(x && scale && shift && w && b && out, "wf_dit_head: null pointer");
+  WF_REQUIRE(L == F * GH * GW, "wf_dit_head: token count does not match the grid");
+  WF_REQUIRE(D % 128 == 0 && ldx % 4 == 0, "wf_dit_head: dim must be a multiple of 128");
+  HeadArgs a{x, ldx, L, D, scale, shift, w, b, 4 * Cout, out, Cout, F, GH, GW, eps};
+  const size_t shmem = static_cast<size_t>(HEAD_TOK) * D * sizeof(float);
+  static size_t configured = 0;
+  if (shmem > configured) {
+    WF_CUDA_OK(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shmem)));
+    configured = shmem;
+  }
+  head_kernel<<<(L + HEAD_TOK - 1) / HEAD_TOK, HEAD_THREADS, shmem, static_cast<cudaStream_t>(stream)>>>(a);
+  WF_LAUNCH_OK();
+  return WF_OK;
+}
+
+extern "C" int wf_gemv_f32(const float* w, const float* x, const float* b, float* out, int N, int K, int silu_in,
+                           int silu_out, void* stream) {
+  WF_REQUIRE(w && x && out && N > 0, "wf_gemv_f32: bad arguments");
+  WF_REQUIRE(K % 4 == 0, "wf_gemv_f32: K must be a multiple of 4");
+  const int blocks = (N * 32 + 255) / 256;
+  gemv_f32_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, x, b, out, N, K, silu_in, silu_out);
+  WF_LAUNCH_OK();
+  return WF_OK;
+}
+
+extern "C" int wf_gelu_erf_bf16(void* x, long long n, void* stream) {
+  WF_REQUIRE(x && n > 0, "wf_gelu_erf_bf16: bad arguments");
+  const int blocks = static_cast<int>(std::min<long long>((n + 255) / 256, static_cast<long long>(sm_count()) * 8));
+  gelu_erf_bf16_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<bf16*>(x), static_cast<size_t>(n));
+  WF_LAUNCH_OK();
+  return WF_OK;
+}
+
+extern "C" int wf_time_sinusoid(const long long* timestep, float* out, int freq_dim, void* stream) {
+  WF_REQUIRE(timestep && out && freq_dim > 0 && freq_dim % 2 == 0, "wf_time_sinusoid: bad arguments");
+  const int half = freq_dim / 2;
+  time_sinusoid_kernel<<<(half + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(timestep, out, half);
+  WF_LAUNCH_OK();
+  return WF_OK;
+}
+
+extern "C" int wf_add_bcast_f32(const float* a, const float* b, float* out, long long rows, int inner, void* stream) {
+  WF_REQUIRE(a && b && out && rows > 0 && inner > 0, "wf_add_bcast_f32: bad arguments");
+  const long long total = rows * inner;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(sm_count()) * 8));
+  add_bcast_f32_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, out, static_cast<size_t>(rows), inner);
+  WF_LAUNCH_OK();
+  return WF_OK;
+}

@@ -1,0 +1,250 @@
+// worldforge_b200 - bf16 GEMM on the 5th-gen tensor cores (tcgen05 + TMEM + TMA).
+//
+//   C[M,N] = A[M,K] * W[N,K]^T (+ bias[N]) with a fused epilogue.
+//
+// This is every nn.Linear of the Wan DiT block (reference wan/modules/model.py:123-126,
+// 197-198, 271-273) under autocast(bf16): bf16 operands, fp32 accumulation in TMEM, one
+// rounding to bf16, then the epilogue the block applies to that value:
+//   EPI_BF16       y = bf16(acc + b)                                   (q,k,v, cross q, text/img embeds)
+//   EPI_GELU_BF16  y = bf16(gelu_tanh(bf16(acc + b)))                  (ffn.0 + nn.GELU('tanh'), :272)
+//   EPI_RESID_F32  x[m,n] += float(bf16(acc + b)) * gate[n]            (x + y*e, :306,:313; gate==null -> x + y, :310)
+//   EPI_F32_OF_BF16 y = float(bf16(acc + b))                           (patch embedding, :534)
+//
+// Layout: A row-major [M,K] (K contiguous) and W row-major [N,K] - nn.Linear's native
+// layout - are both "K-major" UMMA operands, so no transposes exist anywhere.
+// Persistent, warp-specialised CTA (one per SM): warp 0 TMA producer, warp 1 MMA issuer
+// (one elected lane), warp 2 TMEM allocator, warps 4-7 epilogue.  128x256 output tile,
+// 64-wide K blocks in 128-byte-swizzled smem, 4-stage mbarrier ring, two 256-column TMEM
+// accumulators so tile i's epilogue overlaps tile i+1's main loop.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace wf {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BN = 256;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KB
+constexpr int GEMM_B_BYTES = GEMM_BN * GEMM_BK * 2;   // 32 KB
+constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
+constexpr int GEMM_SMEM = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int GEMM_THREADS = 256;
+
+enum { EPI_BF16 = 0, EPI_GELU_BF16 = 1, EPI_RESID_F32 = 2, EPI_F32_OF_BF16 = 3 };
+
+struct GemmArgs {
+  int M, N, K;
+  const bf16* bias;    // [N] or null
+  void* out;           // bf16 [M,ldo] or float [M,ldo]
+  int ldo;
+  const float* gate;   // [N] or null (EPI_RESID_F32)
+};
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float inner = k0 * (x + k1 * x * x * x);
+  return 0.5f * x * (1.0f + tanhf(inner));
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + GEMM_STAGES * GEMM_STAGE_BYTES);
+  uint64_t* empty = full + GEMM_STAGES;
+  uint64_t* acc_full = empty + GEMM_STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int tiles_n = (p.N + GEMM_BN - 1) / GEMM_BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * GEMM_BM, n0 = (tile % tiles_n) * GEMM_BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          uint8_t* a_dst = smem + stage * GEMM_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[stage], GEMM_STAGE_BYTES);
+          tma_load_2d(a_dst, &tmA, &full[stage], kb * GEMM_BK, m0);
+          tma_load_2d(a_dst + GEMM_A_BYTES, &tmB, &full[stage], kb * GEMM_BK, n0);
+        }
+        __syncwarp();
+        if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc = umma_idesc(1, GEMM_BM, GEMM_BN, 0, 0);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * GEMM_BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(smem + stage * GEMM_STAGE_BYTES);
+          const uint32_t b_addr = a_addr + GEMM_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
+            uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_f16_ss(d_tmem, da, db, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty[stage]);                       // smem slot free once these MMAs retire
+          if (kb == num_kb - 1) umma_commit(&acc_full[acc]); // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int row_in_tile = q * 32 + lane_id();
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * GEMM_BM, n0 = (tile % tiles_n) * GEMM_BN;
+      const int m = m0 + row_in_tile;
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * GEMM_BN;
+#pragma unroll 1
+      for (int c = 0; c < GEMM_BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + c, r);
+        tmem_ld_wait();
+        const int n = n0 + c;
+        if (m < p.M && n < p.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float b = p.bias ? __bfloat162float(p.bias[n + j]) : 0.0f;
+            v[j] = bf16_round(__uint_as_float(r[j]) + b);
+          }
+          if (EPI == EPI_BF16 || EPI == EPI_GELU_BF16) {
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + static_cast<size_t>(m) * p.ldo + n);
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float w[8];
+#pragma unroll
+              for (int t = 0; t < 8; ++t) w[t] = (EPI == EPI_GELU_BF16) ? gelu_tanh_f(v[j + t]) : v[j + t];
+              uint4 o;
+              o.x = pack_bf16x2(w[0], w[1]); o.y = pack_bf16x2(w[2], w[3]);
+              o.z = pack_bf16x2(w[4], w[5]); o.w = pack_bf16x2(w[6], w[7]);
+              dst[j / 8] = o;
+            }
+          } else {
+            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(m) * p.ldo + n);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o;
+              if (EPI == EPI_RESID_F32) {
+                float4 x = dst[j / 4];
+                float g0 = 1.f, g1 = 1.f, g2 = 1.f, g3 = 1.f;
+                if (p.gate) { g0 = p.gate[n + j]; g1 = p.gate[n + j + 1]; g2 = p.gate[n + j + 2]; g3 = p.gate[n + j + 3]; }
+                // x + y*e: two separately rounded fp32 ops, as torch evaluates them
+                o.x = __fadd_rn(x.x, __fmul_rn(v[j], g0)); o.y = __fadd_rn(x.y, __fmul_rn(v[j + 1], g1));
+                o.z = __fadd_rn(x.z, __fmul_rn(v[j + 2], g2)); o.w = __fadd_rn(x.w, __fmul_rn(v[j + 3], g3));
+              } else {
+                o.x = v[j]; o.y = v[j + 1]; o.z = v[j + 2]; o.w = v[j + 3];
+              }
+              dst[j / 4] = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int EPI>
+static int launch_gemm(const void* A, int lda, const void* W, int ldw, const GemmArgs& args, cudaStream_t stream) {
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(args.K), static_cast<uint64_t>(args.M)};
+    uint64_t strides[1] = {static_cast<uint64_t>(lda) * 2};
+    uint32_t box[2] = {GEMM_BK, GEMM_BM};
+    int rc = make_tmap(&tmA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(args.K), static_cast<uint64_t>(args.N)};
+    uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
+    uint32_t box[2] = {GEMM_BK, GEMM_BN};
+    int rc = make_tmap(&tmB, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    WF_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    attr_set = true;
+  }
+  const int tiles = ((args.M + GEMM_BM - 1) / GEMM_BM) * ((args.N + GEMM_BN - 1) / GEMM_BN);
+  int grid = sm_count();
+  if (grid > tiles) grid = tiles;
+  gemm_bf16_tcgen05<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(tmA, tmB, args);
+  WF_LAUNCH_OK();
+  return WF_OK;
+}
+
+}  // namespace wf
+
+extern "C" int wf_gemm_bf16(const void* a, int lda, const void* w, int ldw, const void* bias, void* out, int ldo,
+                            const float* gate, int M, int N, int K, int epilogue, void* stream) {
+  using namespace wf;
+  WF_REQUIRE(a && w && out, "wf_gemm_bf16: null pointer");
+  WF_REQUIRE(M > 0 && N > 0 && K > 0, "wf_gemm_bf16: empty problem");
+  WF_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "wf_gemm_bf16: K, lda, ldw must be multiples of 8 (16-byte TMA rows)");
+  WF_REQUIRE(N % 32 == 0, "wf_gemm_bf16: N must be a multiple of 32");
+  WF_REQUIRE(ldo % 8 == 0, "wf_gemm_bf16: ldo must be a multiple of 8");
+  WF_REQUIRE((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(out)) % 16 == 0,
+             "wf_gemm_bf16: pointers must be 16-byte aligned");
+  GemmArgs args{M, N, K, static_cast<const bf16*>(bias), out, ldo, gate};
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (epilogue) {
+    case EPI_BF16: return launch_gemm<EPI_BF16>(a, lda, w, ldw, args, s);
+    case EPI_GELU_BF16: return launch_gemm<EPI_GELU_BF16>(a, lda, w, ldw, args, s);
+    case EPI_RESID_F32: return launch_gemm<EPI_RESID_F32>(a, lda, w, ldw, args, s);
+    case EPI_F32_OF_BF16: return launch_gemm<EPI_F32_OF_BF16>(a, lda, w, ldw, args, s);
+  }
+  return fail(WF_EINVAL, "wf_gemm_bf16: unknown epilogue");
+}

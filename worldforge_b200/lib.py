@@ -1,0 +1,310 @@
+"""ctypes binding of libwf_b200.so (include/wf_b200.h) over torch tensors.
+
+PyTorch is used here only for device memory and streams: every function takes CUDA tensors,
+passes ``data_ptr()`` and the current stream to the C ABI, and raises ``WfError`` when the
+library reports a failure.  There is no CPU or PyTorch fallback: if the shared library is
+missing or the tensors are not on a CUDA device the call fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwf_b200.so")
+
+EPI_BF16, EPI_GELU_BF16, EPI_RESID_F32, EPI_F32_OF_BF16 = 0, 1, 2, 3
+
+
+class WfError(RuntimeError):
+    pass
+
+
+_lib = None
+launches = 0     # kernels launched through this binding (bench.py's gpu_launches)
+
+_vp, _i, _f, _ll, _u = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_uint
+_SIGNATURES = {
+    "wf_gemm_bf16": [_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp],
+    "wf_attention_bf16": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _f, _vp],
+    "wf_layer_norm": [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp],
+    "wf_rms_norm_rope": [_vp, _i, _vp, _vp, _i, _i, _f, _vp],
+    "wf_patchify": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "wf_dit_head": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _f, _vp],
+    "wf_gemv_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "wf_gelu_erf_bf16": [_vp, _ll, _vp],
+    "wf_time_sinusoid": [_vp, _vp, _i, _vp],
+    "wf_add_bcast_f32": [_vp, _vp, _vp, _ll, _i, _vp],
+    "wf_cfg_combine": [_vp, _vp, _vp, _i, _f, _ll, _vp],
+    "wf_x0_convert": [_vp, _i, _vp, _i, _vp, _f, _ll, _vp],
+    "wf_unip_update": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _f, _f, _f, _f, _ll, _vp],
+    "wf_renoise": [_vp, _i, _vp, _vp, _f, _f, _ll, _vp],
+    "wf_dsg": [_vp, _vp, _vp, _i, _f, _ll, _vp, _vp, _vp],
+    "wf_flf_blend": [_vp, _vp, _vp, _vp, _i, _ll, _vp],
+    "wf_latent_denorm": [_vp, _i, _vp, _vp, _vp, _i, _ll, _vp],
+    "wf_latent_norm_replace": [_vp, _vp, _i, _vp, _vp, _vp, _u, _i, _ll, _vp],
+    "wf_quantise_u8": [_vp, _i, _vp, _ll, _vp, _vp],
+}
+_PLAIN = {"wf_last_error": (C.c_char_p, []), "wf_abi_version": (_i, []), "wf_sm_count": (_i, []),
+          "wf_dsg_workspace_bytes": (_ll, []), "wf_quantise_workspace_bytes": (_ll, [])}
+
+
+def exported_symbols():
+    """Every symbol include/wf_b200.h declares (checked by the CPU test-suite)."""
+    return sorted(list(_SIGNATURES) + list(_PLAIN))
+
+
+def load(path: str = LIB_PATH):
+    """Load the shared library (no GPU needed) and declare the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise WfError(f"{path} is missing - run `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(worldforge_b200 has no CPU fallback)")
+    lib = C.CDLL(path)
+    for name, args in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = _i
+    for name, (res, args) in _PLAIN.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = res
+    if lib.wf_abi_version() != 1:
+        raise WfError("libwf_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise WfError("worldforge_b200 kernels take CUDA tensors only (no CPU fallback)")
+    return t.data_ptr()
+
+
+def _call(name: str, *args):
+    global launches
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise WfError(f"{name} failed ({rc}): {lib.wf_last_error().decode()}")
+    launches += 1
+
+
+def _is_bf16(t: torch.Tensor) -> int:
+    if t.dtype == torch.bfloat16:
+        return 1
+    if t.dtype == torch.float32:
+        return 0
+    raise WfError(f"unsupported dtype {t.dtype}")
+
+
+# ---------------------------------------------------------------------------- DiT kernels
+
+def gemm_bf16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor,
+              epilogue: int = EPI_BF16, gate: Optional[torch.Tensor] = None):
+    """out = epilogue(a[M,K] @ w[N,K]^T + bias); a/w bf16 with contiguous K, out [M, N] view (row stride ldo)."""
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1 and out.stride(1) == 1
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    assert out.shape == (M, N)
+    want = torch.bfloat16 if epilogue in (EPI_BF16, EPI_GELU_BF16) else torch.float32
+    assert out.dtype == want, f"epilogue {epilogue} writes {want}"
+    assert bias is None or (bias.dtype == torch.bfloat16 and bias.numel() == N)
+    assert gate is None or (gate.dtype == torch.float32 and gate.numel() == N)
+    _call("wf_gemm_bf16", _p(a), a.stride(0), _p(w), w.stride(0), _p(bias), _p(out), out.stride(0), _p(gate),
+          M, N, K, epilogue, _stream())
+    return out
+
+
+def attention_bf16(q, k, v, out, heads: int, add_in=None, softmax_scale: Optional[float] = None):
+    """q [Lq, >=heads*128], k/v [Lk, ...], out [Lq, ...]: bf16 2-D views with contiguous columns."""
+    for t in (q, k, v, out):
+        assert t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1
+    scale = softmax_scale if softmax_scale is not None else 128 ** -0.5
+    _call("wf_attention_bf16", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
+          _p(add_in), add_in.stride(0) if add_in is not None else 0, q.shape[0], k.shape[0], heads, scale, _stream())
+    return out
+
+
+def layer_norm(x, out, eps: float, scale=None, shift=None, weight=None, bias=None, round_norm_bf16: bool = False):
+    rows, D = x.shape
+    assert x.stride(1) == 1 and out.stride(1) == 1 and out.shape == x.shape
+    for t in (scale, shift, weight, bias):
+        assert t is None or (t.dtype == torch.float32 and t.numel() == D and t.is_contiguous())
+    _call("wf_layer_norm", _p(x), x.stride(0), _is_bf16(x), _p(out), out.stride(0), _is_bf16(out), _p(scale), _p(shift),
+          _p(weight), _p(bias), rows, D, eps, int(round_norm_bf16), _stream())
+    return out
+
+
+def rms_norm_rope_(x, weight, eps: float, rope=None):
+    """In place on a bf16 [rows, D] view; rope: float64 [rows, 64, 2] or None."""
+    rows, D = x.shape
+    assert x.dtype == torch.bfloat16 and x.stride(1) == 1
+    assert weight.dtype == torch.float32 and weight.numel() == D
+    assert rope is None or (rope.dtype == torch.float64 and rope.shape == (rows, 64, 2) and rope.is_contiguous())
+    _call("wf_rms_norm_rope", _p(x), x.stride(0), _p(weight), _p(rope), rows, D, eps, _stream())
+    return x
+
+
+def patchify(hidden, cols):
+    C_, F_, H, W = hidden.shape
+    assert hidden.dtype == torch.bfloat16 and hidden.is_contiguous()
+    assert cols.dtype == torch.bfloat16 and cols.is_contiguous() and cols.shape == (F_ * (H // 2) * (W // 2), 4 * C_)
+    _call("wf_patchify", _p(hidden), _p(cols), C_, F_, H, W, _stream())
+    return cols
+
+
+def dit_head(x, scale, shift, w, b, out, grid, eps: float):
+    L, D = x.shape
+    F_, GH, GW = grid
+    cout = w.shape[0] // 4
+    assert x.dtype == torch.float32 and x.stride(1) == 1 and w.is_contiguous() and w.dtype == torch.float32
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.shape == (cout, F_, 2 * GH, 2 * GW)
+    _call("wf_dit_head", _p(x), x.stride(0), L, D, _p(scale), _p(shift), _p(w), _p(b), cout, _p(out), F_, GH, GW, eps,
+          _stream())
+    return out
+
+
+def gemv_f32(w, x, b, out, silu_in=False, silu_out=False):
+    N, K = w.shape
+    assert w.dtype == torch.float32 and w.is_contiguous() and x.dtype == torch.float32 and x.numel() == K
+    assert out.dtype == torch.float32 and out.numel() == N
+    _call("wf_gemv_f32", _p(w), _p(x), _p(b), _p(out), N, K, int(silu_in), int(silu_out), _stream())
+    return out
+
+
+def gelu_erf_bf16_(x):
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    _call("wf_gelu_erf_bf16", _p(x), x.numel(), _stream())
+    return x
+
+
+def time_sinusoid(timestep, out):
+    assert timestep.dtype == torch.int64 and out.dtype == torch.float32 and out.is_contiguous()
+    _call("wf_time_sinusoid", _p(timestep), _p(out), out.numel(), _stream())
+    return out
+
+
+def add_bcast_f32(a, b, out):
+    assert a.dtype == b.dtype == out.dtype == torch.float32 and a.is_contiguous() and b.is_contiguous() and out.is_contiguous()
+    inner = b.numel()
+    assert a.numel() % inner == 0 and out.numel() == a.numel()
+    _call("wf_add_bcast_f32", _p(a), _p(b), _p(out), a.numel() // inner, inner, _stream())
+    return out
+
+
+# -------------------------------------------------------------------------- sampler kernels
+
+def _flat_ok(*ts):
+    n = ts[0].numel()
+    for t in ts:
+        assert t.is_contiguous() and t.numel() == n
+    assert n % 4 == 0, "element count must be a multiple of 4"
+    return n
+
+
+def cfg_combine(cond, uncond, scale: float):
+    assert cond.dtype == uncond.dtype
+    out = torch.empty_like(cond)
+    n = _flat_ok(cond, uncond)
+    _call("wf_cfg_combine", _p(cond), _p(uncond), _p(out), _is_bf16(cond), float(scale), n, _stream())
+    return out
+
+
+def x0_convert(sample, v, sigma: float):
+    n = _flat_ok(sample, v)
+    dt = torch.bfloat16 if (sample.dtype == torch.bfloat16 and v.dtype == torch.bfloat16) else torch.float32
+    out = torch.empty(sample.shape, dtype=dt, device=sample.device)
+    _call("wf_x0_convert", _p(sample), _is_bf16(sample), _p(v), _is_bf16(v), _p(out), float(sigma), n, _stream())
+    return out
+
+
+def unip_update(x, m0, m1, order: int, c_x: float, c_m0: float, rk: float, c_res: float):
+    n = _flat_ok(x, m0) if m1 is None else _flat_ok(x, m0, m1)
+    out = torch.empty_like(x)
+    _call("wf_unip_update", _p(x), _is_bf16(x), _p(m0), _is_bf16(m0), _p(m1), _is_bf16(m1) if m1 is not None else 0,
+          _p(out), order, float(c_x), float(c_m0), float(rk), float(c_res), n, _stream())
+    return out
+
+
+def renoise(x0, noise, one_minus_sigma: float, sigma: float):
+    n = _flat_ok(x0, noise)
+    assert noise.dtype == torch.float32
+    out = torch.empty(x0.shape, dtype=torch.float32, device=x0.device)
+    _call("wf_renoise", _p(x0), _is_bf16(x0), _p(noise), _p(out), float(one_minus_sigma), float(sigma), n, _stream())
+    return out
+
+
+_ws = {}
+
+
+def _workspace(key: str, nbytes: int, device):
+    k = (key, device)
+    if k not in _ws or _ws[k].numel() < nbytes:
+        _ws[k] = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    return _ws[k]
+
+
+def dsg(g, w, omega: float, stats=None):
+    assert g.dtype == w.dtype
+    n = _flat_ok(g, w)
+    out = torch.empty_like(g)
+    ws = _workspace("dsg", load().wf_dsg_workspace_bytes(), g.device)
+    _call("wf_dsg", _p(g), _p(w), _p(out), _is_bf16(g), float(omega), n, _p(ws), _p(stats), _stream())
+    return out
+
+
+def flf_blend(decoded, ref, mask):
+    """decoded/ref [1,3,F,H,W] fp32, mask [1,1,F,H,W] fp32."""
+    assert decoded.dtype == ref.dtype == mask.dtype == torch.float32
+    assert decoded.is_contiguous() and ref.is_contiguous() and mask.is_contiguous()
+    ch = decoded.shape[1]
+    plane = mask.numel()
+    assert decoded.numel() == ch * plane == ref.numel()
+    out = torch.empty_like(decoded)
+    _call("wf_flf_blend", _p(decoded), _p(ref), _p(mask), _p(out), ch, plane, _stream())
+    return out
+
+
+def latent_denorm(x0, mean_host, inv_std_host):
+    """x0 [1,C,f,h,w]; mean/inv_std: host float32 arrays already rounded to x0's dtype."""
+    assert x0.is_contiguous()
+    ch = x0.shape[1]
+    out = torch.empty(x0.shape, dtype=torch.float32, device=x0.device)
+    m = (C.c_float * ch)(*mean_host); s = (C.c_float * ch)(*inv_std_host)
+    _call("wf_latent_denorm", _p(x0), _is_bf16(x0), _p(out), C.cast(m, _vp), C.cast(s, _vp), ch, x0.numel() // ch, _stream())
+    return out
+
+
+def latent_norm_replace(enc, x0, mean_host, inv_std_host, channels):
+    assert enc.dtype == torch.float32 and enc.is_contiguous() and x0.is_contiguous() and enc.shape == x0.shape
+    ch = x0.shape[1]
+    mask = 0
+    for c in channels:
+        if 0 <= c < ch:
+            mask |= 1 << c
+    out = torch.empty_like(x0)
+    m = (C.c_float * ch)(*mean_host); s = (C.c_float * ch)(*inv_std_host)
+    _call("wf_latent_norm_replace", _p(enc), _p(x0), _is_bf16(x0), _p(out), C.cast(m, _vp), C.cast(s, _vp), mask, ch,
+          x0.numel() // ch, _stream())
+    return out
+
+
+def quantise_u8(x):
+    assert x.is_contiguous()
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    ws = _workspace("quant", load().wf_quantise_workspace_bytes(), x.device)
+    _call("wf_quantise_u8", _p(x), _is_bf16(x), _p(out), x.numel(), _p(ws), _stream())
+    return out
