@@ -28,7 +28,9 @@ constexpr int GEMM_STAGES = 4;
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KB
 constexpr int GEMM_B_BYTES = GEMM_BN * GEMM_BK * 2;   // 32 KB
 constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
-constexpr int GEMM_SMEM = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_LD = 65;                              // padded row of the per-warp transpose tile (floats)
+constexpr int GEMM_EPI_BYTES = 4 * 32 * EPI_LD * 4;     // one 32 x 64 fp32 tile per epilogue warp
+constexpr int GEMM_SMEM = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + GEMM_EPI_BYTES;
 constexpr int GEMM_THREADS = 256;
 
 enum { EPI_BF16 = 0, EPI_GELU_BF16 = 1, EPI_RESID_F32 = 2, EPI_F32_OF_BF16 = 3 };
@@ -57,6 +59,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* acc_full = empty + GEMM_STAGES;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* epi_tile = reinterpret_cast<float*>(smem + GEMM_STAGES * GEMM_STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
@@ -127,63 +130,73 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
+    // TMEM gives each thread one accumulator ROW; global memory wants a warp on one row.  Each warp
+    // transposes 32x32 (fp32 out) / 32x64 (bf16 out) chunks through a private padded smem tile so
+    // that every global load / store instruction covers 128 contiguous bytes of one output row.
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int row_in_tile = q * 32 + lane_id();
+    const int lane = lane_id();
+    float* tile = epi_tile + q * (32 * EPI_LD);
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / tiles_n) * GEMM_BM, n0 = (tile % tiles_n) * GEMM_BN;
-      const int m = m0 + row_in_tile;
+    for (int tile_idx = blockIdx.x; tile_idx < num_tiles; tile_idx += gridDim.x) {
+      const int m0 = (tile_idx / tiles_n) * GEMM_BM + q * 32, n0 = (tile_idx % tiles_n) * GEMM_BN;
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * GEMM_BN;
+      constexpr bool kOutBf16 = (EPI == EPI_BF16 || EPI == EPI_GELU_BF16);
+      constexpr int CH = kOutBf16 ? 64 : 32;
 #pragma unroll 1
-      for (int c = 0; c < GEMM_BN; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_row + c, r);
-        tmem_ld_wait();
+      for (int c = 0; c < GEMM_BN; c += CH) {
         const int n = n0 + c;
-        if (m < p.M && n < p.N) {
-          float v[32];
+        if (n >= p.N) break;                 // warp-uniform
+        {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_row + c, r);
+          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float b = p.bias ? __bfloat162float(p.bias[n + j]) : 0.0f;
-            v[j] = bf16_round(__uint_as_float(r[j]) + b);
+          for (int j = 0; j < 32; ++j) tile[lane * EPI_LD + j] = __uint_as_float(r[j]);
+          if (CH == 64) {
+            tmem_ld_32x32b_x32(t_row + c + 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) tile[lane * EPI_LD + 32 + j] = __uint_as_float(r[j]);
           }
-          if (EPI == EPI_BF16 || EPI == EPI_GELU_BF16) {
-            uint4* dst = reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + static_cast<size_t>(m) * p.ldo + n);
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float w[8];
-#pragma unroll
-              for (int t = 0; t < 8; ++t) w[t] = (EPI == EPI_GELU_BF16) ? gelu_tanh_f(v[j + t]) : v[j + t];
-              uint4 o;
-              o.x = pack_bf16x2(w[0], w[1]); o.y = pack_bf16x2(w[2], w[3]);
-              o.z = pack_bf16x2(w[4], w[5]); o.w = pack_bf16x2(w[6], w[7]);
-              dst[j / 8] = o;
+        }
+        __syncwarp();
+        if (kOutBf16) {
+          const int col = n + 2 * lane;
+          const bool ok = col < p.N;
+          const float b0 = (ok && p.bias) ? __bfloat162float(p.bias[col]) : 0.f;
+          const float b1 = (ok && p.bias) ? __bfloat162float(p.bias[col + 1]) : 0.f;
+          bf16* dst = static_cast<bf16*>(p.out) + static_cast<size_t>(m0) * p.ldo + col;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            if (m0 + rr < p.M && ok) {
+              float y0 = bf16_round(tile[rr * EPI_LD + 2 * lane] + b0);
+              float y1 = bf16_round(tile[rr * EPI_LD + 2 * lane + 1] + b1);
+              if (EPI == EPI_GELU_BF16) { y0 = gelu_tanh_f(y0); y1 = gelu_tanh_f(y1); }
+              *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(rr) * p.ldo) = pack_bf16x2(y0, y1);
             }
-          } else {
-            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(m) * p.ldo + n);
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 o;
-              if (EPI == EPI_RESID_F32) {
-                float4 x = dst[j / 4];
-                float g0 = 1.f, g1 = 1.f, g2 = 1.f, g3 = 1.f;
-                if (p.gate) { g0 = p.gate[n + j]; g1 = p.gate[n + j + 1]; g2 = p.gate[n + j + 2]; g3 = p.gate[n + j + 3]; }
-                // x + y*e: two separately rounded fp32 ops, as torch evaluates them
-                o.x = __fadd_rn(x.x, __fmul_rn(v[j], g0)); o.y = __fadd_rn(x.y, __fmul_rn(v[j + 1], g1));
-                o.z = __fadd_rn(x.z, __fmul_rn(v[j + 2], g2)); o.w = __fadd_rn(x.w, __fmul_rn(v[j + 3], g3));
-              } else {
-                o.x = v[j]; o.y = v[j + 1]; o.z = v[j + 2]; o.w = v[j + 3];
-              }
-              dst[j / 4] = o;
+          }
+        } else {
+          const int col = n + lane;
+          const float b0 = p.bias ? __bfloat162float(p.bias[col]) : 0.f;
+          const float g0 = (EPI == EPI_RESID_F32 && p.gate) ? p.gate[col] : 1.f;
+          float* dst = static_cast<float*>(p.out) + static_cast<size_t>(m0) * p.ldo + col;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            if (m0 + rr < p.M) {
+              const float y = bf16_round(tile[rr * EPI_LD + lane] + b0);
+              float* d = dst + static_cast<size_t>(rr) * p.ldo;
+              if (EPI == EPI_RESID_F32) *d = __fadd_rn(*d, __fmul_rn(y, g0));   // x + y*e, two roundings like torch
+              else *d = y;
             }
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
-      if (lane_id() == 0) mbar_arrive(&acc_empty[acc]);
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
