@@ -102,9 +102,12 @@ int wf_cfg_combine(const void* cond, const void* uncond, void* out, int is_bf16,
 int wf_x0_convert(const void* sample, int sample_bf16, const void* v, int v_bf16, void* out, float sigma,
                   long long n, void* stream);
 /* multistep_uni_p_bh_update, scheduler :1084-1099, with the scalar coefficients evaluated by the host:
- * c_x = sigma_t/sigma_s0, c_m0 = alpha_t*expm1(-h), rk = r_1, c_res = alpha_t*B_h; out has x's dtype. */
+ * c_x = sigma_t/sigma_s0, c_m0 = alpha_t*expm1(-h), c_res = alpha_t*B_h; out has x's dtype.
+ * rk: r_1 itself (rk_is_reciprocal = 0: (m1-m0)/r_1) or 1/r_1 (rk_is_reciprocal = 1: (m1-m0)*(1/r_1), which is
+ * how torch's CUDA division kernel treats a host-side scalar divisor). */
 int wf_unip_update(const void* x, int x_bf16, const void* m0, int m0_bf16, const void* m1, int m1_bf16, void* out,
-                   int order, float c_x, float c_m0, float rk, float c_res, long long n, void* stream);
+                   int order, float c_x, float c_m0, float rk, int rk_is_reciprocal, float c_res, long long n,
+                   void* stream);
 /* add_noise, scheduler :1584: out fp32 = (1-sigma)*x0 + sigma*noise, sigma held in x0's dtype */
 int wf_renoise(const void* x0, int x0_bf16, const float* noise, float* out, float one_minus_sigma, float sigma,
                long long n, void* stream);

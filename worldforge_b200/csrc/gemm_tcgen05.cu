@@ -182,14 +182,23 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const float b0 = p.bias ? __bfloat162float(p.bias[col]) : 0.f;
           const float g0 = (EPI == EPI_RESID_F32 && p.gate) ? p.gate[col] : 1.f;
           float* dst = static_cast<float*>(p.out) + static_cast<size_t>(m0) * p.ldo + col;
-#pragma unroll 8
-          for (int rr = 0; rr < 32; ++rr) {
-            if (m0 + rr < p.M) {
-              const float y = bf16_round(tile[rr * EPI_LD + lane] + b0);
-              float* d = dst + static_cast<size_t>(rr) * p.ldo;
-              if (EPI == EPI_RESID_F32) *d = __fadd_rn(*d, __fmul_rn(y, g0));   // x + y*e, two roundings like torch
-              else *d = y;
+          const int rows_ok = min(32, p.M - m0);          // warp-uniform
+          if (EPI == EPI_RESID_F32) {
+            // all 32 residual loads are issued before the first store: one round trip, not 32
+            float xv[32];
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) xv[rr] = (rr < rows_ok) ? dst[static_cast<size_t>(rr) * p.ldo] : 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) {
+              if (rr < rows_ok) {
+                const float y = bf16_round(tile[rr * EPI_LD + lane] + b0);
+                dst[static_cast<size_t>(rr) * p.ldo] = __fadd_rn(xv[rr], __fmul_rn(y, g0));   // x + y*e: two roundings, like torch
+              }
             }
+          } else {
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr)
+              if (rr < rows_ok) dst[static_cast<size_t>(rr) * p.ldo] = bf16_round(tile[rr * EPI_LD + lane] + b0);
           }
         }
         __syncwarp();

@@ -93,7 +93,7 @@ __global__ void x0_convert_kernel(const void* x, bool x_bf, const void* v, bool 
 // ----------------------------------------------------------------------------- UniP-bh2 update
 struct UnipArgs {
   const void* x; const void* m0; const void* m1; void* out;
-  int x_bf, m0_bf, m1_bf, order;
+  int x_bf, m0_bf, m1_bf, order, rk_is_reciprocal;
   float c_x, c_m0, rk, c_res;
   size_t n4;
 };
@@ -107,7 +107,10 @@ __global__ void unip_update_kernel(UnipArgs p) {
       TV x{xs.v[k], p.x_bf != 0}, m0{a.v[k], p.m0_bf != 0};
       TV r = t_sub(t_mul_s(p.c_x, x), t_mul_s(p.c_m0, m0));
       if (p.order == 2) {
-        TV d1 = t_div_s(t_sub(TV{b.v[k], p.m1_bf != 0}, m0), p.rk);
+        // tensor / r_1: torch's CUDA kernel multiplies by the fp32 reciprocal when r_1 is a host scalar and
+        // divides when it is a device scalar (the resample tables live on the device)
+        TV diff = t_sub(TV{b.v[k], p.m1_bf != 0}, m0);
+        TV d1 = p.rk_is_reciprocal ? t_mul_s(p.rk, diff) : t_div_s(diff, p.rk);
         TV pred{0.5f * d1.v, d1.b && x.b};                    // einsum with rhos_p = [0.5] in x.dtype
         r = t_sub(r, t_mul_s(p.c_res, pred));
       }
@@ -309,11 +312,11 @@ extern "C" int wf_x0_convert(const void* sample, int sample_bf16, const void* v,
 }
 
 extern "C" int wf_unip_update(const void* x, int x_bf16, const void* m0, int m0_bf16, const void* m1, int m1_bf16, void* out, int order,
-                              float c_x, float c_m0, float rk, float c_res, long long n, void* stream) {
+                              float c_x, float c_m0, float rk, int rk_is_reciprocal, float c_res, long long n, void* stream) {
   WF_REQUIRE(x && m0 && out, "wf_unip_update: null pointer");
   WF_REQUIRE(order == 1 || (order == 2 && m1), "wf_unip_update: order must be 1, or 2 with a previous model output");
   WF_VEC4_OK(n, "wf_unip_update");
-  UnipArgs a{x, m0, m1, out, x_bf16, m0_bf16, m1_bf16, order, c_x, c_m0, rk, c_res, static_cast<size_t>(n / 4)};
+  UnipArgs a{x, m0, m1, out, x_bf16, m0_bf16, m1_bf16, order, rk_is_reciprocal, c_x, c_m0, rk, c_res, static_cast<size_t>(n / 4)};
   unip_update_kernel<<<grid_for(n / 4), 256, 0, WF_STREAM>>>(a);
   WF_LAUNCH_OK();
   return WF_OK;

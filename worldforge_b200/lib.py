@@ -40,7 +40,7 @@ _SIGNATURES = {
     "wf_add_bcast_f32": [_vp, _vp, _vp, _ll, _i, _vp],
     "wf_cfg_combine": [_vp, _vp, _vp, _i, _f, _ll, _vp],
     "wf_x0_convert": [_vp, _i, _vp, _i, _vp, _f, _ll, _vp],
-    "wf_unip_update": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _f, _f, _f, _f, _ll, _vp],
+    "wf_unip_update": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _f, _f, _f, _i, _f, _ll, _vp],
     "wf_renoise": [_vp, _i, _vp, _vp, _f, _f, _ll, _vp],
     "wf_dsg": [_vp, _vp, _vp, _i, _f, _ll, _vp, _vp, _vp],
     "wf_flf_blend": [_vp, _vp, _vp, _vp, _i, _ll, _vp],
@@ -231,11 +231,11 @@ def x0_convert(sample, v, sigma: float):
     return out
 
 
-def unip_update(x, m0, m1, order: int, c_x: float, c_m0: float, rk: float, c_res: float):
+def unip_update(x, m0, m1, order: int, c_x: float, c_m0: float, rk: float, rk_is_reciprocal: bool, c_res: float):
     n = _flat_ok(x, m0) if m1 is None else _flat_ok(x, m0, m1)
     out = torch.empty_like(x)
     _call("wf_unip_update", _p(x), _is_bf16(x), _p(m0), _is_bf16(m0), _p(m1), _is_bf16(m1) if m1 is not None else 0,
-          _p(out), order, float(c_x), float(c_m0), float(rk), float(c_res), n, _stream())
+          _p(out), order, float(c_x), float(c_m0), float(rk), int(rk_is_reciprocal), float(c_res), n, _stream())
     return out
 
 

@@ -52,6 +52,14 @@ def latent_stats(latents_mean, latents_std, dtype):
     return mean.float().tolist(), inv_std.float().tolist()
 
 
+def _round_to(v: float, dtype) -> float:
+    """v rounded to ``dtype`` (bf16) and widened back - what a device-side 0-dim fp32 tensor becomes when torch
+    casts it to the common dtype of an op with a bf16 tensor."""
+    if dtype == torch.bfloat16:
+        return float(torch.tensor(v, dtype=torch.float32).to(torch.bfloat16))
+    return float(v)
+
+
 def unip_coefficients(sigmas: torch.Tensor, resample_sigmas: Optional[torch.Tensor], step_index: int, order: int,
                       resampling: bool):
     """(c_x, c_m0, r_1, c_res) of the UniP-bh2 predictor as fp32 values (:1005-1061,1084-1089).
@@ -84,6 +92,26 @@ def unip_coefficients(sigmas: torch.Tensor, resample_sigmas: Optional[torch.Tens
     h_phi_1 = torch.expm1(hh)
     B_h = torch.expm1(hh)
     return (float(sigma_t / sigma_s0), float(alpha_t * h_phi_1), float(rk), float(alpha_t * B_h))
+
+
+def unip_kernel_args(co, order: int, resampling: bool, x_dtype, m0_dtype, m1_dtype):
+    """Turn the fp32 coefficients into the arguments of wf_unip_update, reproducing how torch's CUDA
+    kernels treat the scalar operand of each tensor-scalar op of the reference:
+
+    * not resampling: every coefficient is built from ``self.sigmas`` (host tensors, :838), i.e. a HOST
+      scalar - kept in fp32 inside the kernel; ``tensor / host_scalar`` is evaluated as
+      ``tensor * (1/host_scalar)``;
+    * resampling: sigma_s0 comes from ``self.resample_sigmas``, which the reference moves to the device
+      (:843-846), so every coefficient is a DEVICE 0-dim tensor - cast to the op's common dtype (rounded
+      to bf16 when the other operand is bf16) and ``tensor / device_scalar`` is a true division.
+    """
+    c_x, c_m0, rk, c_res = co
+    bf = torch.bfloat16
+    if not resampling:
+        return (c_x, c_m0, float(torch.tensor(1.0) / torch.tensor(rk, dtype=torch.float32)) if order == 2 else 1.0, True, c_res)
+    diff_dt = bf if (order == 2 and m0_dtype == bf and m1_dtype == bf) else torch.float32
+    pred_dt = bf if (diff_dt == bf and x_dtype == bf) else torch.float32
+    return (_round_to(c_x, x_dtype), _round_to(c_m0, m0_dtype), _round_to(rk, diff_dt), False, _round_to(c_res, pred_dt))
 
 
 class WfUniPCScheduler:
@@ -186,12 +214,18 @@ class WfUniPCScheduler:
 
     # ------------------------------------------------------------------------------ tensor ops -> kernels
     def convert_model_output(self, model_output, *args, sample=None, **kw):
-        return lib.x0_convert(sample.contiguous(), model_output.contiguous(), float(self._sigma_now()))
+        sigma = float(self._sigma_now())
+        if self.is_resampling and self.resample_sigmas is not None:
+            sigma = _round_to(sigma, model_output.dtype)     # device-side scalar: cast to the tensor's dtype
+        return lib.x0_convert(sample.contiguous(), model_output.contiguous(), sigma)
 
     def multistep_uni_p_bh_update(self, model_output=None, *args, sample=None, order=None, **kw):
-        co = unip_coefficients(self.sigmas, self.resample_sigmas, self._step_index, order, self.is_resampling)
+        resampling = self.is_resampling and self.resample_sigmas is not None
+        co = unip_coefficients(self.sigmas, self.resample_sigmas, self._step_index, order, resampling)
+        m0 = self.model_outputs[-1]
         m1 = self.model_outputs[-2] if order == 2 else None
-        return lib.unip_update(sample.contiguous(), self.model_outputs[-1], m1, order, *co)
+        args = unip_kernel_args(co, order, resampling, sample.dtype, m0.dtype, m1.dtype if m1 is not None else None)
+        return lib.unip_update(sample.contiguous(), m0, m1, order, *args)
 
     def add_noise(self, original_samples, noise, timesteps, r: int = 0, use_resample_sigma: bool = False):
         if use_resample_sigma and self.resample_sigmas is not None:
