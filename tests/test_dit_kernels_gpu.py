@@ -128,7 +128,7 @@ def test_layer_norm_modulate(cuda, rows, D):
     want0 = (wan_dit.layer_norm(xb, 1e-6).float() * (1 + sc) + sh).to(BF)
     out0 = torch.empty(rows, D, dtype=BF, device=cuda)
     lib.layer_norm(xb.float().to(cuda), out0, 1e-6, scale=sc.to(cuda), shift=sh.to(cuda), round_norm_bf16=True)
-    bf16_close(out0, want0)
+    bf16_close(out0, want0, ulps=2)   # the intermediate bf16 rounding can flip, which moves the result by up to 2 ulp
     # affine (norm3) and bf16 input / fp32 output variants
     w, b = 1 + torch.randn(D, generator=g(20)) * 0.1, torch.randn(D, generator=g(21)) * 0.1
     want3 = F.layer_norm(x, (D,), w, b, 1e-6)

@@ -73,7 +73,11 @@ def test_scheduler_step_matches_oracle_on_device(cuda, xb, m0b, m1b, order, resa
     if resampling and fp32_inputs:
         # device-side scalar math (log / expm1 on the GPU) may differ from the host's by an fp32 ulp
         assert got_u.dtype == want_u.dtype
-        torch.testing.assert_close(got_u.float(), want_u.float(), rtol=2e-6, atol=2e-6)
+        if got_u.dtype == torch.bfloat16:     # an fp32-ulp change of a coefficient can flip a final bf16 rounding
+            d = (got_u.float() - want_u.float()).abs()
+            assert (d <= want_u.float().abs() * 2.0 ** -7 + 1e-6).all() and (d > 0).float().mean() < 1e-2
+        else:
+            torch.testing.assert_close(got_u, want_u, rtol=2e-6, atol=2e-6)
     else:
         same(got_u, want_u.cpu())
     same(got_x0, want_x0.cpu())
