@@ -131,6 +131,33 @@ int wf_latent_norm_replace(const float* enc, const void* x0, int is_bf16, void* 
 long long wf_quantise_workspace_bytes(void);
 int wf_quantise_u8(const void* x, int is_bf16, unsigned char* out, long long n, void* workspace, void* stream);
 
+/* ---- Wan 3D-VAE (wan/modules/vae.py), channels-last fp32 activations [T][H][W][C] ------------------------ */
+
+/* Implicit-GEMM convolution on the tensor cores (tf32 operands, fp32 accumulation):
+ *   out(t,y,x,n) = bias[n] + sum_tap sum_c W[tap*Cout + n, c] * in(t*t_stride + t_off + dt_tap, y + dy_tap, x + dx_tap, c)
+ * with zero fill outside the input.  taps: ntaps int8 triples (dt, dy, dx).  The output element goes to frame
+ * t*t_mul + n/c_split, row y*sy+oy, column x*sx+ox, channel n%c_split of a channels-last tensor with out_H x out_W
+ * pixels per frame and ldc floats per pixel (planar_clamp = 1: planar [c][frame][out_H][out_W] with channel stride
+ * planar_cstride, values clamped to [-1,1]).  resid (same addressing as out) is added when not NULL.
+ * Replaces CausalConv3d.forward (vae.py:28-36), the Resample convs (:76-96,:128-140,:156-157), the 1x1 convs of
+ * AttentionBlock (:246,:260) and, as a plain GEMM, its q.k^T and p.v products (:252-256). */
+int wf_conv_tf32(const float* in, int in_T, int in_H, int in_W, int Cin, const float* weights, const float* bias,
+                 int Cout, int ntaps, const signed char* taps, int T, int H, int W, int t_stride, int t_off, float* out,
+                 int ldc, int out_H, int out_W, int t_mul, int c_split, int sy, int sx, int oy, int ox,
+                 const float* resid, int planar_clamp, long long planar_cstride, int tile_w, void* stream);
+/* RMS_norm (vae.py:51-54) over the channels of every pixel, optionally followed by SiLU (:195-197) */
+int wf_rms_norm_cl(const float* x, int ldx, float* out, int ldo, const float* gamma, long long pixels, int C, int silu,
+                   void* stream);
+/* planar [C][n] -> channels-last [n][Cp] (channels C..Cp-1 zero) and back (first C of ld channels) */
+int wf_planar_to_cl(const float* src, float* dst, long long n, int C, int Cp, void* stream);
+int wf_cl_to_planar(const float* src, float* dst, long long n, int C, int ld, void* stream);
+/* [T][H][W][C] -> [T][H/2][W/2][4C]: turns ZeroPad2d((0,1,0,1)) + Conv2d(3, stride 2) (vae.py:87-96) into a 2x2-tap conv */
+int wf_space_to_depth(const float* src, float* dst, int T, int H, int W, int C, void* stream);
+/* in-place softmax(scale*x) over the rows of x [rows][ld] (the mid-block attention, vae.py:252-256) */
+int wf_softmax_rows(float* x, int rows, int cols, int ld, float scale, void* stream);
+/* dst[c][r] = src[r][c] */
+int wf_transpose_f32(const float* src, float* dst, int R, int C, int lds, int ldd, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,287 @@
+// worldforge_b200 - convolutions of the Wan 3D-VAE as implicit GEMMs on tcgen05 (kind::tf32).
+//
+// Every convolution of the VAE (reference wan/modules/vae.py: CausalConv3d :17-36, the Resample 2-D convs
+// :76-96, the 1x1 convs of AttentionBlock :234-235 and WanVAE_.conv1/conv2 :505-506) is
+//
+//   out[t, y, x, n] = bias[n] + sum_{tap} sum_{c} W_tap[n, c] * in[t*st + dt_tap, y + dy_tap, x + dx_tap, c]
+//
+// over channels-last fp32 activations in[T][H][W][C].  The A operand of tap `tap` for a 128-pixel output tile
+// (TH x TW pixels of one frame) is therefore just the input tile shifted by (dt, dy, dx): one 4-D TMA box per
+// (tap, 32-channel chunk), with TMA's out-of-bounds zero fill providing the spatial zero padding AND the causal
+// zero history in time.  B is the matching 32-channel slice of the tap's [Cout, Cin] weight matrix.  Operands
+// stay fp32 in HBM and shared memory and are consumed as tf32 - the precision cuDNN uses for the reference's
+// fp32 VAE on a GPU (torch.backends.cudnn.allow_tf32 defaults to True) - with fp32 accumulation in TMEM.
+//
+// The same kernel covers, by parameters only:
+//   * 3x3x3 causal convs (27 taps, dt in {-2,-1,0}), 3x1x1 temporal convs (stride 1 or 2 in time), 1x1x1 convs
+//     and plain GEMMs (attention scores / PV of the mid block);
+//   * nearest-exact 2x upsample + 3x3 conv as four 2x2-tap convs on the LOW-resolution input, one per output
+//     parity, with pre-summed weights (no upsampled tensor is ever materialised; 2.25x fewer FLOPs);
+//   * pad(0,1,0,1) + 3x3 stride-2 conv as a 2x2-tap conv on the space-to-depth input;
+//   * the epilogue options the network needs: bias, residual add (ResidualBlock's x + h, :220; AttentionBlock's
+//     x + identity, :262), the channel->frame de-interleave of upsample3d (:134-137), strided/offset output
+//     placement for the parity convs, and the final planar [3,F,H,W] store with clamp(-1,1).
+//
+// Structure is the GEMM's: persistent CTAs, warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+// warps 4-7 epilogue (smem transpose -> 128-byte coalesced row stores), 4-stage mbarrier ring, two TMEM
+// accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <algorithm>
+
+#include "common.cuh"
+#include "host_util.h"
+
+namespace wf {
+
+constexpr int CV_BM = 128;          // output pixels per tile
+constexpr int CV_BK = 32;           // fp32 channels per k-block = one 128-byte swizzle row
+constexpr int CV_MAX_BN = 192;
+constexpr int CV_STAGES = 4;
+constexpr int CV_A_BYTES = CV_BM * CV_BK * 4;           // 16 KB
+constexpr int CV_B_BYTES = CV_MAX_BN * CV_BK * 4;       // 24 KB (slot size; BN*128 bytes are used)
+constexpr int CV_STAGE_BYTES = CV_A_BYTES + CV_B_BYTES;
+constexpr int CV_EPI_LD = 33;
+constexpr int CV_EPI_BYTES = 4 * 32 * CV_EPI_LD * 4;
+constexpr int CV_SMEM = CV_STAGES * CV_STAGE_BYTES + 1024 + 256 + CV_EPI_BYTES;
+constexpr int CV_THREADS = 256;
+constexpr int CV_MAX_TAPS = 27;
+
+struct ConvArgs {
+  // iteration space of the output tiles
+  int T, H, W;              // output frames / rows / columns this launch produces
+  int TH, TW;               // tile shape, TH*TW == 128
+  int Cin, Cout, BN;        // Cin % 32 == 0 (padded), BN in {16,32,48,...,192}
+  int ntaps;
+  int t_stride, t_off;      // input frame = t*t_stride + t_off + dt
+  int8_t dt[CV_MAX_TAPS], dy[CV_MAX_TAPS], dx[CV_MAX_TAPS];
+  // output placement: element (t, y, x, n) goes to
+  //   frame  t*t_mul + n / c_split,  row y*sy + oy,  column x*sx + ox,  channel n % c_split
+  float* out; int ldc; int out_H, out_W;
+  int t_mul, c_split, sy, sx, oy, ox;
+  const float* bias;        // [Cout] or null
+  const float* resid;       // same addressing as out, or null
+  int planar_clamp;         // 1: out is planar [c_split][frames][out_H][out_W], values clamped to [-1,1]
+  long long planar_cstride; // elements between channels in planar mode
+};
+
+__global__ void __launch_bounds__(CV_THREADS, 1)
+conv_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + CV_STAGES * CV_STAGE_BYTES);
+  uint64_t* empty = full + CV_STAGES;
+  uint64_t* acc_full = empty + CV_STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* epi_tile = reinterpret_cast<float*>(smem + CV_STAGES * CV_STAGE_BYTES + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int tiles_x = (p.W + p.TW - 1) / p.TW, tiles_y = (p.H + p.TH - 1) / p.TH;
+  const int tiles_n = (p.Cout + p.BN - 1) / p.BN;
+  const int tiles_pix = tiles_x * tiles_y * p.T;
+  const int num_tiles = tiles_pix * tiles_n;
+  const int kchunks = p.Cin / CV_BK;
+  const int num_kb = p.ntaps * kchunks;
+  const uint32_t stage_tx = CV_A_BYTES + static_cast<uint32_t>(p.BN) * CV_BK * 4;
+
+  if (warp == 0 && elect_one()) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < CV_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile -> (n-tile fastest: the n-tiles of one pixel tile run back to back and share the A traffic in L2)
+  auto decode = [&](int tile, int& t, int& y0, int& x0, int& n0) {
+    const int nt = tile % tiles_n; int pt = tile / tiles_n;
+    const int xt = pt % tiles_x; pt /= tiles_x;
+    const int yt = pt % tiles_y; t = pt / tiles_y;
+    y0 = yt * p.TH; x0 = xt * p.TW; n0 = nt * p.BN;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int t, y0, x0, n0; decode(tile, t, y0, x0, n0);
+      for (int tap = 0; tap < p.ntaps; ++tap) {
+        const int ti = t * p.t_stride + p.t_off + p.dt[tap], yi = y0 + p.dy[tap], xi = x0 + p.dx[tap];
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (elect_one()) {
+            uint8_t* a_dst = smem + stage * CV_STAGE_BYTES;
+            mbar_arrive_expect_tx(&full[stage], stage_tx);
+            tma_load_4d(a_dst, &tmA, &full[stage], kc * CV_BK, xi, yi, ti);
+            tma_load_2d(a_dst + CV_A_BYTES, &tmB, &full[stage], kc * CV_BK, tap * p.Cout + n0);
+          }
+          __syncwarp();
+          if (++stage == CV_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    const uint32_t idesc = umma_idesc(2, CV_BM, static_cast<uint32_t>(p.BN), 0, 0);   // tf32 x tf32 -> fp32
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 256;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(smem + stage * CV_STAGE_BYTES);
+          const uint32_t b_addr = a_addr + CV_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < CV_BK / 8; ++k) {
+            uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
+            uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_tf32_ss(d_tmem, da, db, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty[stage]);
+          if (kb == num_kb - 1) umma_commit(&acc_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == CV_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue
+    const int q = warp & 3, lane = lane_id();
+    float* tile_s = epi_tile + q * (32 * CV_EPI_LD);
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int t, y0, x0, n0; decode(tile, t, y0, x0, n0);
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
+#pragma unroll 1
+      for (int c = 0; c < p.BN; c += 32) {
+        const int n = n0 + c;
+        if (n >= p.Cout) break;
+        if (p.BN - c >= 32) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_row + c, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) tile_s[lane * CV_EPI_LD + j] = __uint_as_float(r[j]);
+        } else {   // BN = 16 or 48: the last chunk has 16 valid columns; TMEM beyond BN is not ours to read
+          uint32_t r[32];
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+              : "r"(t_row + c) : "memory");
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) tile_s[lane * CV_EPI_LD + j] = __uint_as_float(r[j]);
+        }
+        __syncwarp();
+        const int col = n + lane;
+        const bool col_ok = col < p.Cout && (c + lane) < p.BN;
+        const float b0 = (col_ok && p.bias) ? p.bias[col] : 0.f;
+        const int fo = col_ok ? col / p.c_split : 0, ch = col_ok ? col % p.c_split : 0;
+        const int frame = t * p.t_mul + fo;
+        // 32 rows of this warp = pixels q*32 .. q*32+31 of the TH x TW tile
+        size_t off[32]; bool ok[32];
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) {
+          const int r_in_tile = q * 32 + rr;
+          const int y = y0 + r_in_tile / p.TW, x = x0 + r_in_tile % p.TW;
+          ok[rr] = col_ok && y < p.H && x < p.W;
+          const size_t pix = (static_cast<size_t>(frame) * p.out_H + (y * p.sy + p.oy)) * p.out_W + (x * p.sx + p.ox);
+          off[rr] = p.planar_clamp ? static_cast<size_t>(ch) * p.planar_cstride + pix : pix * p.ldc + ch;
+        }
+        float rv[32];
+        if (p.resid) {
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) rv[rr] = ok[rr] ? p.resid[off[rr]] : 0.f;
+        }
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) {
+          if (ok[rr]) {
+            float v = tile_s[rr * CV_EPI_LD + lane] + b0;
+            if (p.resid) v += rv[rr];
+            if (p.planar_clamp) v = fminf(fmaxf(v, -1.0f), 1.0f);
+            p.out[off[rr]] = v;
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace wf
+
+using namespace wf;
+
+// in: channels-last fp32 [in_T][in_H][in_W][Cin]; weights fp32 [ntaps*Cout][Cin]; taps: int8 triples (dt,dy,dx).
+extern "C" int wf_conv_tf32(const float* in, int in_T, int in_H, int in_W, int Cin, const float* weights, const float* bias,
+                            int Cout, int ntaps, const signed char* taps, int T, int H, int W, int t_stride, int t_off,
+                            float* out, int ldc, int out_H, int out_W, int t_mul, int c_split, int sy, int sx, int oy,
+                            int ox, const float* resid, int planar_clamp, long long planar_cstride, int tile_w,
+                            void* stream) {
+  WF_REQUIRE(in && weights && out && taps, "wf_conv_tf32: null pointer");
+  WF_REQUIRE(Cin > 0 && Cin % 4 == 0, "wf_conv_tf32: Cin must be a positive multiple of 4 (16-byte pixel rows)");
+  WF_REQUIRE(Cout > 0 && ntaps > 0 && ntaps <= CV_MAX_TAPS, "wf_conv_tf32: bad Cout / tap count");
+  WF_REQUIRE(tile_w == 8 || tile_w == 16 || tile_w == 32 || tile_w == 64 || tile_w == 128, "wf_conv_tf32: tile_w must be 8..128, power of two");
+  WF_REQUIRE(T > 0 && H > 0 && W > 0 && c_split > 0 && t_mul > 0, "wf_conv_tf32: empty output");
+  WF_REQUIRE(reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(weights) % 16 == 0, "wf_conv_tf32: 16-byte alignment");
+  ConvArgs a{};
+  a.T = T; a.H = H; a.W = W; a.TW = tile_w; a.TH = CV_BM / tile_w;
+  a.Cin = (Cin + CV_BK - 1) / CV_BK * CV_BK;   // the K loop runs over whole 32-channel chunks; TMA zero-fills the tail
+  a.Cout = Cout;
+  // widest N tile that divides the work evenly enough: 192 for the wide layers, Cout rounded up to 16 otherwise
+  int bn = Cout <= CV_MAX_BN ? (Cout + 15) / 16 * 16 : CV_MAX_BN;
+  if (Cout > CV_MAX_BN && Cout % 192 != 0 && Cout % 128 == 0) bn = 128;
+  a.BN = bn;
+  a.ntaps = ntaps; a.t_stride = t_stride; a.t_off = t_off;
+  for (int i = 0; i < ntaps; ++i) { a.dt[i] = taps[3 * i]; a.dy[i] = taps[3 * i + 1]; a.dx[i] = taps[3 * i + 2]; }
+  a.out = out; a.ldc = ldc; a.out_H = out_H; a.out_W = out_W; a.t_mul = t_mul; a.c_split = c_split;
+  a.sy = sy; a.sx = sx; a.oy = oy; a.ox = ox; a.bias = bias; a.resid = resid;
+  a.planar_clamp = planar_clamp; a.planar_cstride = planar_cstride;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(in_W), static_cast<uint64_t>(in_H), static_cast<uint64_t>(in_T)};
+    uint64_t strides[3] = {static_cast<uint64_t>(Cin) * 4, static_cast<uint64_t>(in_W) * Cin * 4, static_cast<uint64_t>(in_H) * in_W * Cin * 4};
+    uint32_t box[4] = {CV_BK, static_cast<uint32_t>(a.TW), static_cast<uint32_t>(a.TH), 1};
+    int rc = make_tmap(&tmA, in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(ntaps) * Cout};
+    uint64_t strides[1] = {static_cast<uint64_t>(Cin) * 4};
+    uint32_t box[2] = {CV_BK, static_cast<uint32_t>(a.BN)};
+    int rc = make_tmap(&tmB, weights, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    WF_CUDA_OK(cudaFuncSetAttribute(conv_tf32_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM));
+    attr_set = true;
+  }
+  const long long tiles = static_cast<long long>((W + a.TW - 1) / a.TW) * ((H + a.TH - 1) / a.TH) * T * ((Cout + a.BN - 1) / a.BN);
+  const int grid = static_cast<int>(std::min<long long>(tiles, sm_count()));
+  conv_tf32_tcgen05<<<grid, CV_THREADS, CV_SMEM, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, a);
+  WF_LAUNCH_OK();
+  return WF_OK;
+}

@@ -47,6 +47,14 @@ _SIGNATURES = {
     "wf_latent_denorm": [_vp, _i, _vp, _vp, _vp, _i, _ll, _vp],
     "wf_latent_norm_replace": [_vp, _vp, _i, _vp, _vp, _vp, _u, _i, _ll, _vp],
     "wf_quantise_u8": [_vp, _i, _vp, _ll, _vp, _vp],
+    "wf_conv_tf32": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i,
+                     _vp, _i, _ll, _i, _vp],
+    "wf_rms_norm_cl": [_vp, _i, _vp, _i, _vp, _ll, _i, _i, _vp],
+    "wf_planar_to_cl": [_vp, _vp, _ll, _i, _i, _vp],
+    "wf_cl_to_planar": [_vp, _vp, _ll, _i, _i, _vp],
+    "wf_space_to_depth": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "wf_softmax_rows": [_vp, _i, _i, _i, _f, _vp],
+    "wf_transpose_f32": [_vp, _vp, _i, _i, _i, _i, _vp],
 }
 _PLAIN = {"wf_last_error": (C.c_char_p, []), "wf_abi_version": (_i, []), "wf_sm_count": (_i, []),
           "wf_dsg_workspace_bytes": (_ll, []), "wf_quantise_workspace_bytes": (_ll, [])}
@@ -308,3 +316,80 @@ def quantise_u8(x):
     ws = _workspace("quant", load().wf_quantise_workspace_bytes(), x.device)
     _call("wf_quantise_u8", _p(x), _is_bf16(x), _p(out), x.numel(), _p(ws), _stream())
     return out
+
+
+# ------------------------------------------------------------------------------ VAE kernels
+
+def conv_tf32(inp, weights, bias, taps, out, *, T, H, W, Cout, t_stride=1, t_off=0, t_mul=1, c_split=None, sy=1, sx=1,
+              oy=0, ox=0, resid=None, planar_clamp=False, tile_w=16, out_hw=None, ldc=None):
+    """inp: channels-last fp32 [in_T, in_H, in_W, Cin]; weights fp32 [ntaps*Cout, Cin]; taps: list of (dt,dy,dx).
+    out: channels-last fp32 [frames, out_H, out_W, ldc] (or planar [c, frames, out_H, out_W] with planar_clamp)."""
+    assert inp.dtype == torch.float32 and inp.is_contiguous() and inp.dim() == 4
+    in_T, in_H, in_W, Cin = inp.shape
+    ntaps = len(taps)
+    assert weights.dtype == torch.float32 and weights.is_contiguous() and weights.shape == (ntaps * Cout, Cin)
+    assert out.dtype == torch.float32 and out.is_contiguous()
+    tb = (C.c_byte * (3 * ntaps))(*[v for t3 in taps for v in t3])
+    if planar_clamp:
+        cs = out.shape[0]
+        oH, oW = out.shape[2], out.shape[3]
+        cstride = out.stride(0)
+        ld = 0
+    else:
+        oH, oW = (out.shape[1], out.shape[2]) if out_hw is None else out_hw
+        ld = out.shape[3] if ldc is None else ldc
+        cs = Cout if c_split is None else c_split
+        cstride = 0
+    _call("wf_conv_tf32", _p(inp), in_T, in_H, in_W, Cin, _p(weights), _p(bias), Cout, ntaps, C.cast(tb, _vp), T, H, W,
+          t_stride, t_off, _p(out), ld, oH, oW, t_mul, cs, sy, sx, oy, ox, _p(resid), int(planar_clamp), cstride, tile_w,
+          _stream())
+    return out
+
+
+def rms_norm_cl(x, gamma, out=None, silu=True):
+    C_ = x.shape[-1]
+    assert x.dtype == torch.float32 and x.is_contiguous() and gamma.numel() == C_
+    out = torch.empty_like(x) if out is None else out
+    _call("wf_rms_norm_cl", _p(x), C_, _p(out), C_, _p(gamma), x.numel() // C_, C_, int(silu), _stream())
+    return out
+
+
+def planar_to_cl(src, Cp):
+    """[C, ...] planar fp32 -> [..., Cp] channels-last with zero-padded channels."""
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    C_ = src.shape[0]
+    n = src.numel() // C_
+    dst = torch.empty(*src.shape[1:], Cp, dtype=torch.float32, device=src.device)
+    _call("wf_planar_to_cl", _p(src), _p(dst), n, C_, Cp, _stream())
+    return dst
+
+
+def cl_to_planar(src, C_):
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    ld = src.shape[-1]
+    n = src.numel() // ld
+    dst = torch.empty(C_, *src.shape[:-1], dtype=torch.float32, device=src.device)
+    _call("wf_cl_to_planar", _p(src), _p(dst), n, C_, ld, _stream())
+    return dst
+
+
+def space_to_depth(src):
+    T, H, W, C_ = src.shape
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    dst = torch.empty(T, H // 2, W // 2, 4 * C_, dtype=torch.float32, device=src.device)
+    _call("wf_space_to_depth", _p(src), _p(dst), T, H, W, C_, _stream())
+    return dst
+
+
+def softmax_rows_(x, scale: float):
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    _call("wf_softmax_rows", _p(x), x.shape[0], x.shape[1], x.stride(0), float(scale), _stream())
+    return x
+
+
+def transpose_f32(src, dst):
+    assert src.dtype == torch.float32 and src.dim() == 2 and src.stride(1) == 1 and dst.is_contiguous()
+    R, C_ = src.shape
+    assert dst.shape == (C_, R)
+    _call("wf_transpose_f32", _p(src), _p(dst), R, C_, src.stride(0), dst.stride(0), _stream())
+    return dst

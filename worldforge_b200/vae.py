@@ -1,0 +1,356 @@
+"""Wan2.1 causal 3D-VAE on the sm_100a kernels: the object that stands in for ``pipe.vae``.
+
+Surface used by the reference: ``encode(x[1,3,F,H,W]).latent_dist.mode()``
+(pipeline_wan_i2v_clean.py:348, scheduling_unipc_multistep_clean.py:1384), ``decode(z, return_dict=False)[0]``
+(:743, :1285), ``config.{z_dim, latents_mean, latents_std}``, ``temperal_downsample``, ``dtype``.
+
+The network is the reference's ``WanVAE_`` (wan/modules/vae.py) = diffusers' ``AutoencoderKLWan``.  The reference
+walks the clip chunk by chunk with a per-convolution feature cache (vae.py:516-568); the engine evaluates every
+layer over the whole clip at once (the same function - see oracle/wan_vae.py for the three identities used and
+their numerical check against the chunked reference), which turns 21 x 33 tiny cuDNN launches per decode into a
+few dozen full-grid launches:
+
+* activations are channels-last fp32 ``[T][H][W][C]`` so that a convolution tap is a shifted 4-D TMA box;
+* every convolution is ``wf_conv_tf32`` (tcgen05, tf32 operands = cuDNN's default precision for the reference's
+  fp32 VAE, fp32 accumulation); bias, the residual add of ResidualBlock / AttentionBlock, upsample3d's
+  channel->frame de-interleave and the final clamp + planar store are fused into its epilogue;
+* nearest-exact 2x upsampling is never materialised: upsample + 3x3 conv = four 2x2-tap convolutions on the
+  low-resolution tensor (one per output parity) with pre-summed weights;
+* pad(0,1,0,1) + stride-2 3x3 conv = a 2x2-tap convolution on the space-to-depth tensor;
+* RMS-norm + SiLU is one fused pass (``wf_rms_norm_cl``).
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Dict, List, Tuple
+
+import torch
+
+from . import lib
+
+F32 = torch.float32
+
+LATENTS_MEAN = [-0.7571, -0.7089, -0.9113, 0.1075, -0.1745, 0.9653, -0.1517, 1.5508,
+                0.4134, -0.0715, 0.5517, -0.3632, -0.1922, -0.9497, 0.2503, -0.2921]   # reference vae.py:629-632
+LATENTS_STD = [2.8184, 1.4541, 2.3275, 2.6558, 1.2196, 1.7708, 2.6052, 2.0743,
+               3.2687, 2.1526, 2.8652, 1.5579, 1.6382, 1.1253, 2.8251, 1.9160]        # reference vae.py:633-636
+
+TAPS_333 = [(dt - 2, dy - 1, dx - 1) for dt in range(3) for dy in range(3) for dx in range(3)]
+TAPS_1 = [(0, 0, 0)]
+TAPS_T_CAUSAL = [(-2, 0, 0), (-1, 0, 0), (0, 0, 0)]
+TAPS_T_STRIDE2 = [(0, 0, 0), (1, 0, 0), (2, 0, 0)]
+TAPS_S2D = [(0, a, b) for a in range(2) for b in range(2)]
+
+
+def _pad_cin(w2: torch.Tensor) -> torch.Tensor:
+    """[rows, Cin] -> Cin padded to a multiple of 4 (16-byte pixel rows for TMA)."""
+    cin = w2.shape[1]
+    pad = (-cin) % 4
+    if pad:
+        w2 = torch.cat([w2, w2.new_zeros(w2.shape[0], pad)], dim=1)
+    return w2.contiguous()
+
+
+def _w_conv3d(w: torch.Tensor) -> torch.Tensor:
+    """[Co, Ci, kt, kh, kw] -> [(kt*kh*kw)*Co, Ci] tap-major."""
+    co, ci = w.shape[:2]
+    return _pad_cin(w.permute(2, 3, 4, 0, 1).reshape(-1, ci))
+
+
+def _w_upsample_parity(w: torch.Tensor) -> List[torch.Tensor]:
+    """Conv2d weight [Co, Ci, 3, 3] applied after nearest-exact 2x upsampling == for output parity (p, q) a 2x2-tap
+    conv on the low-res input: rows p=0 use (y-1: W[0], y: W[1]+W[2]); p=1 use (y: W[0]+W[1], y+1: W[2])."""
+    def comb(t, par):      # t: [..., 3] along one kernel axis -> [..., 2]
+        a, b, c = t.unbind(-1)
+        return torch.stack([a, b + c], -1) if par == 0 else torch.stack([a + b, c], -1)
+    out = []
+    for p in (0, 1):
+        for q in (0, 1):
+            wy = comb(w.transpose(2, 3), p).transpose(2, 3)      # combine over kh -> [Co,Ci,2,3]
+            wyx = comb(wy, q)                                     # combine over kw -> [Co,Ci,2,2]
+            co, ci = w.shape[:2]
+            out.append(_pad_cin(wyx.permute(2, 3, 0, 1).reshape(-1, ci)))
+    return out
+
+
+def _taps_upsample(p: int, q: int):
+    ys = (-1, 0) if p == 0 else (0, 1)
+    xs = (-1, 0) if q == 0 else (0, 1)
+    return [(0, y, x) for y in ys for x in xs]
+
+
+def _w_s2d(w: torch.Tensor) -> torch.Tensor:
+    """Conv2d weight [Co, Ci, 3, 3], stride 2 after pad(0,1,0,1) -> 2x2-tap weights over the space-to-depth input
+    whose channel index is (p*2+q)*Ci + c:  W'[a,b][co][(p,q,c)] = W[co,c,2a+p,2b+q] (zero where 2a+p or 2b+q is 3)."""
+    co, ci = w.shape[:2]
+    out = w.new_zeros(2, 2, co, 4 * ci)
+    for a in range(2):
+        for b in range(2):
+            for p in range(2):
+                for q in range(2):
+                    if 2 * a + p <= 2 and 2 * b + q <= 2:
+                        out[a, b, :, (p * 2 + q) * ci:(p * 2 + q + 1) * ci] = w[:, :, 2 * a + p, 2 * b + q]
+    return out.reshape(4 * co, 4 * ci).contiguous()
+
+
+class _Dist:
+    def __init__(self, mean):
+        self._mean = mean
+
+    def mode(self):
+        return self._mean
+
+    @property
+    def mean(self):
+        return self._mean
+
+
+class WfWanVAE:
+    """Weights prepared once on the device; ``encode`` / ``decode`` are sequences of C-ABI launches."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device, dim: int = 96, z_dim: int = 16,
+                 dim_mult=(1, 2, 4, 4), num_res_blocks: int = 2, temporal_downsample=(False, True, True)):
+        self.device = torch.device(device)
+        self.dtype = F32
+        self.z_dim = z_dim
+        self.config = SimpleNamespace(z_dim=z_dim, latents_mean=list(LATENTS_MEAN[:z_dim]), latents_std=list(LATENTS_STD[:z_dim]))
+        self.temperal_downsample = list(temporal_downsample)
+        self.dim, self.dim_mult, self.num_res_blocks = dim, tuple(dim_mult), num_res_blocks
+        self.enc_plan, self.dec_plan = self._plans()
+        sd = {k: v.to(device=self.device, dtype=F32) for k, v in state_dict.items()}
+        self.w: Dict[str, torch.Tensor] = {}
+        self._prepare(sd)
+
+    def to(self, *a, **k):
+        return self
+
+    # ------------------------------------------------------------------------------ architecture
+    def _plans(self):
+        dims = [self.dim * u for u in (1,) + self.dim_mult]
+        enc = [("conv", "encoder.conv1", 3, dims[0])]
+        idx = 0
+        for i, (cin, cout) in enumerate(zip(dims[:-1], dims[1:])):
+            for _ in range(self.num_res_blocks):
+                enc.append(("res", f"encoder.downsamples.{idx}", cin, cout)); idx += 1
+                cin = cout
+            if i != len(self.dim_mult) - 1:
+                enc.append(("down3d" if self.temperal_downsample[i] else "down2d", f"encoder.downsamples.{idx}", cout, cout)); idx += 1
+        c = dims[-1]
+        enc += [("res", "encoder.middle.0", c, c), ("attn", "encoder.middle.1", c, c), ("res", "encoder.middle.2", c, c),
+                ("head", "encoder.head", c, self.z_dim * 2)]
+        ddims = [self.dim * u for u in (self.dim_mult[-1],) + self.dim_mult[::-1]]
+        up = tuple(self.temperal_downsample[::-1])
+        c = ddims[0]
+        dec = [("conv", "decoder.conv1", self.z_dim, c), ("res", "decoder.middle.0", c, c), ("attn", "decoder.middle.1", c, c),
+               ("res", "decoder.middle.2", c, c)]
+        idx = 0
+        for i, (cin, cout) in enumerate(zip(ddims[:-1], ddims[1:])):
+            if i in (1, 2, 3):
+                cin //= 2
+            for _ in range(self.num_res_blocks + 1):
+                dec.append(("res", f"decoder.upsamples.{idx}", cin, cout)); idx += 1
+                cin = cout
+            if i != len(self.dim_mult) - 1:
+                dec.append(("up3d" if up[i] else "up2d", f"decoder.upsamples.{idx}", cout, cout // 2)); idx += 1
+        dec.append(("head", "decoder.head", ddims[-1], 3))
+        return enc, dec
+
+    def _prepare(self, sd):
+        W = self.w
+        def conv3(name):
+            W[name + ".w"] = _w_conv3d(sd[name + ".weight"]); W[name + ".b"] = sd[name + ".bias"].contiguous()
+        def gamma(name):
+            W[name] = sd[name].reshape(-1).contiguous()
+        for plan in (self.enc_plan, self.dec_plan):
+            for kind, name, cin, cout in plan:
+                if kind == "conv":
+                    conv3(name)
+                elif kind == "res":
+                    gamma(name + ".residual.0.gamma"); conv3(name + ".residual.2")
+                    gamma(name + ".residual.3.gamma"); conv3(name + ".residual.6")
+                    if cin != cout:
+                        conv3(name + ".shortcut")
+                elif kind == "attn":
+                    gamma(name + ".norm.gamma")
+                    wq = sd[name + ".to_qkv.weight"].reshape(3, cin, cin)
+                    bq = sd[name + ".to_qkv.bias"].reshape(3, cin)
+                    for j, t in enumerate("qkv"):
+                        W[f"{name}.{t}.w"] = wq[j].contiguous(); W[f"{name}.{t}.b"] = bq[j].contiguous()
+                    W[name + ".proj.w"] = sd[name + ".proj.weight"].reshape(cin, cin).contiguous()
+                    W[name + ".proj.b"] = sd[name + ".proj.bias"].contiguous()
+                elif kind in ("down2d", "down3d"):
+                    W[name + ".s2d.w"] = _w_s2d(sd[name + ".resample.1.weight"]); W[name + ".s2d.b"] = sd[name + ".resample.1.bias"].contiguous()
+                    if kind == "down3d":
+                        conv3(name + ".time_conv")
+                elif kind in ("up2d", "up3d"):
+                    for j, wp in enumerate(_w_upsample_parity(sd[name + ".resample.1.weight"])):
+                        W[f"{name}.par{j}.w"] = wp
+                    W[name + ".par.b"] = sd[name + ".resample.1.bias"].contiguous()
+                    if kind == "up3d":
+                        conv3(name + ".time_conv")
+                elif kind == "head":
+                    gamma(name + ".0.gamma"); conv3(name + ".2")
+        conv3("conv1"); conv3("conv2")
+
+    # ------------------------------------------------------------------------------ layers
+    @staticmethod
+    def _tile_w(w: int) -> int:
+        return 16 if w % 16 == 0 else 8
+
+    def _conv(self, x, wname, taps, cout, *, resid=None, t_out=None, t_stride=1, t_off=0, out=None, t_mul=1, c_split=None):
+        T, H, Wd, _ = x.shape
+        t_out = T if t_out is None else t_out
+        if out is None:
+            out = torch.empty(t_out * t_mul, H, Wd, cout if c_split is None else c_split, dtype=F32, device=x.device)
+        lib.conv_tf32(x, self.w[wname + ".w"], self.w[wname + ".b"], taps, out, T=t_out, H=H, W=Wd, Cout=cout,
+                      t_stride=t_stride, t_off=t_off, t_mul=t_mul, c_split=c_split, resid=resid, tile_w=self._tile_w(Wd))
+        return out
+
+    def _res(self, x, name, cin, cout):
+        h = self._conv(x, name + ".shortcut", TAPS_1, cout) if cin != cout else x
+        y = lib.rms_norm_cl(x, self.w[name + ".residual.0.gamma"])
+        y = self._conv(y, name + ".residual.2", TAPS_333, cout)
+        lib.rms_norm_cl(y, self.w[name + ".residual.3.gamma"], out=y)
+        return self._conv(y, name + ".residual.6", TAPS_333, cout, resid=h)
+
+    def _attn(self, x, name, c):
+        T, H, Wd, _ = x.shape
+        n = lib.rms_norm_cl(x, self.w[name + ".norm.gamma"], silu=False)
+        q, k, v = (self._conv(n, f"{name}.{t}", TAPS_1, c) for t in "qkv")
+        del n
+        hw = H * Wd
+        o = torch.empty(T, H, Wd, c, dtype=F32, device=x.device)
+        s = torch.empty(hw, hw, dtype=F32, device=x.device)
+        vt = torch.empty(c, hw, dtype=F32, device=x.device)
+        for t in range(T):
+            qt, kt, vv = q[t].view(1, 1, hw, c), k[t].view(hw, c), v[t].view(hw, c)
+            lib.conv_tf32(qt, kt, None, TAPS_1, s.view(1, 1, hw, hw), T=1, H=1, W=hw, Cout=hw, tile_w=128)
+            lib.softmax_rows_(s, c ** -0.5)
+            lib.transpose_f32(vv, vt)
+            lib.conv_tf32(s.view(1, 1, hw, hw), vt, None, TAPS_1, o[t].view(1, 1, hw, c), T=1, H=1, W=hw, Cout=c, tile_w=128)
+        del q, k, v, s, vt
+        return self._conv(o, name + ".proj", TAPS_1, c, resid=x)
+
+    def _down(self, x, name, c, temporal):
+        T, H, Wd, _ = x.shape
+        s = lib.space_to_depth(x)
+        y = torch.empty(T, H // 2, Wd // 2, c, dtype=F32, device=x.device)
+        lib.conv_tf32(s, self.w[name + ".s2d.w"], self.w[name + ".s2d.b"], TAPS_S2D, y, T=T, H=H // 2, W=Wd // 2, Cout=c,
+                      tile_w=self._tile_w(Wd // 2))
+        del s
+        if temporal and T > 1:
+            t2 = (T - 1) // 2
+            out = torch.empty(1 + t2, H // 2, Wd // 2, c, dtype=F32, device=x.device)
+            out[0].copy_(y[0])
+            self._conv(y, name + ".time_conv", TAPS_T_STRIDE2, c, t_out=t2, t_stride=2, out=out[1:])
+            return out
+        return y
+
+    def _up(self, x, name, c, temporal):
+        T, H, Wd, _ = x.shape
+        if temporal and T > 1:
+            xt = torch.empty(1 + 2 * (T - 1), H, Wd, c, dtype=F32, device=x.device)
+            xt[0].copy_(x[0])
+            # frames 1.. through the temporal conv with an all-zero history; 2C output channels -> two frames of C
+            self._conv(x[1:], name + ".time_conv", TAPS_T_CAUSAL, 2 * c, out=xt[1:], t_mul=2, c_split=c)
+            x = xt
+            T = x.shape[0]
+        out = torch.empty(T, 2 * H, 2 * Wd, c // 2, dtype=F32, device=x.device)
+        for p in (0, 1):
+            for q in (0, 1):
+                lib.conv_tf32(x, self.w[f"{name}.par{p * 2 + q}.w"], self.w[name + ".par.b"], _taps_upsample(p, q), out,
+                              T=T, H=H, W=Wd, Cout=c // 2, sy=2, sx=2, oy=p, ox=q, tile_w=self._tile_w(Wd))
+        return out
+
+    def _run(self, plan, x, final_planar=None):
+        for kind, name, cin, cout in plan:
+            if kind == "conv":
+                x = self._conv(x, name, TAPS_333, cout)
+            elif kind == "res":
+                x = self._res(x, name, cin, cout)
+            elif kind == "attn":
+                x = self._attn(x, name, cin)
+            elif kind in ("down2d", "down3d"):
+                x = self._down(x, name, cin, kind == "down3d")
+            elif kind in ("up2d", "up3d"):
+                x = self._up(x, name, cin, kind == "up3d")
+            elif kind == "head":
+                y = lib.rms_norm_cl(x, self.w[name + ".0.gamma"])
+                if final_planar is not None:
+                    T, H, Wd, _ = y.shape
+                    lib.conv_tf32(y, self.w[name + ".2.w"], self.w[name + ".2.b"], TAPS_333, final_planar, T=T, H=H, W=Wd,
+                                  Cout=cout, planar_clamp=True, tile_w=self._tile_w(Wd))
+                    x = final_planar
+                else:
+                    x = self._conv(y, name + ".2", TAPS_333, cout)
+        return x
+
+    # ------------------------------------------------------------------------------ public surface
+    @torch.no_grad()
+    def encode(self, x: torch.Tensor):
+        """x [1,3,F,H,W] fp32 in [-1,1] -> object with ``.latent_dist.mode()`` = mean latents [1,z,f,H/8,W/8]."""
+        if not x.is_cuda:
+            raise lib.WfError("WfWanVAE runs on CUDA tensors only (no CPU fallback)")
+        assert x.shape[0] == 1 and x.shape[1] == 3
+        cl = lib.planar_to_cl(x[0].to(F32).contiguous(), 4)
+        h = self._run(self.enc_plan, cl)
+        h = self._conv(h, "conv1", TAPS_1, 2 * self.z_dim)
+        mu = lib.cl_to_planar(h, self.z_dim)
+        return SimpleNamespace(latent_dist=_Dist(mu.unsqueeze(0)))
+
+    @torch.no_grad()
+    def decode(self, z: torch.Tensor, return_dict: bool = False):
+        """z [1,z_dim,f,h,w] (un-normalised latents) -> ([1,3,4(f-1)+1,8h,8w] fp32 clamped to [-1,1],)"""
+        if not z.is_cuda:
+            raise lib.WfError("WfWanVAE runs on CUDA tensors only (no CPU fallback)")
+        assert z.shape[0] == 1 and z.shape[1] == self.z_dim
+        f, h, w = z.shape[2:]
+        cl = lib.planar_to_cl(z[0].to(F32).contiguous(), self.z_dim)
+        x = self._conv(cl, "conv2", TAPS_1, self.z_dim)
+        nt = 0
+        for i, up in enumerate(self.temperal_downsample):
+            nt += 1 if up else 0
+        F_out = (f - 1) * (2 ** nt) + 1
+        out = torch.empty(3, F_out, 8 * h, 8 * w, dtype=F32, device=z.device)
+        self._run(self.dec_plan, x, final_planar=out)
+        return (out.unsqueeze(0),)
+
+    @classmethod
+    def random_init(cls, device, seed: int = 4321, **kw):
+        """Random-init weights with the reference network's shapes."""
+        proto = cls.__new__(cls)
+        proto.dim = kw.get("dim", 96); proto.z_dim = kw.get("z_dim", 16)
+        proto.dim_mult = tuple(kw.get("dim_mult", (1, 2, 4, 4))); proto.num_res_blocks = kw.get("num_res_blocks", 2)
+        proto.temperal_downsample = list(kw.get("temporal_downsample", (False, True, True)))
+        enc, dec = proto._plans()
+        g = torch.Generator().manual_seed(seed)
+        sd = {}
+        def conv(name, cin, cout, k):
+            fan = cin * k[0] * k[1] * k[2] if len(k) == 3 else cin * k[0] * k[1]
+            sd[name + ".weight"] = torch.randn(cout, cin, *k, generator=g) / fan ** 0.5
+            sd[name + ".bias"] = 0.02 * torch.randn(cout, generator=g)
+        def gam(name, c, nd):
+            sd[name] = (1.0 + 0.05 * torch.randn(c, generator=g)).reshape(c, *([1] * nd))
+        for plan in (enc, dec):
+            for kind, name, cin, cout in plan:
+                if kind == "conv":
+                    conv(name, cin, cout, (3, 3, 3))
+                elif kind == "res":
+                    gam(name + ".residual.0.gamma", cin, 3); conv(name + ".residual.2", cin, cout, (3, 3, 3))
+                    gam(name + ".residual.3.gamma", cout, 3); conv(name + ".residual.6", cout, cout, (3, 3, 3))
+                    if cin != cout:
+                        conv(name + ".shortcut", cin, cout, (1, 1, 1))
+                elif kind == "attn":
+                    gam(name + ".norm.gamma", cin, 2); conv(name + ".to_qkv", cin, 3 * cin, (1, 1)); conv(name + ".proj", cin, cin, (1, 1))
+                elif kind in ("down2d", "down3d"):
+                    conv(name + ".resample.1", cin, cin, (3, 3))
+                    if kind == "down3d":
+                        conv(name + ".time_conv", cin, cin, (3, 1, 1))
+                elif kind in ("up2d", "up3d"):
+                    conv(name + ".resample.1", cin, cin // 2, (3, 3))
+                    if kind == "up3d":
+                        conv(name + ".time_conv", cin, 2 * cin, (3, 1, 1))
+                elif kind == "head":
+                    gam(name + ".0.gamma", cin, 3); conv(name + ".2", cin, cout, (3, 3, 3))
+        conv("conv1", 2 * proto.z_dim, 2 * proto.z_dim, (1, 1, 1)); conv("conv2", proto.z_dim, proto.z_dim, (1, 1, 1))
+        return cls(sd, device, **kw)
