@@ -128,7 +128,10 @@ def test_layer_norm_modulate(cuda, rows, D):
     want0 = (wan_dit.layer_norm(xb, 1e-6).float() * (1 + sc) + sh).to(BF)
     out0 = torch.empty(rows, D, dtype=BF, device=cuda)
     lib.layer_norm(xb.float().to(cuda), out0, 1e-6, scale=sc.to(cuda), shift=sh.to(cuda), round_norm_bf16=True)
-    bf16_close(out0, want0, ulps=2)   # the intermediate bf16 rounding can flip, which moves the result by up to 2 ulp
+    # here LN's value is rounded to bf16 BEFORE the modulation: where that rounding is a near-tie the two
+    # implementations may pick neighbouring bf16 values, which (1+scale) then carries into the result
+    d0 = (out0.float().cpu() - want0.float()).abs()
+    assert (d0 > 0).float().mean() < 5e-3 and d0.max() <= 2.0 ** -5, (float((d0 > 0).float().mean()), float(d0.max()))
     # affine (norm3) and bf16 input / fp32 output variants
     w, b = 1 + torch.randn(D, generator=g(20)) * 0.1, torch.randn(D, generator=g(21)) * 0.1
     want3 = F.layer_norm(x, (D,), w, b, 1e-6)
