@@ -25,6 +25,7 @@ class WfError(RuntimeError):
 
 _lib = None
 launches = 0     # kernels launched through this binding (bench.py's gpu_launches)
+timed_attention = None   # bench.py: a list here collects a CUDA-event pair around every self-attention launch
 
 _vp, _i, _f, _ll, _u = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_uint
 _SIGNATURES = {
@@ -141,8 +142,15 @@ def attention_bf16(q, k, v, out, heads: int, add_in=None, softmax_scale: Optiona
     for t in (q, k, v, out):
         assert t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1
     scale = softmax_scale if softmax_scale is not None else 128 ** -0.5
+    ev = None
+    if timed_attention is not None and q.shape[0] == k.shape[0]:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()          # on the current stream = the stream the kernel is launched on
     _call("wf_attention_bf16", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
           _p(add_in), add_in.stride(0) if add_in is not None else 0, q.shape[0], k.shape[0], heads, scale, _stream())
+    if ev is not None:
+        ev[1].record()
+        timed_attention.append(ev)
     return out
 
 

@@ -38,90 +38,118 @@ def prepare_condition(vae, image: torch.Tensor, num_frames: int, height: int, wi
     return torch.cat([mask, lat], dim=1)
 
 
+class GuidedSampler:
+    """The loop of pipeline_wan_i2v_clean.py:556-728 as an object: ``begin()`` then ``step(i)`` for every
+    timestep.  ``denoise_loop`` below is the plain loop; bench.py drives ``step`` itself so that it can place
+    host<->device copies around each step."""
+
+    def __init__(self, transformer, vae, scheduler, guidance_scale: float, guided: bool = False, resample_steps: int = 1,
+                 guide_steps: int = 20, omega: float = 1.8, omega_resample: float = 1.0, resample_round: int = 20,
+                 use_pca_channel_selection: bool = False, static: bool = False,
+                 generator: Optional[torch.Generator] = None):
+        self.transformer, self.vae, self.scheduler = transformer, vae, scheduler
+        self.guidance_scale, self.guided, self.resample_steps = guidance_scale, guided, resample_steps
+        self.guide_steps, self.omega, self.omega_resample, self.resample_round = guide_steps, omega, omega_resample, resample_round
+        self.use_pca_channel_selection, self.static, self.generator = use_pca_channel_selection, static, generator
+        self.forwards = 0
+
+    def begin(self, num_inference_steps: int, device):
+        self.scheduler.set_timesteps(num_inference_steps, device=device)
+        if not hasattr(self.scheduler, "derivative_history"):
+            self.scheduler.derivative_history = []
+        return self.scheduler.timesteps
+
+    @torch.no_grad()
+    def step(self, i: int, latents, condition, prompt_embeds, negative_prompt_embeds, image_embeds, video_ref=None,
+             mask=None):
+        sch, tr = self.scheduler, self.transformer
+        device, tdtype = latents.device, tr.dtype
+        t = sch.timesteps[i]
+        do_cfg = self.guidance_scale > 1
+        sch.derivative_history = []
+        x0, out = None, None
+        for r in range(self.resample_steps):
+            if r > 0:
+                sch.set_resample_mode(True)
+                t_model = sch.get_resample_timestep(i).expand(latents.shape[0]).to(device=device)
+                sch._step_index -= 1
+                if sch.lower_order_nums > 0 and sch.last_lower_order_nums < sch.config.solver_order:
+                    sch.lower_order_nums -= 1
+                sch.this_order = sch.last_this_order
+            else:
+                sch.set_resample_mode(False)
+                t_model = t.expand(latents.shape[0])
+            model_in = torch.cat([latents, condition], dim=1).to(tdtype)
+            v = tr(hidden_states=model_in, timestep=t_model, encoder_hidden_states=prompt_embeds,
+                   encoder_hidden_states_image=image_embeds, attention_kwargs=None, return_dict=False)[0]
+            self.forwards += 1
+            if do_cfg:
+                v_u = tr(hidden_states=model_in, timestep=t_model, encoder_hidden_states=negative_prompt_embeds,
+                         encoder_hidden_states_image=image_embeds, attention_kwargs=None, return_dict=False)[0]
+                self.forwards += 1
+                v = lib.cfg_combine(v.contiguous(), v_u.contiguous(), self.guidance_scale)
+                if r < 1:
+                    sch.derivative_history.append(v)
+            out = sch.step(v, t, latents, mask=mask, guided=self.guided and i < self.guide_steps and r < self.resample_steps,
+                           video_latents=video_ref, vae=self.vae, resampling=r > 0, return_dict=True, current_step=i,
+                           resample_count=self.resample_steps, is_resample_round=i < self.resample_round,
+                           use_pca_channel_selection=self.use_pca_channel_selection, static=self.static)
+            if hasattr(out, "pred_x0"):
+                x0 = out.pred_x0
+            if i >= self.resample_round:
+                break
+            if r < self.resample_steps - 1 and x0 is not None:
+                if self.generator is not None:   # CPU generator: the noise stream is part of the result (:643-645)
+                    noise = torch.randn(x0.shape, generator=self.generator).pin_memory().to(device=device, non_blocking=True)
+                else:
+                    noise = torch.randn(x0.shape, device=device)
+                t_noise = sch.get_resample_timestep(i)
+                if t_noise.dim() == 0:
+                    t_noise = t_noise.unsqueeze(0)
+                latents = sch.add_noise(x0, noise, t_noise.to(device=device), r, use_resample_sigma=True)
+
+        if len(sch.derivative_history) > 1:                 # DSG (:664-708)
+            g, w = sch.derivative_history[-1], sch.derivative_history[0]
+            if i >= self.guide_steps:
+                self.omega = self.omega_resample            # sticks for the rest of the run (:678-679)
+            better = lib.dsg(g.contiguous(), w.contiguous(), self.omega)
+            sch._step_index -= 1
+            if sch.lower_order_nums > 0 and sch.last_lower_order_nums < sch.config.solver_order:
+                sch.lower_order_nums -= 1
+            m = sch.convert_model_output(better, sample=latents)
+            sch.last_sample = latents
+            sch.model_outputs[-1] = m
+            latents = sch.multistep_uni_p_bh_update(model_output=better, sample=latents, order=sch.this_order)
+            sch._step_index += 1
+            if 0 <= sch.lower_order_nums < sch.config.solver_order:
+                sch.lower_order_nums += 1
+            latents = latents.to(dtype=tdtype)
+        else:
+            latents = out.prev_sample
+        sch.set_resample_mode(False)
+        return latents
+
+
 @torch.no_grad()
 def denoise_loop(transformer, vae, scheduler, latents, condition, prompt_embeds, negative_prompt_embeds,
                  image_embeds, num_inference_steps: int, guidance_scale: float, video_ref=None, mask=None,
                  guided: bool = False, resample_steps: int = 1, guide_steps: int = 20, omega: float = 1.8,
                  omega_resample: float = 1.0, resample_round: int = 20, use_pca_channel_selection: bool = False,
                  static: bool = False, generator: Optional[torch.Generator] = None,
-                 on_step: Optional[Callable] = None, max_steps: Optional[int] = None,
-                 timesteps_are_set: bool = False) -> torch.Tensor:
-    """The loop of pipeline_wan_i2v_clean.py:556-728.  ``latents`` [1,16,f,h,w] fp32 on the device."""
+                 on_step: Optional[Callable] = None, max_steps: Optional[int] = None) -> torch.Tensor:
+    """``latents`` [1,16,f,h,w] fp32 on the device -> latents after the last step."""
     device = latents.device
-    tdtype = transformer.dtype
-    do_cfg = guidance_scale > 1
-    if not timesteps_are_set:
-        scheduler.set_timesteps(num_inference_steps, device=device)
-    timesteps = scheduler.timesteps
-    if not hasattr(scheduler, "derivative_history"):
-        scheduler.derivative_history = []
+    sampler = GuidedSampler(transformer, vae, scheduler, guidance_scale, guided, resample_steps, guide_steps, omega,
+                            omega_resample, resample_round, use_pca_channel_selection, static, generator)
+    timesteps = sampler.begin(num_inference_steps, device)
     if video_ref is not None and guided:
         video_ref = video_ref.to(device=device, dtype=torch.float32)
     if mask is not None and guided:
         mask = mask.to(device)
-    out = None
-    for i, t in enumerate(timesteps):
+    for i in range(len(timesteps)):
         if max_steps is not None and i >= max_steps:
             break
-        scheduler.derivative_history = []
-        x0 = None
-        for r in range(resample_steps):
-            if r > 0:
-                scheduler.set_resample_mode(True)
-                t_model = scheduler.get_resample_timestep(i).expand(latents.shape[0]).to(device=device)
-                scheduler._step_index -= 1
-                if scheduler.lower_order_nums > 0 and scheduler.last_lower_order_nums < scheduler.config.solver_order:
-                    scheduler.lower_order_nums -= 1
-                scheduler.this_order = scheduler.last_this_order
-            else:
-                scheduler.set_resample_mode(False)
-                t_model = t.expand(latents.shape[0])
-            model_in = torch.cat([latents, condition], dim=1).to(tdtype)
-            v = transformer(hidden_states=model_in, timestep=t_model, encoder_hidden_states=prompt_embeds,
-                            encoder_hidden_states_image=image_embeds, attention_kwargs=None, return_dict=False)[0]
-            if do_cfg:
-                v_u = transformer(hidden_states=model_in, timestep=t_model, encoder_hidden_states=negative_prompt_embeds,
-                                  encoder_hidden_states_image=image_embeds, attention_kwargs=None, return_dict=False)[0]
-                v = lib.cfg_combine(v.contiguous(), v_u.contiguous(), guidance_scale)
-                if r < 1:
-                    scheduler.derivative_history.append(v)
-            out = scheduler.step(v, t, latents, mask=mask, guided=guided and i < guide_steps and r < resample_steps,
-                                 video_latents=video_ref, vae=vae, resampling=r > 0, return_dict=True, current_step=i,
-                                 resample_count=resample_steps, is_resample_round=i < resample_round,
-                                 use_pca_channel_selection=use_pca_channel_selection, static=static)
-            if hasattr(out, "pred_x0"):
-                x0 = out.pred_x0
-            if i >= resample_round:
-                break
-            if r < resample_steps - 1 and x0 is not None:
-                if generator is not None:       # CPU generator: the noise stream is part of the result (:643-645)
-                    noise = torch.randn(x0.shape, generator=generator).pin_memory().to(device=device, non_blocking=True)
-                else:
-                    noise = torch.randn(x0.shape, device=device)
-                t_noise = scheduler.get_resample_timestep(i)
-                if t_noise.dim() == 0:
-                    t_noise = t_noise.unsqueeze(0)
-                latents = scheduler.add_noise(x0, noise, t_noise.to(device=device), r, use_resample_sigma=True)
-
-        if len(scheduler.derivative_history) > 1:           # DSG (:664-708)
-            g, w = scheduler.derivative_history[-1], scheduler.derivative_history[0]
-            if i >= guide_steps:
-                omega = omega_resample                      # sticks for the rest of the run (:678-679)
-            better = lib.dsg(g.contiguous(), w.contiguous(), omega)
-            scheduler._step_index -= 1
-            if scheduler.lower_order_nums > 0 and scheduler.last_lower_order_nums < scheduler.config.solver_order:
-                scheduler.lower_order_nums -= 1
-            m = scheduler.convert_model_output(better, sample=latents)
-            scheduler.last_sample = latents
-            scheduler.model_outputs[-1] = m
-            latents = scheduler.multistep_uni_p_bh_update(model_output=better, sample=latents, order=scheduler.this_order)
-            scheduler._step_index += 1
-            if 0 <= scheduler.lower_order_nums < scheduler.config.solver_order:
-                scheduler.lower_order_nums += 1
-            latents = latents.to(dtype=tdtype)
-        else:
-            latents = out.prev_sample
-        scheduler.set_resample_mode(False)
+        latents = sampler.step(i, latents, condition, prompt_embeds, negative_prompt_embeds, image_embeds, video_ref, mask)
         if on_step is not None:
             on_step(i, latents)
     return latents
