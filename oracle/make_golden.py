@@ -1,0 +1,138 @@
+"""Generate tests/golden/wan_golden.pt from the UNMODIFIED reference (build container only).
+
+TEST INFRASTRUCTURE ONLY.  The reference pins nothing itself (no tests, no golden vectors), so the
+fixtures are outputs of the reference's own modules, imported from /root/reference through oracle/ref_shim.py, on
+inputs and random-init weights that are reproducible from seeds (oracle.*.init_params, worldforge_b200.synth):
+
+  dit_fp32    WanModel.forward in fp32                                   (wan/modules/model.py:493-582)
+  dit_amp     the same under bf16 autocast with the module's fp32 islands (the GPU dtype flow, run on the CPU)
+  vae_mu/dec  WanVAE_.encode / .decode, chunked with the feature cache   (wan/modules/vae.py:516-568)
+  sched_*     14 guided steps (IRR + FLF + DSG) driven through the reference's UniPCMultistepScheduler
+              (utils/scheduling_unipc_multistep_clean.py), per-step latents and the FLF channel choices
+
+Run:  python -m oracle.make_golden     (the GPU box never runs this; it only reads the committed file)
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import adapters, pipeline, ref_shim, wan_dit, wan_vae  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden", "wan_golden.pt")
+
+DIT_CFG = dict(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=64, text_len=16, img_dim=32, img_len=5, freq_dim=32)
+DIT_GRID = (3, 8, 12)
+SCHED_DIT = dict(dim=128, ffn_dim=256, num_heads=1, num_layers=1, text_dim=32, text_len=8, img_dim=16, img_len=3, freq_dim=32)
+SCHED_KNOBS = dict(guided=True, resample_steps=2, guide_steps=12, omega=4.0, omega_resample=4.0, resample_round=13,
+                   use_pca_channel_selection=True, static=True)
+
+
+def dit_inputs():
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(36, *DIT_GRID, generator=g)
+    ctx = torch.randn(16, 64, generator=g)
+    clip = torch.randn(5, 32, generator=g)
+    return x, torch.tensor([737]), ctx, clip
+
+
+def ref_dit(amp: bool):
+    cfg = wan_dit.DitConfig(**DIT_CFG)
+    P = wan_dit.init_params(cfg, 7)
+    mod = ref_shim.load_wan_model_module(cpu_autocast=amp)
+    mod.T5_CONTEXT_TOKEN_NUMBER = cfg.text_len      # the I2V cross-attention splits image / text tokens at this constant
+    m = mod.WanModel(model_type="i2v", in_dim=36, dim=cfg.dim, ffn_dim=cfg.ffn_dim, freq_dim=cfg.freq_dim,
+                     text_dim=cfg.text_dim, out_dim=16, num_heads=cfg.num_heads, num_layers=cfg.num_layers, text_len=cfg.text_len)
+    m.img_emb = mod.MLPProj(cfg.img_dim, cfg.dim)     # the image-embedding width is hard-coded to 1280 in the constructor
+    m.load_state_dict({k: v.clone() for k, v in P.items()})
+    m.eval()
+    x, t, ctx, clip = dit_inputs()
+    L = DIT_GRID[0] * DIT_GRID[1] * DIT_GRID[2] // 4
+    with torch.no_grad():
+        if amp:
+            bf = torch.bfloat16
+            with torch.autocast("cpu", dtype=bf):
+                return m([x[:16].to(bf)], t, [ctx.to(bf)], seq_len=L, clip_fea=clip.unsqueeze(0).to(bf), y=[x[16:].to(bf)])[0]
+        return m([x[:16]], t, [ctx], seq_len=L, clip_fea=clip.unsqueeze(0), y=[x[16:]])[0]
+
+
+def ref_vae():
+    cfg = wan_vae.VaeConfig(dim=16)
+    P = wan_vae.init_params(cfg, 5)
+    vm = ref_shim.load_wan_vae_module()
+    m = vm.WanVAE_(dim=16, z_dim=16, dim_mult=[1, 2, 4, 4], num_res_blocks=2, attn_scales=[],
+                   temperal_downsample=[False, True, True], dropout=0.0).eval()
+    sd = m.state_dict()
+    m.load_state_dict({k: P[k].reshape(sd[k].shape) for k in sd})
+    g = torch.Generator().manual_seed(1)
+    video = torch.rand(3, 9, 32, 48, generator=g) * 2 - 1
+    z = torch.randn(16, 3, 4, 6, generator=g)
+    with torch.no_grad():
+        mu = m.encode(video.unsqueeze(0), [0.0, 1.0])[0]
+        dec = m.decode(z.unsqueeze(0), [0.0, 1.0])[0].clamp(-1, 1)
+    return mu, dec
+
+
+def sched_setup():
+    from worldforge_b200 import synth
+    dcfg = wan_dit.DitConfig(**SCHED_DIT)
+    vcfg = wan_vae.VaeConfig(dim=8)
+    PD, PV = wan_dit.init_params(dcfg, 1), wan_vae.init_params(vcfg, 2)
+    inp = synth.make_inputs(9, 64, 96, text_len=8, text_dim=32, img_len=3, img_dim=16)
+    return dcfg, vcfg, PD, PV, inp
+
+
+def run_sched(sched, steps=14):
+    dcfg, vcfg, PD, PV, inp = sched_setup()
+    hist = []
+    pipeline.denoise_loop(adapters.OracleTransformer(PD, dcfg, amp=True), adapters.OracleVAE(PV, vcfg), sched,
+                          inp.latents.clone(), inp.condition, inp.prompt_embeds, inp.negative_prompt_embeds, inp.image_embeds,
+                          steps, 4.0, video_ref=inp.video_ref, mask=inp.mask, generator=torch.Generator().manual_seed(42),
+                          on_step=lambda i, l: hist.append(l.clone()), **SCHED_KNOBS)
+    return hist
+
+
+def ref_sched():
+    sm = ref_shim.load_scheduler_module()
+    s = sm.UniPCMultistepScheduler(num_train_timesteps=1000, solver_order=2, prediction_type="flow_prediction",
+                                   use_flow_sigmas=True, flow_shift=3.0)
+    # record the FLF choices the reference's selector makes
+    log = []
+    orig = sm.VideoMotionPCASelector.select_motion_related_channels
+    def spy(self, *a, **k):
+        r = orig(self, *a, **k)
+        log.append((k.get("current_step"), list(r)))
+        return r
+    sm.VideoMotionPCASelector.select_motion_related_channels = spy
+    hist = run_sched(s)
+    s50 = sm.UniPCMultistepScheduler(num_train_timesteps=1000, solver_order=2, prediction_type="flow_prediction",
+                                     use_flow_sigmas=True, flow_shift=3.0)
+    s50.set_timesteps(50)
+    return hist, log, dict(timesteps=s50.timesteps.clone(), sigmas=s50.sigmas.clone(),
+                           resample_timesteps=s50.resample_timesteps.clone())
+
+
+def main():
+    assert ref_shim.available(), "/root/reference is not mounted"
+    torch.manual_seed(0)
+    mu, dec = ref_vae()
+    hist, flf_log, tables = ref_sched()
+    gold = {
+        "dit_fp32": ref_dit(False).clone(), "dit_amp": ref_dit(True).float().clone(),
+        "vae_mu": mu.clone(), "vae_dec": dec.clone(),
+        "sched_latents": torch.stack([h.float() for h in hist]), "sched_dtype": str(hist[-1].dtype), "sched_flf": flf_log,
+        "sched_tables_50": tables,
+        "meta": {"reference_commit": "3314da5", "torch": torch.__version__, "generator": "oracle/make_golden.py"},
+    }
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    torch.save(gold, OUT)
+    print("wrote", OUT, os.path.getsize(OUT), "bytes")
+
+
+if __name__ == "__main__":
+    main()

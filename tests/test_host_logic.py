@@ -1,0 +1,167 @@
+"""Host-side logic of the engine that needs no GPU: schedules and solver coefficients, FLF policy and flow metrics,
+weight re-packing for the fused convolution forms, RoPE tables, key-name mapping, synthetic inputs."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import flf as oflf
+from oracle import pipeline as opipe
+from oracle import unipc, wan_dit, wan_vae
+from worldforge_b200 import flf_select, scheduler as wsched, synth, transformer as wtr, vae as wvae
+
+
+@pytest.mark.parametrize("n,shift", [(50, 3.0), (10, 5.0), (2, 3.0)])
+def test_schedule_tables(n, shift):
+    a, b = unipc.OracleUniPC(flow_shift=shift), wsched.WfUniPCScheduler(flow_shift=shift)
+    a.set_timesteps(n); b.set_timesteps(n)
+    assert torch.equal(a.timesteps, b.timesteps) and torch.equal(a.sigmas, b.sigmas)
+    assert torch.equal(a.resample_sigmas, b.resample_sigmas) and torch.equal(a.resample_timesteps, b.resample_timesteps)
+    for i in (0, n - 1, n + 3):
+        assert int(a.get_resample_timestep(i)) == int(b.get_resample_timestep(i))
+
+
+def test_unip_coefficients_reproduce_the_oracle_update_on_cpu():
+    """With fp32 tensors every coefficient convention collapses to plain fp32 arithmetic, so the closed form
+    c_x*x - c_m0*m0 - c_res*0.5*(m1-m0)/r1 must reproduce the oracle's update."""
+    s = unipc.OracleUniPC(flow_shift=3.0)
+    s.set_timesteps(10)
+    g = torch.Generator().manual_seed(0)
+    x, m0, m1 = (torch.randn(1, 4, 2, 3, 3, generator=g) for _ in range(3))
+    for idx, order in [(0, 1), (4, 2), (9, 1)]:
+        s._step_index = idx
+        s.model_outputs = [m1, m0]
+        want = s.multistep_uni_p_bh_update(model_output=None, sample=x, order=order)
+        c_x, c_m0, rk, c_res = wsched.unip_coefficients(s.sigmas, None, idx, order, False)
+        got = c_x * x - c_m0 * m0
+        if order == 2:
+            got = got - c_res * (0.5 * ((m1 - m0) / rk))
+        torch.testing.assert_close(got, want, rtol=1e-6, atol=1e-6)
+    assert wsched.unip_coefficients(s.sigmas, None, 9, 1, False)[:2] == (0.0, -1.0)     # last step: x' = m0
+
+
+def test_scheduler_state_machine_matches_oracle_without_tensors():
+    """Order / index bookkeeping over a guided run (the pipeline pokes this state directly)."""
+    class Fake:                                   # tensor stand-in: the bookkeeping must not depend on values
+        dtype = torch.float32
+    for cls in (unipc.OracleUniPC, wsched.WfUniPCScheduler):
+        s = cls(flow_shift=3.0)
+        s.set_timesteps(6)
+        s.convert_model_output = lambda v, sample=None, **k: 0.0
+        s.multistep_uni_p_bh_update = lambda model_output=None, sample=None, order=None, **k: order
+        trace = []
+        for i, t in enumerate(s.timesteps):
+            for r in range(2 if i < 4 else 1):
+                if r > 0:
+                    s.set_resample_mode(True)
+                    s._step_index -= 1
+                    if s.lower_order_nums > 0 and s.last_lower_order_nums < 2:
+                        s.lower_order_nums -= 1
+                    s.this_order = s.last_this_order
+                else:
+                    s.set_resample_mode(False)
+                out = s.step(0.0, t, 0.0, resampling=r > 0, is_resample_round=i < 4)
+                trace.append((i, r, s._step_index, s.this_order, s.lower_order_nums, out.prev_sample))
+            s.set_resample_mode(False)
+        if cls is unipc.OracleUniPC:
+            want = trace
+    assert trace == want
+    assert [t[3] for t in want if t[1] == 0] == [1, 2, 2, 2, 2, 1]       # first and last step are first order
+
+
+def test_flf_policy_and_metrics_match_oracle():
+    rng = np.random.RandomState(0)
+    for step in (2, 5, 6, 10, 11, 30):
+        for _ in range(20):
+            sc = rng.rand(16).tolist()
+            assert flf_select.selection_policy(sc, step) == oflf.policy(sc, step)
+    tied = [0.5] * 16
+    assert flf_select.selection_policy(tied, 20) == oflf.policy(tied, 20) and len(oflf.policy(tied, 20)) == 2
+    g = torch.Generator().manual_seed(1)
+    a, b = torch.randn(20, 2, 12, 16, generator=g) * 3, torch.randn(20, 2, 12, 16, generator=g) * 3
+    assert flf_select.flow_similarity(a, b) == oflf.flow_similarity(a.unsqueeze(0), b.unsqueeze(0))
+
+
+def test_farneback_front_end_matches_oracle():
+    import cv2
+    v = np.arange(256, dtype=np.uint8).reshape(16, 16)
+    assert np.array_equal(cv2.cvtColor(np.repeat(v[:, :, None], 3, axis=2), cv2.COLOR_RGB2GRAY), v)   # RGB2GRAY(v,v,v) == v
+    u8 = (np.random.RandomState(2).rand(2, 4, 24, 32) * 255).astype(np.uint8)
+    sel = flf_select.FlowChannelSelector(threads=2)
+    got = sel._flows(u8)
+    for c in range(2):
+        assert torch.equal(got[c], oflf.farneback_flows(u8[c])[0])
+
+
+def test_upsample_conv_as_four_parity_convs():
+    """nearest-exact 2x upsample + 3x3 conv == for each output parity a 2x2-tap conv on the low-res input."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 6, 5, 7, generator=g)           # [T, C, H, W]
+    w = torch.randn(4, 6, 3, 3, generator=g)
+    want = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest-exact"), w, padding=1)
+    ws = wvae._w_upsample_parity(w)
+    out = torch.zeros_like(want)
+    for p in (0, 1):
+        for q in (0, 1):
+            taps = wvae._taps_upsample(p, q)
+            wp = ws[p * 2 + q][:, :6].reshape(4, 4, 6)  # [tap, Co, Ci]
+            for k, (_, dy, dx) in enumerate(taps):
+                xs = F.pad(x, (1, 1, 1, 1))[:, :, 1 + dy:1 + dy + 5, 1 + dx:1 + dx + 7]
+                out[:, :, p::2, q::2] += torch.einsum("oc,tchw->tohw", wp[k], xs)
+    torch.testing.assert_close(out, want, rtol=1e-5, atol=1e-5)
+
+
+def test_stride2_conv_as_space_to_depth_conv():
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 4, 8, 12, generator=g)
+    w = torch.randn(5, 4, 3, 3, generator=g)
+    want = F.conv2d(F.pad(x, (0, 1, 0, 1)), w, stride=2)
+    ws = wvae._w_s2d(w).reshape(2, 2, 5, 16)            # [a, b, Co, (p,q,c)]
+    s2d = x.reshape(2, 4, 4, 2, 6, 2).permute(0, 3, 5, 1, 2, 4).reshape(2, 16, 4, 6)   # channel = (p*2+q)*4 + c
+    out = torch.zeros_like(want)
+    sp = F.pad(s2d, (0, 1, 0, 1))
+    for a in range(2):
+        for b in range(2):
+            out += torch.einsum("oc,tchw->tohw", ws[a, b], sp[:, :, a:a + 4, b:b + 6])
+    torch.testing.assert_close(out, want, rtol=1e-5, atol=1e-5)
+
+
+def test_rope_table_and_key_names():
+    grid = (3, 4, 5)
+    ang = wan_dit.rope_angles(128, grid)
+    tab = wtr.rope_table(grid)
+    assert torch.equal(tab[..., 0], ang.real) and torch.equal(tab[..., 1], ang.imag)
+    cfg = wan_dit.DitConfig(dim=128, ffn_dim=256, num_heads=1, num_layers=1, text_dim=32, text_len=8, img_dim=16, img_len=3, freq_dim=32)
+    P = wan_dit.init_params(cfg, 0)
+    assert wtr.to_vendored_names(P) is P
+    diff = {"blocks.0.attn1.to_q.weight": 1, "blocks.0.norm2.weight": 2, "blocks.0.scale_shift_table": 3, "scale_shift_table": 4,
+            "condition_embedder.time_proj.bias": 5, "proj_out.weight": 6, "blocks.0.attn2.add_k_proj.bias": 7,
+            "blocks.0.ffn.net.0.proj.weight": 8, "patch_embedding.weight": 9}
+    m = wtr.to_vendored_names(diff)
+    assert m == {"blocks.0.self_attn.q.weight": 1, "blocks.0.norm3.weight": 2, "blocks.0.modulation": 3, "head.modulation": 4,
+                 "time_projection.1.bias": 5, "head.head.weight": 6, "blocks.0.cross_attn.k_img.bias": 7,
+                 "blocks.0.ffn.0.weight": 8, "patch_embedding.weight": 9}
+    assert set(wan_dit.param_shapes(cfg)) == set(P)
+
+
+def test_synthetic_inputs_and_soften_mask():
+    inp = synth.make_inputs(9, 64, 96, text_len=8, text_dim=32, img_len=3, img_dim=16)
+    assert inp.latents.shape == (1, 16, 3, 8, 12) and inp.condition.shape == (1, 20, 3, 8, 12)
+    assert torch.equal(inp.condition[:, :4], opipe.first_frame_mask(9, 8, 12))
+    assert inp.video_ref.shape == (1, 3, 9, 64, 96) and 0 <= inp.video_ref.min() and inp.video_ref.max() <= 1
+    assert inp.mask.shape == (1, 1, 9, 64, 96) and (inp.mask[:, :, 0] == 1).all()
+    m = np.zeros((2, 32, 40), np.float32); m[1, :, :20] = 1
+    s = synth.soften_mask(m, 15, "sine")
+    assert (s[0] == 0).all() and s[1, 0, 0] == 1 and 0 < s[1, 0, 19] < 0.2 and (s[1, :, 20:] == 0).all()
+    assert np.all(np.diff(s[1, 0, :20]) <= 1e-6)          # ramps down towards the boundary
+    with pytest.raises(ValueError):
+        synth.soften_mask(m, 15, "nope")
+    assert (torch.roll(inp.video_ref[0, :, 0], 2, dims=2) == inp.video_ref[0, :, 1]).all()     # 2 px per frame
+
+
+def test_latent_stats_rounding():
+    mh, sh = wsched.latent_stats(wan_vae.LATENTS_MEAN, wan_vae.LATENTS_STD, torch.bfloat16)
+    assert mh[0] == float(torch.tensor(wan_vae.LATENTS_MEAN[0]).bfloat16())
+    assert sh[3] == float((1.0 / torch.tensor(wan_vae.LATENTS_STD[3]).bfloat16()).float())
+    m32, s32 = wsched.latent_stats(wan_vae.LATENTS_MEAN, wan_vae.LATENTS_STD, torch.float32)
+    assert abs(s32[3] - 1 / 2.6558) < 1e-7
