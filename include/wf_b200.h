@@ -75,9 +75,10 @@ int wf_rms_norm_rope(void* x, int ldx, const float* weight, const double* rope, 
 int wf_patchify(const void* hidden, void* cols, int C, int F, int H, int W, void* stream);
 
 /* Head.forward + unpatchify (model.py:337-347, 584-607): fp32 LN, modulation, fp32 Linear(D -> 4*Cout),
- * scatter to out fp32 [Cout, F, 2*GH, 2*GW]. */
+ * scatter to out fp32 [Cout, F, 2*GH, 2*GW].  x holds the L tokens starting at global token tok_offset
+ * (0 and L = F*GH*GW on one GPU; a contiguous shard under sequence parallelism). */
 int wf_dit_head(const float* x, int ldx, int L, int D, const float* scale, const float* shift, const float* w,
-                const float* b, int Cout, float* out, int F, int GH, int GW, float eps, void* stream);
+                const float* b, int Cout, float* out, int F, int GH, int GW, float eps, int tok_offset, void* stream);
 
 /* fp32 matrix-vector product with optional SiLU on the input and/or output: the time_embedding /
  * time_projection MLPs at batch 1 (model.py:546-550). */

@@ -200,6 +200,7 @@ struct HeadArgs {
   int NO;                                   // 4 * Cout
   float* out; int Cout, F, GH, GW;          // out [Cout, F, 2*GH, 2*GW]
   float eps;
+  int tok_offset;                           // global index of x's first row (sequence-parallel shards)
 };
 
 __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadArgs p) {
@@ -244,7 +245,8 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadArgs p) {
       if (lane == 0 && tok < p.L) {
         v += p.b[o];
         const int c = o % p.Cout, pq = o / p.Cout, ph = pq >> 1, pw = pq & 1;
-        const int gw = tok % p.GW, gh = (tok / p.GW) % p.GH, f = tok / (p.GW * p.GH);
+        const int gt = tok + p.tok_offset;
+        const int gw = gt % p.GW, gh = (gt / p.GW) % p.GH, f = gt / (p.GW * p.GH);
         p.out[((static_cast<size_t>(c) * p.F + f) * (2 * p.GH) + 2 * gh + ph) * (2 * p.GW) + 2 * gw + pw] = v;
       }
     }
@@ -349,11 +351,11 @@ extern "C" int wf_patchify(const void* hidden, void* cols, int C, int F, int H, 
 
 extern "C" int wf_dit_head(const float* x, int ldx, int L, int D, const float* scale, const float* shift,
                            const float* w, const float* b, int Cout, float* out, int F, int GH, int GW, float eps,
-                           void* stream) {
+                           int tok_offset, void* stream) {
   WF_REQUIRE(x && scale && shift && w && b && out, "wf_dit_head: null pointer");
-  WF_REQUIRE(L == F * GH * GW, "wf_dit_head: token count does not match the grid");
+  WF_REQUIRE(tok_offset >= 0 && tok_offset + L <= F * GH * GW, "wf_dit_head: token range does not fit the grid");
   WF_REQUIRE(D % 128 == 0 && ldx % 4 == 0, "wf_dit_head: dim must be a multiple of 128");
-  HeadArgs a{x, ldx, L, D, scale, shift, w, b, 4 * Cout, out, Cout, F, GH, GW, eps};
+  HeadArgs a{x, ldx, L, D, scale, shift, w, b, 4 * Cout, out, Cout, F, GH, GW, eps, tok_offset};
   const size_t shmem = static_cast<size_t>(HEAD_TOK) * D * sizeof(float);
   static size_t configured = 0;
   if (shmem > configured) {

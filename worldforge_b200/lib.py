@@ -34,7 +34,7 @@ _SIGNATURES = {
     "wf_layer_norm": [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp],
     "wf_rms_norm_rope": [_vp, _i, _vp, _vp, _i, _i, _f, _vp],
     "wf_patchify": [_vp, _vp, _i, _i, _i, _i, _vp],
-    "wf_dit_head": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _f, _vp],
+    "wf_dit_head": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _f, _i, _vp],
     "wf_gemv_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "wf_gelu_erf_bf16": [_vp, _ll, _vp],
     "wf_time_sinusoid": [_vp, _vp, _i, _vp],
@@ -182,14 +182,14 @@ def patchify(hidden, cols):
     return cols
 
 
-def dit_head(x, scale, shift, w, b, out, grid, eps: float):
+def dit_head(x, scale, shift, w, b, out, grid, eps: float, tok_offset: int = 0):
     L, D = x.shape
     F_, GH, GW = grid
     cout = w.shape[0] // 4
     assert x.dtype == torch.float32 and x.stride(1) == 1 and w.is_contiguous() and w.dtype == torch.float32
     assert out.dtype == torch.float32 and out.is_contiguous() and out.shape == (cout, F_, 2 * GH, 2 * GW)
     _call("wf_dit_head", _p(x), x.stride(0), L, D, _p(scale), _p(shift), _p(w), _p(b), cout, _p(out), F_, GH, GW, eps,
-          _stream())
+          tok_offset, _stream())
     return out
 
 

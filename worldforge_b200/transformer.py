@@ -143,6 +143,7 @@ class WfWanTransformer:
         self._ctx_cache = {}
         self.cache_context = True
         self.calls = 0
+        self.sp = None
 
     def to(self, *a, **k):          # survives pipe.to("cuda")
         return self
@@ -235,16 +236,17 @@ class WfWanTransformer:
         return self
 
     # ------------------------------------------------------------------------------ buffers
-    def _buffers(self, L: int):
-        if L not in self._buf:
+    def _buffers(self, L: int, Ll: int):
+        """L: tokens of the whole clip; Ll: tokens this rank owns (L / sequence-parallel world size)."""
+        if (L, Ll) not in self._buf:
             c, dev = self.cfg, self.device
             e = lambda *s, dt=BF: torch.empty(*s, dtype=dt, device=dev)
-            self._buf[L] = SimpleNamespace(
-                cols=e(L, c.in_dim * 4), x=e(L, c.dim, dt=F32), h=e(L, c.dim), qkv=e(L, 3 * c.dim), att=e(L, c.dim),
-                cq=e(L, c.dim), ca_img=e(L, c.dim), ff=e(L, c.ffn_dim),
+            self._buf[(L, Ll)] = SimpleNamespace(
+                cols=e(L, c.in_dim * 4), x=e(Ll, c.dim, dt=F32), h=e(Ll, c.dim), qkv=e(Ll, 3 * c.dim), att=e(Ll, c.dim),
+                cq=e(Ll, c.dim), ca_img=e(Ll, c.dim), ff=e(Ll, c.ffn_dim),
                 sinus=e(c.freq_dim, dt=F32), e1=e(c.dim, dt=F32), e=e(c.dim, dt=F32), e0=e(6 * c.dim, dt=F32),
                 mod=e(c.num_layers, 6, c.dim, dt=F32), hmod=e(2, c.dim, dt=F32))
-        return self._buf[L]
+        return self._buf[(L, Ll)]
 
     def _context_kv(self, ctx_txt_in: torch.Tensor, ctx_img_in: torch.Tensor):
         """Per-block cross-attention K|V of the text and image context.  They depend only on the
@@ -294,14 +296,19 @@ class WfWanTransformer:
         grid = (Fr, H // 2, W // 2)
         L = grid[0] * grid[1] * grid[2]
         D, nh = c.dim, c.num_heads
-        B = self._buffers(L)
-        if grid not in self._rope:
-            self._rope[grid] = rope_table(grid).to(self.device)
-        rope = self._rope[grid]
+        sp = self.sp                                   # sequence parallelism (worldforge_b200.ulysses), None on one GPU
+        P, rk = (sp.world, sp.rank) if sp is not None else (1, 0)
+        if L % P or nh % P:
+            raise ValueError(f"{L} tokens / {nh} heads do not split over {P} ranks")
+        Ll = L // P                                    # this rank owns the contiguous token range [rk*Ll, (rk+1)*Ll)
+        B = self._buffers(L, Ll)
+        if (grid, P, rk) not in self._rope:
+            self._rope[(grid, P, rk)] = rope_table(grid)[rk * Ll:(rk + 1) * Ll].contiguous().to(self.device)
+        rope = self._rope[(grid, P, rk)]
 
         # patch embedding (bf16 token stream, held in fp32 storage)
         lib.patchify(hs, B.cols)
-        lib.gemm_bf16(B.cols, self.patch_w, self.patch_b, B.x, lib.EPI_F32_OF_BF16)
+        lib.gemm_bf16(B.cols[rk * Ll:(rk + 1) * Ll], self.patch_w, self.patch_b, B.x, lib.EPI_F32_OF_BF16)
         # time embedding -> per-block modulation tables
         lib.time_sinusoid(timestep.reshape(-1)[:1].to(torch.int64).contiguous(), B.sinus)
         lib.gemv_f32(self.t0_w, B.sinus, self.t0_b, B.e1, silu_out=True)
@@ -318,8 +325,12 @@ class WfWanTransformer:
             lib.gemm_bf16(B.h, b.qkv_w, b.qkv_b, B.qkv, lib.EPI_BF16)
             lib.rms_norm_rope_(B.qkv[:, :D], b.norm_q, c.eps, rope)
             lib.rms_norm_rope_(B.qkv[:, D:2 * D], b.norm_k, c.eps, rope)
-            lib.attention_bf16(B.qkv[:, :D], B.qkv[:, D:2 * D], B.qkv[:, 2 * D:], B.att, nh)
-            lib.gemm_bf16(B.att, b.o_w, b.o_b, B.x, lib.EPI_RESID_F32, gate=e[2])
+            if sp is None:
+                lib.attention_bf16(B.qkv[:, :D], B.qkv[:, D:2 * D], B.qkv[:, 2 * D:], B.att, nh)
+                att = B.att
+            else:
+                att = sp.attention(B.qkv, nh)          # Ulysses: heads <-> tokens all-to-all around the same kernel
+            lib.gemm_bf16(att, b.o_w, b.o_b, B.x, lib.EPI_RESID_F32, gate=e[2])
             # cross attention: image keys, then text keys with the image result added
             lib.layer_norm(B.x, B.h, c.eps, weight=b.n3_w, bias=b.n3_b)
             lib.gemm_bf16(B.h, b.cq_w, b.cq_b, B.cq, lib.EPI_BF16)
@@ -333,8 +344,13 @@ class WfWanTransformer:
             lib.gemm_bf16(B.h, b.f0_w, b.f0_b, B.ff, lib.EPI_GELU_BF16)
             lib.gemm_bf16(B.ff, b.f2_w, b.f2_b, B.x, lib.EPI_RESID_F32, gate=e[5])
 
-        out = torch.empty(c.out_dim, Fr, H, W, dtype=F32, device=self.device)
-        lib.dit_head(B.x, B.hmod[1], B.hmod[0], self.head_w, self.head_b, out, grid, c.eps)
+        if sp is None:
+            out = torch.empty(c.out_dim, Fr, H, W, dtype=F32, device=self.device)
+            lib.dit_head(B.x, B.hmod[1], B.hmod[0], self.head_w, self.head_b, out, grid, c.eps)
+        else:                                          # every rank scatters its tokens into a zero canvas; sum = gather
+            out = torch.zeros(c.out_dim, Fr, H, W, dtype=F32, device=self.device)
+            lib.dit_head(B.x, B.hmod[1], B.hmod[0], self.head_w, self.head_b, out, grid, c.eps, tok_offset=rk * Ll)
+            sp.all_reduce(out)
         return (out.unsqueeze(0).to(self.dtype),)
 
     def flops_per_forward(self, L: int) -> float:

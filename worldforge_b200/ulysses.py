@@ -1,0 +1,77 @@
+"""Ulysses sequence parallelism for the DiT: tokens sharded across the GPUs of one box, heads exchanged around attention.
+
+The clip's L tokens (frame-major, exactly the order WanModel flattens them, reference wan/modules/model.py:537) are cut
+into P contiguous shards - the layout of the reference design wan/distributed/xdit_context_parallel.py:160-162 - and every
+token-local op of the block (LayerNorm, the GEMMs, RMSNorm over the full width, RoPE with global positions,
+cross-attention to the replicated 769-token context, FFN) runs on the local shard without communication.  Self-attention
+needs every key: one all-to-all turns the fused q|k|v shard [L/P, 3, H, 128] into [L, 3, H/P, 128] (all tokens, this
+rank's heads), the same attention kernel runs on H/P heads, and a second all-to-all returns [L/P, H, 128] - the
+head<->sequence exchange of the reference's LongCat path (longcat_video/context_parallel/ulysses_wrapper.py:87-105), but
+ONE collective for q, k and v instead of three and no second staging copy on the way in.  The 64-channel head output is
+scattered by each rank into a zero canvas and summed (8 MB).  Weights are replicated (33 GB of 180 GB).
+
+The scheduler, FLF and the VAE round trip operate on the replicated 8 MB latents and run identically on every rank (the
+causal VAE does not shard along frames: "replicas only").
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def heads_to_tokens_layout(qkv: torch.Tensor, world: int) -> torch.Tensor:
+    """[Ll, 3*H*128] (token shard, all heads) -> send buffer [world, Ll, 3*(H/world)*128]; block d goes to rank d."""
+    Ll, W3 = qkv.shape
+    hp = W3 // (3 * world)
+    return qkv.view(Ll, 3, world, hp).permute(2, 0, 1, 3).contiguous()
+
+
+def tokens_from_ranks(recv: torch.Tensor) -> torch.Tensor:
+    """receive buffer [world(src), Ll, 3*hp] -> [L, 3*hp]: source rank r owns token block r, so this is already global order."""
+    world, Ll = recv.shape[:2]
+    return recv.reshape(world * Ll, -1)
+
+
+def tokens_to_heads_layout(recv: torch.Tensor) -> torch.Tensor:
+    """receive buffer of the return trip [world(src), Ll, hp] -> [Ll, world*hp] = [Ll, H*128] (heads of rank r at block r)."""
+    world, Ll, hp = recv.shape
+    return recv.permute(1, 0, 2).reshape(Ll, world * hp)
+
+
+class SequenceParallel:
+    def __init__(self, group=None):
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.a2a_calls = 0
+
+    def all_to_all(self, send: torch.Tensor) -> torch.Tensor:
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv.view(-1), send.view(-1), group=self.group)
+        self.a2a_calls += 1
+        return recv
+
+    def all_reduce(self, t: torch.Tensor):
+        dist.all_reduce(t, group=self.group)
+
+    def attention(self, qkv: torch.Tensor, heads: int, attn_fn=None) -> torch.Tensor:
+        """qkv [L/P, 3*heads*128] bf16 (RMSNorm + RoPE already applied) -> attention output [L/P, heads*128]."""
+        from . import lib
+        P = self.world
+        hl = heads // P
+        recv = self.all_to_all(heads_to_tokens_layout(qkv, P))          # [P, Ll, 3*hl*128]
+        full = tokens_from_ranks(recv)                                   # [L, 3*hl*128]
+        w = hl * 128
+        out = torch.empty(full.shape[0], w, dtype=qkv.dtype, device=qkv.device)
+        if attn_fn is None:
+            lib.attention_bf16(full[:, :w], full[:, w:2 * w], full[:, 2 * w:], out, hl)
+        else:
+            attn_fn(full[:, :w], full[:, w:2 * w], full[:, 2 * w:], out, hl)
+        back = self.all_to_all(out.view(P, full.shape[0] // P, w))       # block d = token shard d, already contiguous
+        return tokens_to_heads_layout(back)
+
+
+def enable(transformer, group=None) -> SequenceParallel:
+    sp = SequenceParallel(group)
+    transformer.sp = sp
+    return sp
