@@ -22,6 +22,8 @@
 // straight from its TMA box; P goes through 128-byte-swizzled shared memory.  O stays in
 // TMEM for the whole key loop; it is rescaled there only when a row maximum grows by more
 // than 2^8 (lazy rescaling), so the common path never touches O.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -285,6 +287,284 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
 }
 
+
+// =====================================================================================================================
+// v2: the same algorithm with (a) S double-buffered in TMEM so the tensor core computes S(j+1) for both tiles while the
+// softmax warps still work on block j - the softmax never waits for the MMA and vice versa except through P;
+// (b) packed fp32x2 arithmetic (FFMA2 / FADD2), 3-input max (FMNMX3) and one fused multiply-add per score for
+// "scale, subtract the running maximum"; (c) optionally, every fourth pair of exponentials evaluated on the FMA pipe
+// (Cody-Waite range reduction + a degree-3 polynomial, relative error 7.5e-5, far below the bf16 rounding P gets
+// anyway), because at 64-key blocks the MUFU pipe (16 ex2 / clk / SM) needs exactly as many cycles as the MMAs.
+// TMEM columns: S_t[buf] at (2t+buf)*64, O_t at 256 + 128 t.
+// =====================================================================================================================
+constexpr uint32_t AT2_TMEM_O = 256;
+
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d;
+}
+// 2^x for a pair, x <= ~8, on the FMA / ALU pipes: x = n + f, n = round(x), f in [-0.5, 0.5], 2^f by a cubic
+__device__ __forceinline__ void exp2_poly2(uint64_t x2, float& e0, float& e1) {
+  float x0, x1; unpack2(x2, x0, x1);
+  x2 = pack2(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+  const uint64_t magic = pack2(12582912.0f, 12582912.0f), nmagic = pack2(-12582912.0f, -12582912.0f);
+  const uint64_t t2 = fadd2(x2, magic);                       // low mantissa bits = round(x)
+  const uint64_t n2 = fadd2(t2, nmagic);
+  const uint64_t f2 = ffma2(n2, pack2(-1.0f, -1.0f), x2);
+  uint64_t p2 = ffma2(pack2(0.0551716685f, 0.0551716685f), f2, pack2(0.2426111251f, 0.2426111251f));
+  p2 = ffma2(p2, f2, pack2(0.6932609677f, 0.6932609677f));
+  p2 = ffma2(p2, f2, pack2(0.9999280572f, 0.9999280572f));
+  float p0, p1, t0, t1; unpack2(p2, p0, p1); unpack2(t2, t0, t1);
+  e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+  e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+}
+
+template <bool POLY>
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attention_tcgen05_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, AttnArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_OFF_BAR);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = kv_full + AT_STAGES;
+  uint64_t* s_full = kv_empty + AT_STAGES;   // [tile][buf] -> 4
+  uint64_t* p_full = s_full + 4;             // 2
+  uint64_t* o_done = p_full + 2;             // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int head = blockIdx.y;
+  const int q0 = blockIdx.x * (2 * AT_BM);
+  const int nblk = (p.Lk + AT_BN - 1) / AT_BN;
+  const int col0 = head * AT_D;
+
+  if (warp == 0 && elect_one()) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); }
+  if (warp == 1 && elect_one()) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < AT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1);
+    for (int t = 0; t < 2; ++t) { mbar_init(&p_full[t], 4); mbar_init(&o_done[t], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, 2 * AT_Q_BYTES);
+      for (int t = 0; t < 2; ++t)
+        for (int half = 0; half < 2; ++half)
+          tma_load_2d(smem + t * AT_Q_BYTES + half * (AT_Q_BYTES / 2), &tmQ, q_full, col0 + half * 64, q0 + t * AT_BM);
+    }
+    __syncwarp();
+    for (int j = 0; j < nblk; ++j) {
+      const int stage = j % AT_STAGES;
+      mbar_wait(&kv_empty[stage], ((j / AT_STAGES) & 1) ^ 1);
+      if (elect_one()) {
+        uint8_t* kdst = smem + AT_OFF_KV + stage * AT_KV_BYTES;
+        uint8_t* vdst = kdst + AT_K_BYTES;
+        mbar_arrive_expect_tx(&kv_full[stage], AT_KV_BYTES);
+        for (int half = 0; half < 2; ++half) {
+          tma_load_2d(kdst + half * (AT_K_BYTES / 2), &tmK, &kv_full[stage], col0 + half * 64, j * AT_BN);
+          tma_load_2d(vdst + half * (AT_K_BYTES / 2), &tmV, &kv_full[stage], col0 + half * 64, j * AT_BN);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_s = umma_idesc(1, AT_BM, AT_BN, 0, 0);
+    constexpr uint32_t idesc_o = umma_idesc(1, AT_BM, AT_D, 0, 1);
+    const uint32_t q_addr = smem_u32(smem);
+    const uint32_t p_addr = smem_u32(smem + AT_OFF_P);
+    auto issue_s = [&](int t, int stage, int buf) {
+      const uint32_t k_addr = smem_u32(smem + AT_OFF_KV + stage * AT_KV_BYTES);
+#pragma unroll
+      for (int ks = 0; ks < AT_D / 16; ++ks) {
+        uint64_t da = umma_desc_sw128(q_addr + t * AT_Q_BYTES + (ks >> 2) * (AT_Q_BYTES / 2) + (ks & 3) * 32, 16, 1024);
+        uint64_t db = umma_desc_sw128(k_addr + (ks >> 2) * (AT_K_BYTES / 2) + (ks & 3) * 32, 16, 1024);
+        umma_f16_ss(tmem_base + (2 * t + buf) * AT_BN, da, db, idesc_s, ks != 0);
+      }
+      umma_commit(&s_full[2 * t + buf]);
+    };
+    auto issue_pv = [&](int t, int stage, int j) {
+      const uint32_t v_addr = smem_u32(smem + AT_OFF_KV + stage * AT_KV_BYTES + AT_K_BYTES);
+#pragma unroll
+      for (int ks = 0; ks < AT_BN / 16; ++ks) {
+        uint64_t da = umma_desc_sw128(p_addr + t * AT_P_BYTES + ks * 32, 16, 1024);
+        uint64_t db = umma_desc_sw128(v_addr + ks * 2048, AT_K_BYTES / 2, 1024);
+        umma_f16_ss(tmem_base + AT2_TMEM_O + t * AT_D, da, db, idesc_o, (j | ks) != 0);
+      }
+      umma_commit(&o_done[t]);
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    if (elect_one()) { issue_s(0, 0, 0); issue_s(1, 0, 0); }
+    __syncwarp();
+    for (int j = 0; j < nblk; ++j) {
+      const int stage = j % AT_STAGES;
+      if (j + 1 < nblk) {
+        // S(j+1) goes to the other S buffer: its last reader, softmax(j-1), signalled p_full(j-1), which was waited below
+        const int nstage = (j + 1) % AT_STAGES;
+        mbar_wait(&kv_full[nstage], ((j + 1) / AT_STAGES) & 1);
+        tc_fence_after();
+        if (elect_one()) { issue_s(0, nstage, (j + 1) & 1); issue_s(1, nstage, (j + 1) & 1); }
+        __syncwarp();
+      }
+      mbar_wait(&p_full[0], j & 1);
+      tc_fence_after();
+      if (elect_one()) issue_pv(0, stage, j);
+      __syncwarp();
+      mbar_wait(&p_full[1], j & 1);
+      tc_fence_after();
+      if (elect_one()) { issue_pv(1, stage, j); umma_commit(&kv_empty[stage]); }
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    const int t = (warp - 4) >> 2;
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane_id();
+    const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t o_tmem = tmem_base + lane_addr + AT2_TMEM_O + t * AT_D;
+    uint8_t* p_row = smem + AT_OFF_P + t * AT_P_BYTES + row * 128;
+    const float c = p.scale_log2;
+    const uint64_t c2 = pack2(c, c);
+    float m_ref = 0.f, l = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      const int buf = j & 1;
+      mbar_wait(&s_full[2 * t + buf], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t r[64];
+      {
+        uint32_t (&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+        uint32_t (&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
+        const uint32_t s_tmem = tmem_base + lane_addr + (2 * t + buf) * AT_BN;
+        tmem_ld_32x32b_x32(s_tmem, r0);
+        tmem_ld_32x32b_x32(s_tmem + 32, r1);
+        tmem_ld_wait();
+      }
+      const int valid = p.Lk - j * AT_BN;
+      if (valid < AT_BN) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) if (i >= valid) r[i] = 0xff800000u;   // -inf
+      }
+      float mx = fmax3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
+#pragma unroll
+      for (int i = 3; i < 63; i += 2) mx = fmax3(mx, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+      mx = fmaxf(mx, __uint_as_float(r[63]));
+      const float m_blk = mx * c;
+      float alpha = 1.0f;
+      bool grow = false;
+      if (j == 0) {
+        m_ref = m_blk;
+      } else if (m_blk - m_ref > AT_RESCALE_THRESHOLD) {
+        alpha = ex2(m_ref - m_blk);
+        m_ref = m_blk;
+        grow = true;
+      }
+      const uint64_t nm2 = pack2(-m_ref, -m_ref);
+      uint64_t sum2 = pack2(0.f, 0.f);
+      uint32_t pk[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const uint64_t x2 = ffma2(pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), c2, nm2);
+        float e0, e1;
+        if (POLY && (i & 3) == 3 && valid >= AT_BN) {
+          exp2_poly2(x2, e0, e1);
+        } else {
+          float x0, x1; unpack2(x2, x0, x1);
+          e0 = ex2(x0); e1 = ex2(x1);
+        }
+        sum2 = fadd2(sum2, pack2(e0, e1));
+        pk[i] = pack_bf16x2(e0, e1);
+      }
+      float s_lo, s_hi; unpack2(sum2, s_lo, s_hi);
+      l = l * alpha + (s_lo + s_hi);
+      if (j > 0) {
+        mbar_wait(&o_done[t], (j - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll 1
+          for (int cc = 0; cc < AT_D; cc += 32) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(o_tmem + cc, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x32(o_tmem + cc, o);
+          }
+          tmem_st_wait();
+        }
+      }
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        uint4 v = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+        *reinterpret_cast<uint4*>(p_row + ((ch ^ (row & 7)) << 4)) = v;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&p_full[t]);
+    }
+    mbar_wait(&o_done[t], (nblk - 1) & 1);
+    tc_fence_after();
+    const int q = q0 + t * AT_BM + row;
+    const float inv_l = 1.0f / l;
+#pragma unroll 1
+    for (int cc = 0; cc < AT_D; cc += 32) {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(o_tmem + cc, o);
+      tmem_ld_wait();
+      if (q < p.Lq) {
+        bf16* dst = p.out + static_cast<size_t>(q) * p.ldo + col0 + cc;
+        const bf16* add = p.add_in ? p.add_in + static_cast<size_t>(q) * p.ld_add + col0 + cc : nullptr;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          float w[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) w[u] = __uint_as_float(o[i + u]) * inv_l;
+          if (add) {
+            uint4 a = *reinterpret_cast<const uint4*>(add + i);
+            const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float2 f = __bfloat1622float2(a2[u]);
+              w[2 * u] = __fadd_rn(bf16_round(w[2 * u]), f.x);
+              w[2 * u + 1] = __fadd_rn(bf16_round(w[2 * u + 1]), f.y);
+            }
+          }
+          uint4 v = make_uint4(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]), pack_bf16x2(w[4], w[5]),
+                               pack_bf16x2(w[6], w[7]));
+          *reinterpret_cast<uint4*>(dst + i) = v;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace wf
 
 extern "C" int wf_attention_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out,
@@ -308,15 +588,23 @@ extern "C" int wf_attention_bf16(const void* q, int ldq, const void* k, int ldk,
   if ((rc = mk(&tmQ, q, ldq, Lq, AT_BM))) return rc;
   if ((rc = mk(&tmK, k, ldk, Lk, AT_BN))) return rc;
   if ((rc = mk(&tmV, v, ldv, Lk, AT_BN))) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // WF_ATTN=1: v1 (single S buffer); 2: v2 (double-buffered S, packed fp32x2 softmax); 3 (default): v2 + polynomial ex2 offload
+  static int variant = 0;
+  if (variant == 0) {
+    const char* e = getenv("WF_ATTN");
+    variant = e ? atoi(e) : 3;
+    if (variant < 1 || variant > 3) variant = 3;
     WF_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-    attr_set = true;
+    WF_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    WF_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
   }
   AttnArgs args{Lq, Lk, static_cast<bf16*>(out), ldo, static_cast<const bf16*>(add_in), ld_add,
                 softmax_scale * 1.4426950408889634f};
   dim3 grid((Lq + 2 * AT_BM - 1) / (2 * AT_BM), heads);
-  attention_tcgen05<<<grid, AT_THREADS, AT_SMEM, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, args);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (variant == 1) attention_tcgen05<<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);
+  else if (variant == 2) attention_tcgen05_v2<false><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);
+  else attention_tcgen05_v2<true><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);
   WF_LAUNCH_OK();
   return WF_OK;
 }
