@@ -16,6 +16,8 @@
 // (one elected lane), warp 2 TMEM allocator, warps 4-7 epilogue.  128x256 output tile,
 // 64-wide K blocks in 128-byte-swizzled smem, 4-stage mbarrier ring, two 256-column TMEM
 // accumulators so tile i's epilogue overlaps tile i+1's main loop.
+#include <algorithm>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -41,6 +43,7 @@ struct GemmArgs {
   void* out;           // bf16 [M,ldo] or float [M,ldo]
   int ldo;
   const float* gate;   // [N] or null (EPI_RESID_F32)
+  int group_n;         // n-tiles per raster group (L2 working-set control)
 };
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {
@@ -66,6 +69,16 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int tiles_n = (p.N + GEMM_BN - 1) / GEMM_BN;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+  // Raster order: groups of `group_n` n-tiles are swept over ALL m-tiles before the next group starts, n fastest inside
+  // a group.  The CTAs in flight then share a few A row-blocks and at most group_n weight column-blocks - a working
+  // set sized to stay in the 126 MB L2 - instead of streaming the whole weight matrix from HBM once per wave.
+  auto tile_origin = [&](int tile, int& m0, int& n0) {
+    const int per_group = p.group_n * tiles_m;
+    const int g = tile / per_group, r = tile - g * per_group;
+    const int gw = min(p.group_n, tiles_n - g * p.group_n);     // the last group may be narrower
+    m0 = (r / gw) * GEMM_BM;
+    n0 = (g * p.group_n + r % gw) * GEMM_BN;
+  };
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
@@ -86,7 +99,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ------------------------------------------------------------ TMA producer
     int stage = 0; uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / tiles_n) * GEMM_BM, n0 = (tile % tiles_n) * GEMM_BN;
+      int m0, n0; tile_origin(tile, m0, n0);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         if (elect_one()) {
@@ -138,7 +151,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     float* tile = epi_tile + q * (32 * EPI_LD);
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile_idx = blockIdx.x; tile_idx < num_tiles; tile_idx += gridDim.x) {
-      const int m0 = (tile_idx / tiles_n) * GEMM_BM + q * 32, n0 = (tile_idx % tiles_n) * GEMM_BN;
+      int m0, n0; tile_origin(tile_idx, m0, n0); m0 += q * 32;
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * GEMM_BN;
@@ -260,7 +273,10 @@ extern "C" int wf_gemm_bf16(const void* a, int lda, const void* w, int ldw, cons
   WF_REQUIRE(ldo % 8 == 0, "wf_gemm_bf16: ldo must be a multiple of 8");
   WF_REQUIRE((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(out)) % 16 == 0,
              "wf_gemm_bf16: pointers must be 16-byte aligned");
-  GemmArgs args{M, N, K, static_cast<const bf16*>(bias), out, ldo, gate};
+  // n-tiles per raster group: keep group_n weight column-blocks (256 x K bf16 each) within ~40 MB of L2
+  const long long col_block_bytes = 2ll * GEMM_BN * K;
+  int group_n = static_cast<int>(std::max<long long>(1, (40ll << 20) / col_block_bytes));
+  GemmArgs args{M, N, K, static_cast<const bf16*>(bias), out, ldo, gate, group_n};
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (epilogue) {
     case EPI_BF16: return launch_gemm<EPI_BF16>(a, lda, w, ldw, args, s);
