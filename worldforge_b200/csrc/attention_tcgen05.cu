@@ -588,12 +588,13 @@ extern "C" int wf_attention_bf16(const void* q, int ldq, const void* k, int ldk,
   if ((rc = mk(&tmQ, q, ldq, Lq, AT_BM))) return rc;
   if ((rc = mk(&tmK, k, ldk, Lk, AT_BN))) return rc;
   if ((rc = mk(&tmV, v, ldv, Lk, AT_BN))) return rc;
-  // WF_ATTN=1: v1 (single S buffer); 2: v2 (double-buffered S, packed fp32x2 softmax); 3 (default): v2 + polynomial ex2 offload
+  // WF_ATTN=1: v1 (single S buffer); 2 (default): v2 (double-buffered S, packed fp32x2 softmax); 3: v2 + polynomial ex2
+  // offload (measured slower than 2 on B200: the extra FMA-pipe instructions cost more issue slots than the MUFU time they free)
   static int variant = 0;
   if (variant == 0) {
     const char* e = getenv("WF_ATTN");
-    variant = e ? atoi(e) : 3;
-    if (variant < 1 || variant > 3) variant = 3;
+    variant = e ? atoi(e) : 2;
+    if (variant < 1 || variant > 3) variant = 2;
     WF_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
     WF_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
     WF_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
