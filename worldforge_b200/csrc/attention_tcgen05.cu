@@ -330,7 +330,21 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x2, float& e0, float& e1) {
   e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
 }
 
-template <bool POLY>
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (here the bf16 probabilities, two per 32-bit column) is read from
+// tensor memory instead of shared memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// PTMEM: P_t(j) is stored back into the first 32 columns of the S buffer it was computed from (64 bf16 = 32 columns)
+// and consumed by the PV product as a TMEM operand: no shared-memory round trip for P, which with 64-key blocks is
+// what pushes shared-memory reads (Q 32 KB + K 16 KB per S product, P 16 KB + V 16 KB per PV product) past the MMA time.
+template <bool POLY, bool PTMEM>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tcgen05_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, AttnArgs p) {
@@ -406,9 +420,13 @@ attention_tcgen05_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const uint32_t v_addr = smem_u32(smem + AT_OFF_KV + stage * AT_KV_BYTES + AT_K_BYTES);
 #pragma unroll
       for (int ks = 0; ks < AT_BN / 16; ++ks) {
-        uint64_t da = umma_desc_sw128(p_addr + t * AT_P_BYTES + ks * 32, 16, 1024);
         uint64_t db = umma_desc_sw128(v_addr + ks * 2048, AT_K_BYTES / 2, 1024);
-        umma_f16_ss(tmem_base + AT2_TMEM_O + t * AT_D, da, db, idesc_o, (j | ks) != 0);
+        if (PTMEM) {
+          umma_f16_ts(tmem_base + AT2_TMEM_O + t * AT_D, tmem_base + (2 * t + (j & 1)) * AT_BN + ks * 8, db, idesc_o, (j | ks) != 0);
+        } else {
+          uint64_t da = umma_desc_sw128(p_addr + t * AT_P_BYTES + ks * 32, 16, 1024);
+          umma_f16_ss(tmem_base + AT2_TMEM_O + t * AT_D, da, db, idesc_o, (j | ks) != 0);
+        }
       }
       umma_commit(&o_done[t]);
     };
@@ -496,28 +514,35 @@ attention_tcgen05_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
       float s_lo, s_hi; unpack2(sum2, s_lo, s_hi);
       l = l * alpha + (s_lo + s_hi);
-      if (j > 0) {
+      const bool any_grow = __any_sync(0xffffffffu, grow);
+      if (j > 0 && (!PTMEM || any_grow)) {
+        // S(j) complete implies PV(j-2) complete (in-order MMA pipe), so this parity wait can only mean PV(j-1)
         mbar_wait(&o_done[t], (j - 1) & 1);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, grow)) {
+      }
+      if (j > 0 && any_grow) {
 #pragma unroll 1
-          for (int cc = 0; cc < AT_D; cc += 32) {
-            uint32_t o[32];
-            tmem_ld_32x32b_x32(o_tmem + cc, o);
-            tmem_ld_wait();
+        for (int cc = 0; cc < AT_D; cc += 32) {
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(o_tmem + cc, o);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x32b_x32(o_tmem + cc, o);
-          }
-          tmem_st_wait();
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_32x32b_x32(o_tmem + cc, o);
         }
+        tmem_st_wait();
       }
+      if (PTMEM) {
+        tmem_st_32x32b_x32(tmem_base + lane_addr + (2 * t + buf) * AT_BN, pk);
+        tmem_st_wait();
+      } else {
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        uint4 v = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
-        *reinterpret_cast<uint4*>(p_row + ((ch ^ (row & 7)) << 4)) = v;
+        for (int ch = 0; ch < 8; ++ch) {
+          uint4 v = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+          *reinterpret_cast<uint4*>(p_row + ((ch ^ (row & 7)) << 4)) = v;
+        }
+        fence_proxy_async_smem();
       }
-      fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane_id() == 0) mbar_arrive(&p_full[t]);
@@ -594,18 +619,20 @@ extern "C" int wf_attention_bf16(const void* q, int ldq, const void* k, int ldk,
   if (variant == 0) {
     const char* e = getenv("WF_ATTN");
     variant = e ? atoi(e) : 2;
-    if (variant < 1 || variant > 3) variant = 2;
+    if (variant < 1 || variant > 4) variant = 2;
     WF_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-    WF_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-    WF_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)));
+    WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)));
+    WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)));
   }
   AttnArgs args{Lq, Lk, static_cast<bf16*>(out), ldo, static_cast<const bf16*>(add_in), ld_add,
                 softmax_scale * 1.4426950408889634f};
   dim3 grid((Lq + 2 * AT_BM - 1) / (2 * AT_BM), heads);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (variant == 1) attention_tcgen05<<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);
-  else if (variant == 2) attention_tcgen05_v2<false><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);
-  else attention_tcgen05_v2<true><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);
+  else if (variant == 2) attention_tcgen05_v2<false, false><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);
+  else if (variant == 3) attention_tcgen05_v2<true, false><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);
+  else attention_tcgen05_v2<false, true><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);   // 4: P through TMEM
   WF_LAUNCH_OK();
   return WF_OK;
 }
