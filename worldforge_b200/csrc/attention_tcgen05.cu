@@ -613,13 +613,14 @@ extern "C" int wf_attention_bf16(const void* q, int ldq, const void* k, int ldk,
   if ((rc = mk(&tmQ, q, ldq, Lq, AT_BM))) return rc;
   if ((rc = mk(&tmK, k, ldk, Lk, AT_BN))) return rc;
   if ((rc = mk(&tmV, v, ldv, Lk, AT_BN))) return rc;
-  // WF_ATTN=1: v1 (single S buffer); 2 (default): v2 (double-buffered S, packed fp32x2 softmax); 3: v2 + polynomial ex2
-  // offload (measured slower than 2 on B200: the extra FMA-pipe instructions cost more issue slots than the MUFU time they free)
+  // WF_ATTN=1: v1 (single S buffer, P through smem); 2: v2 (double-buffered S, packed fp32x2 softmax, P through smem);
+  // 3: v2 + polynomial ex2 offload (measured slower on B200: the extra FMA-pipe instructions cost more issue slots than
+  // the MUFU time they free); 4 (default): v2 with P kept in TMEM as the A operand of the PV product
   static int variant = 0;
   if (variant == 0) {
     const char* e = getenv("WF_ATTN");
-    variant = e ? atoi(e) : 2;
-    if (variant < 1 || variant > 4) variant = 2;
+    variant = e ? atoi(e) : 4;
+    if (variant < 1 || variant > 4) variant = 4;
     WF_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
     WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)));
     WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)));
