@@ -187,3 +187,66 @@ def load_scheduler_module():
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
     return m
+
+
+REF_LONGCAT = os.path.join(REF_ROOT, "longcat_for_worldforge")
+
+
+def _fake_xformers():
+    """xformers is not installed; the LongCat attention modules call it when ``enable_xformers`` is set.  A stand-in
+    with the two entry points they use (attention.py:100, :243-246), computed with SDPA in fp32."""
+    if "xformers" in sys.modules:
+        return
+    xf = types.ModuleType("xformers"); ops = types.ModuleType("xformers.ops")
+    fmha = types.ModuleType("xformers.ops.fmha"); ab = types.ModuleType("xformers.ops.fmha.attn_bias")
+
+    class BlockDiagonalMask:
+        def __init__(self, q_lens, k_lens):
+            self.q_lens, self.k_lens = q_lens, k_lens
+
+        @classmethod
+        def from_seqlens(cls, q_lens, k_lens):
+            return cls(list(q_lens), list(k_lens))
+
+    def memory_efficient_attention(q, k, v, attn_bias=None, op=None):
+        # q [B, M, H, K]; with a block-diagonal mask B == 1 and the sequences are concatenated along M
+        def sdpa(a, b, c):
+            o = torch.nn.functional.scaled_dot_product_attention(a.transpose(1, 2).float(), b.transpose(1, 2).float(),
+                                                                 c.transpose(1, 2).float())
+            return o.transpose(1, 2).to(a.dtype)
+        if attn_bias is None:
+            return sdpa(q, k, v)
+        outs, qo, ko = [], 0, 0
+        for ql, kl in zip(attn_bias.q_lens, attn_bias.k_lens):
+            outs.append(sdpa(q[:, qo:qo + ql], k[:, ko:ko + kl], v[:, ko:ko + kl]))
+            qo += ql; ko += kl
+        return torch.cat(outs, dim=1)
+
+    ab.BlockDiagonalMask = BlockDiagonalMask
+    fmha.attn_bias = ab
+    ops.fmha = fmha
+    ops.memory_efficient_attention = memory_efficient_attention
+    xf.ops = ops
+    sys.modules.update({"xformers": xf, "xformers.ops": ops, "xformers.ops.fmha": fmha, "xformers.ops.fmha.attn_bias": ab})
+
+
+def load_longcat_dit_module():
+    """longcat_video.modules.longcat_video_dit, unmodified, importable on the CPU: diffusers stand-in, a stub for the
+    Triton block-sparse package (only reached by the 720p refine pass), SDPA-backed xformers, context-parallel size 1."""
+    assert os.path.isdir(REF_LONGCAT)
+    install_diffusers_shim()
+    _fake_xformers()
+    if REF_LONGCAT not in sys.path:
+        sys.path.insert(0, REF_LONGCAT)
+    for name in ("longcat_video", "longcat_video.modules", "longcat_video.context_parallel", "longcat_video.block_sparse_attention"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = [os.path.join(REF_LONGCAT, *name.split("."))]
+            sys.modules[name] = m
+    if "longcat_video.block_sparse_attention.bsa_interface" not in sys.modules:
+        stub = types.ModuleType("longcat_video.block_sparse_attention.bsa_interface")
+        stub.flash_attn_bsa_3d = None
+        sys.modules["longcat_video.block_sparse_attention.bsa_interface"] = stub
+    cpu = importlib.import_module("longcat_video.context_parallel.context_parallel_util")
+    cpu.cp_size = 1
+    return importlib.import_module("longcat_video.modules.longcat_video_dit")
