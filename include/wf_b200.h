@@ -37,14 +37,17 @@ int wf_sm_count(void);
 #define WF_EPI_GELU_BF16 1   /* out bf16           = bf16(gelu_tanh(bf16(acc + bias)))                  */
 #define WF_EPI_RESID_F32 2   /* out fp32 (in place) += float(bf16(acc + bias)) * gate[n]  (gate NULL: 1) */
 #define WF_EPI_F32_OF_BF16 3 /* out fp32           = float(bf16(acc + bias))                            */
+#define WF_EPI_RESID_BF16 4  /* out bf16 (in place) = bf16(float(out) + gate * float(bf16(acc + bias)))   */
 
 /* nn.Linear under autocast(bf16): out = a[M,K] . w[N,K]^T + bias, fused epilogue.
  * Replaces every F.linear of WanAttentionBlock / text_embedding / img_emb / patch_embedding
  * (wan/modules/model.py:123-126,197-198,271-273,456-460) together with the elementwise op that
  * follows it (GELU :272; gated residual :306,:313; residual :310).
- * a, w: bf16 row-major, K contiguous (lda, ldw in elements, multiples of 8); bias: bf16 [N] or NULL. */
+ * a, w: bf16 row-major, K contiguous (lda, ldw in elements, multiples of 8); bias: bf16 [N] or NULL.
+ * gate: fp32 [N] (gate_rows = 0) or a [groups, N] table where row m uses group m / gate_rows - the per-frame adaLN
+ * gates of LongCat (longcat_video/modules/longcat_video_dit.py:83-85,101-103). */
 int wf_gemm_bf16(const void* a, int lda, const void* w, int ldw, const void* bias, void* out, int ldo,
-                 const float* gate, int M, int N, int K, int epilogue, void* stream);
+                 const float* gate, int gate_rows, int M, int N, int K, int epilogue, void* stream);
 
 /* flash_attention(q, k, v) for head_dim 128, non-causal (wan/modules/attention.py:24-130; call sites
  * model.py:149-154 self-attention, :220-222 cross-attention).  q [Lq, heads*128], k/v [Lk, heads*128],
@@ -62,7 +65,7 @@ int wf_attention_bf16(const void* q, int ldq, const void* k, int ldk, const void
  * bf16 token stream of block 0. */
 int wf_layer_norm(const void* x, int ldx, int x_is_bf16, void* out, int ldo, int out_is_bf16, const float* scale,
                   const float* shift, const float* weight, const float* bias, int rows, int D, float eps,
-                  int round_norm_bf16, void* stream);
+                  int round_norm_bf16, int rows_per_group, void* stream);   /* rows_per_group > 0: scale/shift are [groups, D] */
 
 /* WanRMSNorm over the full model dim (model.py:81-89) followed by rope_apply (:43-70), in place on a
  * bf16 [rows, D] slice (leading dimension ldx).  rope: fp64 [rows, 64, 2] (cos, sin) per token and
@@ -77,8 +80,25 @@ int wf_patchify(const void* hidden, void* cols, int C, int F, int H, int W, void
 /* Head.forward + unpatchify (model.py:337-347, 584-607): fp32 LN, modulation, fp32 Linear(D -> 4*Cout),
  * scatter to out fp32 [Cout, F, 2*GH, 2*GW].  x holds the L tokens starting at global token tok_offset
  * (0 and L = F*GH*GW on one GPU; a contiguous shard under sequence parallelism). */
-int wf_dit_head(const float* x, int ldx, int L, int D, const float* scale, const float* shift, const float* w,
-                const float* b, int Cout, float* out, int F, int GH, int GW, float eps, int tok_offset, void* stream);
+int wf_dit_head(const void* x, int x_is_bf16, int ldx, int L, int D, const float* scale, const float* shift, const float* w,
+                const float* b, int Cout, float* out, int F, int GH, int GW, float eps, int tok_offset, int rows_per_group,
+                int round_bf16, void* stream);
+/* rows_per_group / round_bf16: LongCat's FinalLayer_FP32 (longcat_video/modules/blocks.py:147-156): per-frame shift / scale
+ * tables and the modulated row rounded to bf16 before the fp32 projection. */
+
+/* ---- LongCat-Video DiT extras (longcat_for_worldforge/longcat_video/modules) ---------------------------------------- */
+/* per-head RMSNorm with a bf16 gain (blocks.py:46-52) + fp32 rotate-half RoPE (rope_3d.py:99-119), in place on a bf16
+ * [rows, heads*128] slice; rope: fp32 [rows, 64, 2] (cos, sin) or NULL */
+int wf_rms_norm_head_rope(void* x, int ldx, const void* gain_bf16, const float* rope, long long rows, int heads, float eps,
+                          void* stream);
+/* FeedForwardSwiGLU gate (blocks.py:39): in bf16 [rows, 2F] = [w1 x | w3 x] -> out bf16 [rows, F] = silu(w1 x) * (w3 x) */
+int wf_swiglu_bf16(const void* in, void* out, long long rows, int F, void* stream);
+/* TimestepEmbedder.timestep_embedding (blocks.py:184-191) in fp32: t [n] -> out [n, dim] = [cos | sin] */
+int wf_timestep_embedding_f32(const float* t, float* out, int n, int dim, void* stream);
+/* out[T,R] = act(x[T,K]) . W[R,K]^T + b in fp32 on bf16 weights, T <= 32: the t-embedder MLP and every block's
+ * adaLN_modulation inside the reference's autocast(float32) islands (longcat_video_dit.py:82-85,312-313) */
+int wf_small_gemm_f32(const float* x, const void* w_bf16, const void* b_bf16, float* out, int T, int R, int K, int silu_in,
+                      void* stream);
 
 /* fp32 matrix-vector product with optional SiLU on the input and/or output: the time_embedding /
  * time_projection MLPs at batch 1 (model.py:546-550). */

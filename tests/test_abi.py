@@ -50,10 +50,10 @@ def test_argument_validation_without_gpu():
     """WF_EINVAL paths return before any CUDA call."""
     from worldforge_b200 import lib
     h = lib.load()
-    assert h.wf_gemm_bf16(None, 8, None, 8, None, None, 8, None, 1, 32, 8, 0, None) == -1
+    assert h.wf_gemm_bf16(None, 8, None, 8, None, None, 8, None, 0, 1, 32, 8, 0, None) == -1
     assert b"null" in h.wf_last_error()
     buf = ctypes.create_string_buffer(64)
     p = ctypes.cast(buf, ctypes.c_void_p)
-    assert h.wf_gemm_bf16(p, 8, p, 8, None, p, 8, None, 4, 33, 8, 0, None) == -1      # N not a multiple of 32
+    assert h.wf_gemm_bf16(p, 8, p, 8, None, p, 8, None, 0, 4, 33, 8, 0, None) == -1      # N not a multiple of 32
     assert h.wf_cfg_combine(p, p, p, 1, 1.0, 6, None) == -1                             # not a multiple of 4
     assert h.wf_rms_norm_rope(p, 8, p, p, 1, 72, 1e-6, None) == -1                      # RoPE needs head_dim 128

@@ -51,12 +51,14 @@ struct LnArgs {
   const float* weight;  // affine:   y*weight+bias      ; may be null
   const float* bias;
   int D; float eps; int round_norm_bf16;
+  int rows_per_group;   // > 0: scale/shift are [groups, D] tables, row r uses group r / rows_per_group (per-frame adaLN)
 };
 
 __global__ void __launch_bounds__(LN_THREADS) layer_norm_kernel(LnArgs p) {
   __shared__ float red[32];
   const int row = blockIdx.x;
   const int nvec = p.D >> 2;
+  const size_t goff = p.rows_per_group > 0 ? static_cast<size_t>(row / p.rows_per_group) * p.D : 0;
   float4 v[LN_MAXV];
   float sum = 0.f;
 #pragma unroll
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(LN_THREADS) layer_norm_kernel(LnArgs p) {
       for (int u = 0; u < 4; ++u) {
         if (p.weight) y[u] = y[u] * p.weight[c + u] + p.bias[c + u];
         if (p.round_norm_bf16) y[u] = bf16_round(y[u]);
-        if (p.scale) y[u] = __fadd_rn(__fmul_rn(y[u], __fadd_rn(1.0f, p.scale[c + u])), p.shift[c + u]);
+        if (p.scale) y[u] = __fadd_rn(__fmul_rn(y[u], __fadd_rn(1.0f, p.scale[goff + c + u])), p.shift[goff + c + u]);
       }
       if (p.out_is_bf16) {
         uint2 o = make_uint2(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]));
@@ -194,13 +196,15 @@ constexpr int HEAD_THREADS = 256;
 constexpr int HEAD_TOK = 4;
 
 struct HeadArgs {
-  const float* x; int ldx; int L; int D;
-  const float* scale; const float* shift;   // [D]
+  const void* x; int x_is_bf16; int ldx; int L; int D;
+  const float* scale; const float* shift;   // [D] (or [groups, D])
   const float* w; const float* b;           // [NO, D], [NO]
   int NO;                                   // 4 * Cout
   float* out; int Cout, F, GH, GW;          // out [Cout, F, 2*GH, 2*GW]
   float eps;
   int tok_offset;                           // global index of x's first row (sequence-parallel shards)
+  int rows_per_group;                       // > 0: scale/shift are [groups, D] tables (per-frame modulation)
+  int round_bf16;                           // 1: the modulated row is rounded to bf16 before the fp32 projection
 };
 
 __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadArgs p) {
@@ -211,16 +215,21 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadArgs p) {
     const int tok = tok0 + t;
     float* row = sh + t * p.D;
     if (tok >= p.L) { for (int i = threadIdx.x; i < p.D; i += HEAD_THREADS) row[i] = 0.f; continue; }
-    const float* xr = p.x + static_cast<size_t>(tok) * p.ldx;
     float s = 0.f;
-    for (int i = threadIdx.x; i < p.D; i += HEAD_THREADS) { float v = xr[i]; row[i] = v; s += v; }
+    for (int i = threadIdx.x; i < p.D; i += HEAD_THREADS) {
+      const size_t at = static_cast<size_t>(tok) * p.ldx + i;
+      float v = p.x_is_bf16 ? __bfloat162float(static_cast<const bf16*>(p.x)[at]) : static_cast<const float*>(p.x)[at];
+      row[i] = v; s += v;
+    }
     const float mean = block_sum<HEAD_THREADS>(s, red) / p.D;
     float sq = 0.f;
     for (int i = threadIdx.x; i < p.D; i += HEAD_THREADS) { float d = row[i] - mean; sq += d * d; }
     const float rstd = rsqrtf(block_sum<HEAD_THREADS>(sq, red) / p.D + p.eps);
+    const size_t goff = p.rows_per_group > 0 ? static_cast<size_t>((tok + p.tok_offset) / p.rows_per_group) * p.D : 0;
     for (int i = threadIdx.x; i < p.D; i += HEAD_THREADS) {
       float y = (row[i] - mean) * rstd;
-      row[i] = __fadd_rn(__fmul_rn(y, __fadd_rn(1.0f, p.scale[i])), p.shift[i]);
+      y = __fadd_rn(__fmul_rn(y, __fadd_rn(1.0f, p.scale[goff + i])), p.shift[goff + i]);
+      row[i] = p.round_bf16 ? bf16_round(y) : y;
     }
   }
   __syncthreads();
@@ -309,19 +318,124 @@ __global__ void add_bcast_f32_kernel(const float* __restrict__ a, const float* _
     out[i] = __fadd_rn(a[i], b[i % inner]);
 }
 
+
+// ------------------------------------------------ per-head RMSNorm (+ fp32 RoPE): LongCat's q_norm / k_norm + rope_3d
+// x: bf16 [rows, heads*128] slice (leading dimension ldx); gain bf16 [128]; rope fp32 [rows, 64, 2] (cos, sin) or null.
+// RMSNorm_FP32 (blocks.py:46-52): (x.float()*rsqrt(mean(x^2)+eps)).type_as(x) * weight  -> bf16 (bf16 gain);
+// RotaryPositionalEmbedding.forward (rope_3d.py:99-119): q*cos + rotate_half(q)*sin in fp32, back to bf16.
+__global__ void __launch_bounds__(256) rms_head_rope_kernel(bf16* x, int ldx, const bf16* __restrict__ gain,
+                                                            const float* __restrict__ rope, size_t rows, int heads, float eps) {
+  const int lane = threadIdx.x & 31;
+  const size_t unit = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;      // (row, head)
+  if (unit >= rows * heads) return;
+  const size_t row = unit / heads;
+  const int head = static_cast<int>(unit % heads);
+  bf16* px = x + row * ldx + head * 128 + lane * 4;
+  const uint2 raw = *reinterpret_cast<const uint2*>(px);
+  float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+  float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+  float ss = a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
+  ss = warp_sum(ss);
+  const float rstd = rsqrtf(ss * (1.0f / 128.0f) + eps);
+  const uint2 graw = *reinterpret_cast<const uint2*>(gain + lane * 4);
+  float2 g0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&graw.x));
+  float2 g1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&graw.y));
+  float v[4] = {bf16_round(__fmul_rn(bf16_round(__fmul_rn(a.x, rstd)), g0.x)), bf16_round(__fmul_rn(bf16_round(__fmul_rn(a.y, rstd)), g0.y)),
+                bf16_round(__fmul_rn(bf16_round(__fmul_rn(b.x, rstd)), g1.x)), bf16_round(__fmul_rn(bf16_round(__fmul_rn(b.y, rstd)), g1.y))};
+  if (rope) {
+    const float4 cs = *reinterpret_cast<const float4*>(rope + (row * 64 + lane * 2) * 2);   // (cos0, sin0, cos1, sin1)
+    const float r0 = __fadd_rn(__fmul_rn(v[0], cs.x), __fmul_rn(-v[1], cs.y));
+    const float i0 = __fadd_rn(__fmul_rn(v[1], cs.x), __fmul_rn(v[0], cs.y));
+    const float r1 = __fadd_rn(__fmul_rn(v[2], cs.z), __fmul_rn(-v[3], cs.w));
+    const float i1 = __fadd_rn(__fmul_rn(v[3], cs.z), __fmul_rn(v[2], cs.w));
+    v[0] = r0; v[1] = i0; v[2] = r1; v[3] = i1;
+  }
+  *reinterpret_cast<uint2*>(px) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+}
+
+// ------------------------------------------------------------------- SwiGLU gate: silu(w1 x) * (w3 x), bf16 (blocks.py:39)
+// in bf16 [rows, 2F] = [w1 x | w3 x]; out bf16 [rows, F]
+__global__ void swiglu_bf16_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, size_t rows, int F) {
+  const int f8 = F >> 3;
+  const size_t total = rows * f8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t r = i / f8; const int c = static_cast<int>(i % f8) * 8;
+    const uint4 a = *reinterpret_cast<const uint4*>(in + r * 2 * F + c);
+    const uint4 b = *reinterpret_cast<const uint4*>(in + r * 2 * F + F + c);
+    const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
+    uint32_t o[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float2 x = __bfloat1622float2(a2[u]), y = __bfloat1622float2(b2[u]);
+      const float s0 = bf16_round(x.x / (1.0f + expf(-x.x))), s1 = bf16_round(x.y / (1.0f + expf(-x.y)));
+      o[u] = pack_bf16x2(__fmul_rn(s0, y.x), __fmul_rn(s1, y.y));
+    }
+    *reinterpret_cast<uint4*>(out + r * F + c) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ------------------------------------------- TimestepEmbedder.timestep_embedding (blocks.py:184-191), fp32 like the reference
+__global__ void timestep_embedding_f32_kernel(const float* __restrict__ t, float* __restrict__ out, int n, int half) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * half) return;
+  const int r = i / half, k = i % half;
+  const float freq = expf(__fmul_rn(-9.210340371976184f, static_cast<float>(k)) / static_cast<float>(half));
+  const float arg = __fmul_rn(t[r], freq);
+  out[r * 2 * half + k] = cosf(arg);
+  out[r * 2 * half + half + k] = sinf(arg);
+}
+
+// ----------------------------- out[T, R] = act_in(x[T, K]) . W[R, K]^T + b : fp32 math on bf16-valued weights (the adaLN tables)
+// one warp per output row r, all T <= 32 input rows staged in shared memory
+__global__ void __launch_bounds__(256) small_gemm_f32_kernel(const float* __restrict__ x, const bf16* __restrict__ w,
+                                                             const bf16* __restrict__ b, float* __restrict__ out, int T, int R,
+                                                             int K, int silu_in) {
+  extern __shared__ float xs[];
+  for (int i = threadIdx.x; i < T * K; i += blockDim.x) {
+    float v = x[i];
+    if (silu_in) v = v / (1.0f + expf(-v));
+    xs[i] = v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= R) return;
+  const bf16* wr = w + static_cast<size_t>(r) * K;
+  float acc[32];
+#pragma unroll
+  for (int t = 0; t < 32; ++t) acc[t] = 0.f;
+  for (int k = lane * 2; k < K; k += 64) {
+    const float2 wv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(wr + k));
+#pragma unroll
+    for (int t = 0; t < 32; ++t)
+      if (t < T) acc[t] += wv.x * xs[t * K + k] + wv.y * xs[t * K + k + 1];
+  }
+  const float bias = b ? __bfloat162float(b[r]) : 0.f;
+#pragma unroll
+  for (int t = 0; t < 32; ++t) {
+    if (t < T) {
+      const float v = warp_sum(acc[t]);
+      if (lane == 0) out[static_cast<size_t>(t) * R + r] = v + bias;
+    }
+  }
+}
+
 }  // namespace wf
 
 using namespace wf;
 
 extern "C" int wf_layer_norm(const void* x, int ldx, int x_is_bf16, void* out, int ldo, int out_is_bf16,
                              const float* scale, const float* shift, const float* weight, const float* bias,
-                             int rows, int D, float eps, int round_norm_bf16, void* stream) {
+                             int rows, int D, float eps, int round_norm_bf16, int rows_per_group, void* stream) {
   WF_REQUIRE(x && out && rows > 0, "wf_layer_norm: bad arguments");
   WF_REQUIRE(D % 4 == 0 && D <= 4 * LN_THREADS * LN_MAXV, "wf_layer_norm: dim must be a multiple of 4 and <= 8192");
   WF_REQUIRE(ldx % 4 == 0 && ldo % 4 == 0, "wf_layer_norm: leading dimensions must be multiples of 4");
   WF_REQUIRE((scale == nullptr) == (shift == nullptr) && (weight == nullptr) == (bias == nullptr),
              "wf_layer_norm: scale/shift and weight/bias come in pairs");
-  LnArgs a{x, ldx, x_is_bf16, out, ldo, out_is_bf16, scale, shift, weight, bias, D, eps, round_norm_bf16};
+  WF_REQUIRE(rows_per_group >= 0, "wf_layer_norm: rows_per_group must be >= 0");
+  LnArgs a{x, ldx, x_is_bf16, out, ldo, out_is_bf16, scale, shift, weight, bias, D, eps, round_norm_bf16, rows_per_group};
   layer_norm_kernel<<<rows, LN_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a);
   WF_LAUNCH_OK();
   return WF_OK;
@@ -349,13 +463,13 @@ extern "C" int wf_patchify(const void* hidden, void* cols, int C, int F, int H, 
   return WF_OK;
 }
 
-extern "C" int wf_dit_head(const float* x, int ldx, int L, int D, const float* scale, const float* shift,
+extern "C" int wf_dit_head(const void* x, int x_is_bf16, int ldx, int L, int D, const float* scale, const float* shift,
                            const float* w, const float* b, int Cout, float* out, int F, int GH, int GW, float eps,
-                           int tok_offset, void* stream) {
+                           int tok_offset, int rows_per_group, int round_bf16, void* stream) {
   WF_REQUIRE(x && scale && shift && w && b && out, "wf_dit_head: null pointer");
   WF_REQUIRE(tok_offset >= 0 && tok_offset + L <= F * GH * GW, "wf_dit_head: token range does not fit the grid");
   WF_REQUIRE(D % 128 == 0 && ldx % 4 == 0, "wf_dit_head: dim must be a multiple of 128");
-  HeadArgs a{x, ldx, L, D, scale, shift, w, b, 4 * Cout, out, Cout, F, GH, GW, eps, tok_offset};
+  HeadArgs a{x, x_is_bf16, ldx, L, D, scale, shift, w, b, 4 * Cout, out, Cout, F, GH, GW, eps, tok_offset, rows_per_group, round_bf16};
   const size_t shmem = static_cast<size_t>(HEAD_TOK) * D * sizeof(float);
   static size_t configured = 0;
   if (shmem > configured) {
@@ -398,6 +512,51 @@ extern "C" int wf_add_bcast_f32(const float* a, const float* b, float* out, long
   const long long total = rows * inner;
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(sm_count()) * 8));
   add_bcast_f32_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, out, static_cast<size_t>(rows), inner);
+  WF_LAUNCH_OK();
+  return WF_OK;
+}
+
+extern "C" int wf_rms_norm_head_rope(void* x, int ldx, const void* gain_bf16, const float* rope, long long rows, int heads,
+                                     float eps, void* stream) {
+  WF_REQUIRE(x && gain_bf16 && rows > 0 && heads > 0 && ldx % 4 == 0, "wf_rms_norm_head_rope: bad arguments");
+  const long long threads = rows * heads * 32;
+  rms_head_rope_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<bf16*>(x), ldx, static_cast<const bf16*>(gain_bf16), rope, static_cast<size_t>(rows), heads, eps);
+  WF_LAUNCH_OK();
+  return WF_OK;
+}
+
+extern "C" int wf_swiglu_bf16(const void* in, void* out, long long rows, int F, void* stream) {
+  WF_REQUIRE(in && out && rows > 0 && F > 0 && F % 8 == 0, "wf_swiglu_bf16: bad arguments");
+  const long long total = rows * (F / 8);
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(sm_count()) * 16));
+  swiglu_bf16_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(in), static_cast<bf16*>(out),
+                                                                           static_cast<size_t>(rows), F);
+  WF_LAUNCH_OK();
+  return WF_OK;
+}
+
+extern "C" int wf_timestep_embedding_f32(const float* t, float* out, int n, int dim, void* stream) {
+  WF_REQUIRE(t && out && n > 0 && dim > 0 && dim % 2 == 0, "wf_timestep_embedding_f32: bad arguments");
+  const int total = n * (dim / 2);
+  timestep_embedding_f32_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(t, out, n, dim / 2);
+  WF_LAUNCH_OK();
+  return WF_OK;
+}
+
+extern "C" int wf_small_gemm_f32(const float* x, const void* w_bf16, const void* b_bf16, float* out, int T, int R, int K,
+                                 int silu_in, void* stream) {
+  WF_REQUIRE(x && w_bf16 && out && T > 0 && T <= 32 && R > 0 && K > 0 && K % 2 == 0, "wf_small_gemm_f32: 1..32 rows, even K");
+  const size_t shmem = static_cast<size_t>(T) * K * sizeof(float);
+  WF_REQUIRE(shmem <= 200 * 1024, "wf_small_gemm_f32: T*K too large for shared memory");
+  static size_t configured = 0;
+  if (shmem > configured) {
+    WF_CUDA_OK(cudaFuncSetAttribute(small_gemm_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shmem)));
+    configured = shmem;
+  }
+  const int blocks = (R * 32 + 255) / 256;
+  small_gemm_f32_kernel<<<blocks, 256, shmem, static_cast<cudaStream_t>(stream)>>>(x, static_cast<const bf16*>(w_bf16),
+                                                                                  static_cast<const bf16*>(b_bf16), out, T, R, K, silu_in);
   WF_LAUNCH_OK();
   return WF_OK;
 }

@@ -9,6 +9,8 @@
 //   EPI_GELU_BF16  y = bf16(gelu_tanh(bf16(acc + b)))                  (ffn.0 + nn.GELU('tanh'), :272)
 //   EPI_RESID_F32  x[m,n] += float(bf16(acc + b)) * gate[n]            (x + y*e, :306,:313; gate==null -> x + y, :310)
 //   EPI_F32_OF_BF16 y = float(bf16(acc + b))                           (patch embedding, :534)
+//   EPI_RESID_BF16 x[m,n] = bf16(float(x) + gate * float(bf16(acc + b)))  (LongCat's bf16 residual stream,
+//                  longcat_video_dit.py:101-103,109,114-116; gate may be a per-frame table)
 //
 // Layout: A row-major [M,K] (K contiguous) and W row-major [N,K] - nn.Linear's native
 // layout - are both "K-major" UMMA operands, so no transposes exist anywhere.
@@ -35,7 +37,7 @@ constexpr int GEMM_EPI_BYTES = 4 * 32 * EPI_LD * 4;     // one 32 x 64 fp32 tile
 constexpr int GEMM_SMEM = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + GEMM_EPI_BYTES;
 constexpr int GEMM_THREADS = 256;
 
-enum { EPI_BF16 = 0, EPI_GELU_BF16 = 1, EPI_RESID_F32 = 2, EPI_F32_OF_BF16 = 3 };
+enum { EPI_BF16 = 0, EPI_GELU_BF16 = 1, EPI_RESID_F32 = 2, EPI_F32_OF_BF16 = 3, EPI_RESID_BF16 = 4 };
 
 struct GemmArgs {
   int M, N, K;
@@ -44,6 +46,7 @@ struct GemmArgs {
   int ldo;
   const float* gate;   // [N] or null (EPI_RESID_F32)
   int group_n;         // n-tiles per raster group (L2 working-set control)
+  int gate_rows;       // > 0: gate is a [groups, N] table, row m uses group m / gate_rows (per-frame adaLN gates)
 };
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {
@@ -155,7 +158,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * GEMM_BN;
-      constexpr bool kOutBf16 = (EPI == EPI_BF16 || EPI == EPI_GELU_BF16);
+      constexpr bool kOutBf16 = (EPI == EPI_BF16 || EPI == EPI_GELU_BF16 || EPI == EPI_RESID_BF16);
       constexpr int CH = kOutBf16 ? 64 : 32;
 #pragma unroll 1
       for (int c = 0; c < GEMM_BN; c += CH) {
@@ -181,6 +184,28 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const float b0 = (ok && p.bias) ? __bfloat162float(p.bias[col]) : 0.f;
           const float b1 = (ok && p.bias) ? __bfloat162float(p.bias[col + 1]) : 0.f;
           bf16* dst = static_cast<bf16*>(p.out) + static_cast<size_t>(m0) * p.ldo + col;
+          if (EPI == EPI_RESID_BF16) {
+            const int rows_ok = min(32, p.M - m0);
+            uint32_t xv[32];
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr)
+              xv[rr] = (ok && rr < rows_ok) ? *reinterpret_cast<const uint32_t*>(dst + static_cast<size_t>(rr) * p.ldo) : 0u;
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) {
+              if (ok && rr < rows_ok) {
+                float g0 = 1.f, g1 = 1.f;
+                if (p.gate) {
+                  const float* gp = p.gate + (p.gate_rows > 0 ? static_cast<size_t>((m0 + rr) / p.gate_rows) * p.N : 0) + col;
+                  g0 = gp[0]; g1 = gp[1];
+                }
+                const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xv[rr]));
+                const float y0 = bf16_round(tile[rr * EPI_LD + 2 * lane] + b0);
+                const float y1 = bf16_round(tile[rr * EPI_LD + 2 * lane + 1] + b1);
+                *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(rr) * p.ldo) =
+                    pack_bf16x2(__fadd_rn(x.x, __fmul_rn(g0, y0)), __fadd_rn(x.y, __fmul_rn(g1, y1)));
+              }
+            }
+          } else {
 #pragma unroll 8
           for (int rr = 0; rr < 32; ++rr) {
             if (m0 + rr < p.M && ok) {
@@ -190,10 +215,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(rr) * p.ldo) = pack_bf16x2(y0, y1);
             }
           }
+          }
         } else {
           const int col = n + lane;
           const float b0 = p.bias ? __bfloat162float(p.bias[col]) : 0.f;
-          const float g0 = (EPI == EPI_RESID_F32 && p.gate) ? p.gate[col] : 1.f;
+          const float g0 = (EPI == EPI_RESID_F32 && p.gate && p.gate_rows == 0) ? p.gate[col] : 1.f;
           float* dst = static_cast<float*>(p.out) + static_cast<size_t>(m0) * p.ldo + col;
           const int rows_ok = min(32, p.M - m0);          // warp-uniform
           if (EPI == EPI_RESID_F32) {
@@ -205,7 +231,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int rr = 0; rr < 32; ++rr) {
               if (rr < rows_ok) {
                 const float y = bf16_round(tile[rr * EPI_LD + lane] + b0);
-                dst[static_cast<size_t>(rr) * p.ldo] = __fadd_rn(xv[rr], __fmul_rn(y, g0));   // x + y*e: two roundings, like torch
+                const float g = (p.gate && p.gate_rows > 0) ? p.gate[static_cast<size_t>((m0 + rr) / p.gate_rows) * p.N + col] : g0;
+                dst[static_cast<size_t>(rr) * p.ldo] = __fadd_rn(xv[rr], __fmul_rn(y, g));   // x + y*e: two roundings, like torch
               }
             }
           } else {
@@ -264,7 +291,7 @@ static int launch_gemm(const void* A, int lda, const void* W, int ldw, const Gem
 }  // namespace wf
 
 extern "C" int wf_gemm_bf16(const void* a, int lda, const void* w, int ldw, const void* bias, void* out, int ldo,
-                            const float* gate, int M, int N, int K, int epilogue, void* stream) {
+                            const float* gate, int gate_rows, int M, int N, int K, int epilogue, void* stream) {
   using namespace wf;
   WF_REQUIRE(a && w && out, "wf_gemm_bf16: null pointer");
   WF_REQUIRE(M > 0 && N > 0 && K > 0, "wf_gemm_bf16: empty problem");
@@ -276,13 +303,15 @@ extern "C" int wf_gemm_bf16(const void* a, int lda, const void* w, int ldw, cons
   // n-tiles per raster group: keep group_n weight column-blocks (256 x K bf16 each) within ~40 MB of L2
   const long long col_block_bytes = 2ll * GEMM_BN * K;
   int group_n = static_cast<int>(std::max<long long>(1, (40ll << 20) / col_block_bytes));
-  GemmArgs args{M, N, K, static_cast<const bf16*>(bias), out, ldo, gate, group_n};
+  WF_REQUIRE(gate_rows >= 0, "wf_gemm_bf16: gate_rows must be >= 0");
+  GemmArgs args{M, N, K, static_cast<const bf16*>(bias), out, ldo, gate, group_n, gate_rows};
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (epilogue) {
     case EPI_BF16: return launch_gemm<EPI_BF16>(a, lda, w, ldw, args, s);
     case EPI_GELU_BF16: return launch_gemm<EPI_GELU_BF16>(a, lda, w, ldw, args, s);
     case EPI_RESID_F32: return launch_gemm<EPI_RESID_F32>(a, lda, w, ldw, args, s);
     case EPI_F32_OF_BF16: return launch_gemm<EPI_F32_OF_BF16>(a, lda, w, ldw, args, s);
+    case EPI_RESID_BF16: return launch_gemm<EPI_RESID_BF16>(a, lda, w, ldw, args, s);
   }
   return fail(WF_EINVAL, "wf_gemm_bf16: unknown epilogue");
 }

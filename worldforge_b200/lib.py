@@ -16,7 +16,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwf_b200.so")
 
-EPI_BF16, EPI_GELU_BF16, EPI_RESID_F32, EPI_F32_OF_BF16 = 0, 1, 2, 3
+EPI_BF16, EPI_GELU_BF16, EPI_RESID_F32, EPI_F32_OF_BF16, EPI_RESID_BF16 = 0, 1, 2, 3, 4
 
 
 class WfError(RuntimeError):
@@ -29,12 +29,16 @@ timed_attention = None   # bench.py: a list here collects a CUDA-event pair arou
 
 _vp, _i, _f, _ll, _u = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_uint
 _SIGNATURES = {
-    "wf_gemm_bf16": [_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp],
+    "wf_gemm_bf16": [_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
     "wf_attention_bf16": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _f, _vp],
-    "wf_layer_norm": [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp],
+    "wf_layer_norm": [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _vp],
     "wf_rms_norm_rope": [_vp, _i, _vp, _vp, _i, _i, _f, _vp],
     "wf_patchify": [_vp, _vp, _i, _i, _i, _i, _vp],
-    "wf_dit_head": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _f, _i, _vp],
+    "wf_dit_head": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _f, _i, _i, _i, _vp],
+    "wf_rms_norm_head_rope": [_vp, _i, _vp, _vp, _ll, _i, _f, _vp],
+    "wf_swiglu_bf16": [_vp, _vp, _ll, _i, _vp],
+    "wf_timestep_embedding_f32": [_vp, _vp, _i, _i, _vp],
+    "wf_small_gemm_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "wf_gemv_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "wf_gelu_erf_bf16": [_vp, _ll, _vp],
     "wf_time_sinusoid": [_vp, _vp, _i, _vp],
@@ -121,18 +125,19 @@ def _is_bf16(t: torch.Tensor) -> int:
 # ---------------------------------------------------------------------------- DiT kernels
 
 def gemm_bf16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor,
-              epilogue: int = EPI_BF16, gate: Optional[torch.Tensor] = None):
+              epilogue: int = EPI_BF16, gate: Optional[torch.Tensor] = None, gate_rows: int = 0):
     """out = epilogue(a[M,K] @ w[N,K]^T + bias); a/w bf16 with contiguous K, out [M, N] view (row stride ldo)."""
     M, K = a.shape
     N = w.shape[0]
     assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1 and out.stride(1) == 1
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
     assert out.shape == (M, N)
-    want = torch.bfloat16 if epilogue in (EPI_BF16, EPI_GELU_BF16) else torch.float32
+    want = torch.bfloat16 if epilogue in (EPI_BF16, EPI_GELU_BF16, EPI_RESID_BF16) else torch.float32
     assert out.dtype == want, f"epilogue {epilogue} writes {want}"
     assert bias is None or (bias.dtype == torch.bfloat16 and bias.numel() == N)
-    assert gate is None or (gate.dtype == torch.float32 and gate.numel() == N)
-    _call("wf_gemm_bf16", _p(a), a.stride(0), _p(w), w.stride(0), _p(bias), _p(out), out.stride(0), _p(gate),
+    assert gate is None or (gate.dtype == torch.float32 and gate.is_contiguous() and
+                            gate.numel() == (N if gate_rows == 0 else N * ((M + gate_rows - 1) // gate_rows)))
+    _call("wf_gemm_bf16", _p(a), a.stride(0), _p(w), w.stride(0), _p(bias), _p(out), out.stride(0), _p(gate), gate_rows,
           M, N, K, epilogue, _stream())
     return out
 
@@ -154,13 +159,17 @@ def attention_bf16(q, k, v, out, heads: int, add_in=None, softmax_scale: Optiona
     return out
 
 
-def layer_norm(x, out, eps: float, scale=None, shift=None, weight=None, bias=None, round_norm_bf16: bool = False):
+def layer_norm(x, out, eps: float, scale=None, shift=None, weight=None, bias=None, round_norm_bf16: bool = False,
+               rows_per_group: int = 0):
     rows, D = x.shape
     assert x.stride(1) == 1 and out.stride(1) == 1 and out.shape == x.shape
-    for t in (scale, shift, weight, bias):
+    groups = 1 if rows_per_group == 0 else (rows + rows_per_group - 1) // rows_per_group
+    for t in (scale, shift):
+        assert t is None or (t.dtype == torch.float32 and t.numel() == D * groups and t.is_contiguous())
+    for t in (weight, bias):
         assert t is None or (t.dtype == torch.float32 and t.numel() == D and t.is_contiguous())
     _call("wf_layer_norm", _p(x), x.stride(0), _is_bf16(x), _p(out), out.stride(0), _is_bf16(out), _p(scale), _p(shift),
-          _p(weight), _p(bias), rows, D, eps, int(round_norm_bf16), _stream())
+          _p(weight), _p(bias), rows, D, eps, int(round_norm_bf16), rows_per_group, _stream())
     return out
 
 
@@ -182,14 +191,14 @@ def patchify(hidden, cols):
     return cols
 
 
-def dit_head(x, scale, shift, w, b, out, grid, eps: float, tok_offset: int = 0):
+def dit_head(x, scale, shift, w, b, out, grid, eps: float, tok_offset: int = 0, rows_per_group: int = 0, round_bf16: bool = False):
     L, D = x.shape
     F_, GH, GW = grid
     cout = w.shape[0] // 4
-    assert x.dtype == torch.float32 and x.stride(1) == 1 and w.is_contiguous() and w.dtype == torch.float32
+    assert x.stride(1) == 1 and w.is_contiguous() and w.dtype == torch.float32
     assert out.dtype == torch.float32 and out.is_contiguous() and out.shape == (cout, F_, 2 * GH, 2 * GW)
-    _call("wf_dit_head", _p(x), x.stride(0), L, D, _p(scale), _p(shift), _p(w), _p(b), cout, _p(out), F_, GH, GW, eps,
-          tok_offset, _stream())
+    _call("wf_dit_head", _p(x), _is_bf16(x), x.stride(0), L, D, _p(scale), _p(shift), _p(w), _p(b), cout, _p(out), F_, GH, GW,
+          eps, tok_offset, rows_per_group, int(round_bf16), _stream())
     return out
 
 
@@ -205,6 +214,38 @@ def gelu_erf_bf16_(x):
     assert x.dtype == torch.bfloat16 and x.is_contiguous()
     _call("wf_gelu_erf_bf16", _p(x), x.numel(), _stream())
     return x
+
+
+def rms_norm_head_rope_(x, gain, eps: float, rope=None):
+    """In place on a bf16 [rows, heads*128] view; gain bf16 [128]; rope fp32 [rows, 64, 2] or None."""
+    rows, W = x.shape
+    assert x.dtype == torch.bfloat16 and x.stride(1) == 1 and W % 128 == 0
+    assert gain.dtype == torch.bfloat16 and gain.numel() == 128
+    assert rope is None or (rope.dtype == torch.float32 and rope.shape == (rows, 64, 2) and rope.is_contiguous())
+    _call("wf_rms_norm_head_rope", _p(x), x.stride(0), _p(gain), _p(rope), rows, W // 128, eps, _stream())
+    return x
+
+
+def swiglu_bf16(inp, out):
+    rows, F2 = inp.shape
+    assert inp.dtype == torch.bfloat16 and inp.is_contiguous() and out.is_contiguous() and out.shape == (rows, F2 // 2)
+    _call("wf_swiglu_bf16", _p(inp), _p(out), rows, F2 // 2, _stream())
+    return out
+
+
+def timestep_embedding_f32(t, out):
+    assert t.dtype == torch.float32 and out.dtype == torch.float32 and out.is_contiguous() and out.shape[0] == t.numel()
+    _call("wf_timestep_embedding_f32", _p(t.contiguous()), _p(out), t.numel(), out.shape[1], _stream())
+    return out
+
+
+def small_gemm_f32(x, w, b, out, silu_in=False):
+    T, K = x.shape
+    R = w.shape[0]
+    assert x.dtype == torch.float32 and x.is_contiguous() and w.dtype == torch.bfloat16 and w.is_contiguous() and w.shape[1] == K
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.shape == (T, R)
+    _call("wf_small_gemm_f32", _p(x), _p(w), _p(b), _p(out), T, R, K, int(silu_in), _stream())
+    return out
 
 
 def time_sinusoid(timestep, out):

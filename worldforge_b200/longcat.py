@@ -1,0 +1,223 @@
+"""LongCat-Video DiT forward on the sm_100a kernels: the object that stands in for ``pipe.dit``.
+
+Call surface of the reference pipeline (longcat_for_worldforge/longcat_video/pipeline_longcat_video.py:867-873):
+``dit(hidden_states[B,16,T,H,W], timestep[B,T], encoder_hidden_states[B,1,N,4096], encoder_attention_mask[B,N],
+num_cond_latents=1) -> fp32 Tensor[B,16,T,H,W]``, plus ``.dtype`` (:725), ``.config.in_channels`` (:773),
+``.cp_split_hw`` (:689).
+
+The arithmetic is ``LongCatVideoTransformer3DModel`` (longcat_video/modules/longcat_video_dit.py:280-370) in the
+reference's GPU configuration - bf16 module, fp32 islands (see oracle/longcat_dit.py): bf16 residual stream, per-FRAME
+adaLN modulation (timestep [B,T], the condition frame at t = 0), per-head RMSNorm with a bf16 gain, fp32 rotate-half RoPE,
+condition / noise split self-attention (attention.py:124-135), cross-attention for the noise tokens only (:262-273),
+SwiGLU feed-forward.  It reuses the Wan kernels (tcgen05 GEMM with a bf16-residual epilogue and per-frame gates,
+tcgen05 flash attention on column slices of the fused qkv buffer, fused LayerNorm+modulate) plus four LongCat-specific
+ones (``wf_rms_norm_head_rope``, ``wf_swiglu_bf16``, ``wf_timestep_embedding_f32``, ``wf_small_gemm_f32``).
+
+LoRA (longcat_video_dit.py:197-249): the reference applies ``W x + m*a*up(down(x))`` at run time; merge it into the weights
+before ``from_state_dict`` (``W' = W + m*a*up@down``) - not done here.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from types import SimpleNamespace
+from typing import Dict, Tuple
+
+import torch
+
+from . import lib
+
+BF, F32 = torch.bfloat16, torch.float32
+
+
+@dataclass
+class LongCatConfig:
+    in_channels: int = 16
+    out_channels: int = 16
+    hidden_size: int = 4096
+    depth: int = 48
+    num_heads: int = 32
+    caption_channels: int = 4096
+    mlp_ratio: int = 4
+    adaln_tembed_dim: int = 512
+    frequency_embedding_size: int = 256
+    patch: Tuple[int, int, int] = (1, 2, 2)
+
+    @property
+    def ffn_dim(self):
+        h = int(2 * int(self.hidden_size * self.mlp_ratio) / 3)
+        return 256 * ((h + 255) // 256)
+
+
+def rope_table(grid, head_dim: int = 128) -> torch.Tensor:
+    """fp32 [N, head_dim/2, 2] (cos, sin) of rope_3d.py:63-95,109-112: fp32 angles position*freq, then cos / sin in fp32.
+    The reference repeats every frequency for the two members of a pair, so one (cos, sin) per pair suffices."""
+    T, H, W = grid
+    d6 = head_dim // 6
+    parts = []
+    for n, dim in zip((T, H, W), (head_dim - 4 * d6, 2 * d6, 2 * d6)):
+        f = 1.0 / (10000 ** (torch.arange(0, dim, 2)[: dim // 2].float() / dim))
+        parts.append(torch.arange(n, dtype=F32)[:, None] * f[None])
+    ft, fh, fw = parts
+    a = torch.cat([ft[:, None, None, :].expand(T, H, W, -1), fh[None, :, None, :].expand(T, H, W, -1),
+                   fw[None, None, :, :].expand(T, H, W, -1)], dim=-1).reshape(T * H * W, head_dim // 2)
+    return torch.stack([a.cos(), a.sin()], dim=-1).contiguous()
+
+
+class WfLongCatTransformer:
+    def __init__(self, cfg: LongCatConfig, device):
+        assert cfg.hidden_size // cfg.num_heads == 128 and cfg.patch == (1, 2, 2)
+        self.cfg, self.device = cfg, torch.device(device)
+        self.dtype = BF
+        self.config = SimpleNamespace(in_channels=cfg.in_channels, out_channels=cfg.out_channels, patch_size=cfg.patch)
+        self.cp_split_hw = [1, 1]
+        self.blocks = []
+        self._buf, self._rope, self._ctx_cache = {}, {}, {}
+        self.calls = 0
+
+    def to(self, *a, **k):
+        return self
+
+    @classmethod
+    def from_state_dict(cls, sd: Dict[str, torch.Tensor], cfg: LongCatConfig, device) -> "WfLongCatTransformer":
+        self = cls(cfg, device)
+        dev = self.device
+        bf = lambda k: sd[k].to(device=dev, dtype=BF).contiguous()
+        f32_of_bf = lambda k: sd[k].to(device=dev, dtype=BF).to(F32).contiguous()       # bf16 parameter used in an fp32 island
+        C = cfg.hidden_size
+        self.patch_w = sd["x_embedder.proj.weight"].flatten(1).to(device=dev, dtype=BF).contiguous()
+        self.patch_b = bf("x_embedder.proj.bias")
+        self.t0_w, self.t0_b, self.t2_w, self.t2_b = bf("t_embedder.mlp.0.weight"), bf("t_embedder.mlp.0.bias"), bf("t_embedder.mlp.2.weight"), bf("t_embedder.mlp.2.bias")
+        self.y0_w, self.y0_b, self.y2_w, self.y2_b = bf("y_embedder.y_proj.0.weight"), bf("y_embedder.y_proj.0.bias"), bf("y_embedder.y_proj.2.weight"), bf("y_embedder.y_proj.2.bias")
+        self.final_w, self.final_b = f32_of_bf("final_layer.linear.weight"), f32_of_bf("final_layer.linear.bias")
+        ada_w, ada_b = [], []
+        for i in range(cfg.depth):
+            p = f"blocks.{i}."
+            b = SimpleNamespace()
+            b.qkv_w, b.qkv_b = bf(p + "attn.qkv.weight"), bf(p + "attn.qkv.bias")
+            b.qn, b.kn = bf(p + "attn.q_norm.weight"), bf(p + "attn.k_norm.weight")
+            b.proj_w, b.proj_b = bf(p + "attn.proj.weight"), bf(p + "attn.proj.bias")
+            b.cq_w, b.cq_b = bf(p + "cross_attn.q_linear.weight"), bf(p + "cross_attn.q_linear.bias")
+            b.ckv_w, b.ckv_b = bf(p + "cross_attn.kv_linear.weight"), bf(p + "cross_attn.kv_linear.bias")
+            b.cproj_w, b.cproj_b = bf(p + "cross_attn.proj.weight"), bf(p + "cross_attn.proj.bias")
+            b.cqn, b.ckn = bf(p + "cross_attn.q_norm.weight"), bf(p + "cross_attn.k_norm.weight")
+            b.n_w, b.n_b = f32_of_bf(p + "pre_crs_attn_norm.weight"), f32_of_bf(p + "pre_crs_attn_norm.bias")
+            b.w13 = torch.cat([sd[p + "ffn.w1.weight"], sd[p + "ffn.w3.weight"]], dim=0).to(device=dev, dtype=BF).contiguous()
+            b.w2 = bf(p + "ffn.w2.weight")
+            self.blocks.append(b)
+            ada_w.append(sd[p + "adaLN_modulation.1.weight"]); ada_b.append(sd[p + "adaLN_modulation.1.bias"])
+        ada_w.append(sd["final_layer.adaLN_modulation.1.weight"]); ada_b.append(sd["final_layer.adaLN_modulation.1.bias"])
+        self.ada_w = torch.cat(ada_w, dim=0).to(device=dev, dtype=BF).contiguous()      # [(6*depth + 2)*C, A]
+        self.ada_b = torch.cat(ada_b, dim=0).to(device=dev, dtype=BF).contiguous()
+        return self
+
+    def _buffers(self, N, Nn, T):
+        key = (N, Nn, T)
+        if key not in self._buf:
+            c, dev = self.cfg, self.device
+            C, Fd = c.hidden_size, c.ffn_dim
+            e = lambda *s, dt=BF: torch.empty(*s, dtype=dt, device=dev)
+            self._buf[key] = SimpleNamespace(
+                cols=e(N, c.in_channels * 4), x=e(N, C), h=e(N, C), qkv=e(N, 3 * C), att=e(N, C), cq=e(Nn, C), ca=e(Nn, C),
+                h13=e(N, 2 * Fd), ff=e(N, Fd), temb=e(T, c.frequency_embedding_size, dt=F32), t1=e(T, c.adaln_tembed_dim, dt=F32),
+                t=e(T, c.adaln_tembed_dim, dt=F32), mod=e(T, (6 * c.depth + 2) * C, dt=F32))
+        return self._buf[key]
+
+    def _context(self, ctx):
+        """Caption embedding and every block's cross-attention K|V: functions of the prompt only, computed once."""
+        key = (ctx.data_ptr(), ctx._version, ctx.shape[0])
+        if key in self._ctx_cache:
+            return self._ctx_cache[key]
+        c, dev = self.cfg, self.device
+        M, C = ctx.shape[0], c.hidden_size
+        e = lambda *s: torch.empty(*s, dtype=BF, device=dev)
+        y1 = lib.gemm_bf16(ctx.to(BF).contiguous(), self.y0_w, self.y0_b, e(M, C), lib.EPI_GELU_BF16)
+        y = lib.gemm_bf16(y1, self.y2_w, self.y2_b, e(M, C), lib.EPI_BF16)
+        kvs = []
+        for b in self.blocks:
+            kv = lib.gemm_bf16(y, b.ckv_w, b.ckv_b, e(M, 2 * C), lib.EPI_BF16)
+            # kv_linear output is [M, 2, H, 128] (attention.py:215): k = first C columns, v = last C
+            lib.rms_norm_head_rope_(kv[:, :C], b.ckn, 1e-6, None)
+            kvs.append(kv)
+        if len(self._ctx_cache) >= 4:
+            self._ctx_cache.pop(next(iter(self._ctx_cache)))
+        self._ctx_cache[key] = kvs
+        return kvs
+
+    @torch.no_grad()
+    def __call__(self, hidden_states, timestep, encoder_hidden_states, encoder_attention_mask=None, num_cond_latents: int = 0, **kw):
+        if not hidden_states.is_cuda:
+            raise lib.WfError("WfLongCatTransformer runs on CUDA tensors only (no CPU fallback)")
+        B = hidden_states.shape[0]
+        if timestep.dim() == 1:
+            timestep = timestep.unsqueeze(1).expand(-1, hidden_states.shape[2])
+        outs = []
+        for s in range(B):
+            ctx = encoder_hidden_states[s, 0]
+            if encoder_attention_mask is not None:
+                m = encoder_attention_mask[s].reshape(-1) != 0
+                n_valid = int(m.sum())
+                if not bool(m[:n_valid].all()):
+                    ctx = ctx[m]                       # general mask: gather the valid tokens (longcat_video_dit.py:323)
+                else:
+                    ctx = ctx[:n_valid]
+            outs.append(self._forward_one(hidden_states[s], timestep[s], ctx, num_cond_latents))
+        return torch.stack(outs)
+
+    def _forward_one(self, x, timestep, ctx, num_cond):
+        c = self.cfg
+        self.calls += 1
+        C, Hn, Fd = c.hidden_size, c.num_heads, c.ffn_dim
+        xb = x.to(BF).contiguous()
+        _, T, H, W = xb.shape
+        grid = (T, H // 2, W // 2)
+        per = grid[1] * grid[2]
+        N = T * per
+        nc = num_cond * per
+        Nn = N - nc
+        Bf = self._buffers(N, Nn, T)
+        if grid not in self._rope:
+            self._rope[grid] = rope_table(grid).to(self.device)
+        rope = self._rope[grid]
+
+        lib.patchify(xb, Bf.cols)
+        lib.gemm_bf16(Bf.cols, self.patch_w, self.patch_b, Bf.x, lib.EPI_BF16)
+        # per-frame timestep embedding and ALL adaLN tables in fp32: timestep.to(bf16).float() as the reference does (:307,:313)
+        ts = timestep.to(BF).to(F32).contiguous()
+        lib.timestep_embedding_f32(ts, Bf.temb)
+        lib.small_gemm_f32(Bf.temb, self.t0_w, self.t0_b, Bf.t1)
+        lib.small_gemm_f32(Bf.t1, self.t2_w, self.t2_b, Bf.t, silu_in=True)
+        lib.small_gemm_f32(Bf.t, self.ada_w, self.ada_b, Bf.mod, silu_in=True)
+        mod = Bf.mod.view(T, 6 * c.depth + 2, C).permute(1, 0, 2).contiguous()      # [table, T, C]: each table contiguous
+        kvs = self._context(ctx)
+
+        for i, b in enumerate(self.blocks):
+            # [T, C] tables of this block: shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp (chunk order, :83-85)
+            tab = [mod[6 * i + j] for j in range(6)]
+            lib.layer_norm(Bf.x, Bf.h, 1e-6, scale=tab[1], shift=tab[0], rows_per_group=per)
+            lib.gemm_bf16(Bf.h, b.qkv_w, b.qkv_b, Bf.qkv, lib.EPI_BF16)
+            lib.rms_norm_head_rope_(Bf.qkv[:, :C], b.qn, 1e-6, rope)
+            lib.rms_norm_head_rope_(Bf.qkv[:, C:2 * C], b.kn, 1e-6, rope)
+            q, k, v = Bf.qkv[:, :C], Bf.qkv[:, C:2 * C], Bf.qkv[:, 2 * C:]
+            if nc > 0:      # condition tokens see only condition tokens; noise tokens see everything (attention.py:124-135)
+                lib.attention_bf16(q[:nc], k[:nc], v[:nc], Bf.att[:nc], Hn)
+                lib.attention_bf16(q[nc:], k, v, Bf.att[nc:], Hn)
+            else:
+                lib.attention_bf16(q, k, v, Bf.att, Hn)
+            lib.gemm_bf16(Bf.att, b.proj_w, b.proj_b, Bf.x, lib.EPI_RESID_BF16, gate=tab[2], gate_rows=per)
+            # cross attention, noise tokens only
+            lib.layer_norm(Bf.x, Bf.h, 1e-6, weight=b.n_w, bias=b.n_b)
+            lib.gemm_bf16(Bf.h[nc:], b.cq_w, b.cq_b, Bf.cq, lib.EPI_BF16)
+            lib.rms_norm_head_rope_(Bf.cq, b.cqn, 1e-6, None)
+            kv = kvs[i]
+            lib.attention_bf16(Bf.cq, kv[:, :C], kv[:, C:], Bf.ca, Hn)
+            lib.gemm_bf16(Bf.ca, b.cproj_w, b.cproj_b, Bf.x[nc:], lib.EPI_RESID_BF16)
+            # SwiGLU feed-forward
+            lib.layer_norm(Bf.x, Bf.h, 1e-6, scale=tab[4], shift=tab[3], rows_per_group=per)
+            lib.gemm_bf16(Bf.h, b.w13, None, Bf.h13, lib.EPI_BF16)
+            lib.swiglu_bf16(Bf.h13, Bf.ff)
+            lib.gemm_bf16(Bf.ff, b.w2, None, Bf.x, lib.EPI_RESID_BF16, gate=tab[5], gate_rows=per)
+
+        shift, scale = mod[6 * c.depth], mod[6 * c.depth + 1]
+        out = torch.empty(c.out_channels, T, H, W, dtype=F32, device=self.device)
+        lib.dit_head(Bf.x, scale, shift, self.final_w, self.final_b, out, grid, 1e-6, rows_per_group=per, round_bf16=True)
+        return out
