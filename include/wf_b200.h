@@ -148,9 +148,17 @@ int wf_latent_denorm(const void* x0, int is_bf16, float* out, const float* mean,
 int wf_latent_norm_replace(const float* enc, const void* x0, int is_bf16, void* out, const float* mean,
                            const float* inv_std, unsigned replace_mask, int channels, long long per_channel,
                            void* stream);
-/* FLF scoring front end, scheduler :376-378 + :175-176: global min-max normalise, *255, truncate to uint8 */
+/* FLF scoring front end: min-max normalise the n elements and quantise to uint8.
+ * mode 0 - Wan selector (scheduler :376-378 + :175-176): n*255, truncated, over the whole 16-channel tensor;
+ * mode 1 - LongCat selector (scheduling_flow_match_euler_discrete.py:329-330 + :147-151), called per channel:
+ *          ((n+1)*127.5).clip(0,255), truncated. */
 long long wf_quantise_workspace_bytes(void);
-int wf_quantise_u8(const void* x, int is_bf16, unsigned char* out, long long n, void* workspace, void* stream);
+int wf_quantise_u8(const void* x, int is_bf16, unsigned char* out, long long n, int mode, void* workspace, void* stream);
+/* LongCat CFG-zero + sign flip (pipeline_longcat_video.py:374-383, 875-888), fp32:
+ * st = <cond,uncond>/(|uncond|^2 + 1e-8); out = -(uncond*st + scale*(cond - uncond*st)).  workspace: wf_dsg_workspace_bytes().
+ * stats (device float[1] or NULL) receives st. */
+int wf_cfg_zero(const float* cond, const float* uncond, float* out, float scale, long long n, void* workspace, float* stats,
+                void* stream);
 
 /* ---- Wan 3D-VAE (wan/modules/vae.py), channels-last fp32 activations [T][H][W][C] ------------------------ */
 

@@ -56,3 +56,27 @@ class OracleVAE:
     def decode(self, z, return_dict=False):
         assert z.shape[0] == 1
         return (wan_vae.decode(self.P, self.cfg, z[0].cpu()).unsqueeze(0).to(z.device),)
+
+
+class OracleLongCatDit:
+    """Quacks like ``pipe.dit`` (pipeline_longcat_video.py:867-873) on top of oracle.longcat_dit."""
+
+    def __init__(self, params, cfg, amp: bool = True):
+        from . import longcat_dit
+        self._ld = longcat_dit
+        self.P, self.cfg, self.amp = params, cfg, amp
+        self.dtype = torch.bfloat16
+        self.config = SimpleNamespace(in_channels=cfg.in_channels)
+        self.cp_split_hw = [1, 1]
+        self.calls = 0
+
+    def __call__(self, hidden_states, timestep, encoder_hidden_states, encoder_attention_mask=None, num_cond_latents=0, **kw):
+        outs = []
+        for s in range(hidden_states.shape[0]):
+            ctx = encoder_hidden_states[s, 0]
+            if encoder_attention_mask is not None:
+                ctx = ctx[encoder_attention_mask[s].reshape(-1) != 0]
+            self.calls += 1
+            outs.append(self._ld.dit_forward(self.P, self.cfg, hidden_states[s].cpu(), timestep[s].cpu(), ctx.cpu(),
+                                             num_cond_latents=num_cond_latents, amp=self.amp))
+        return torch.stack(outs).to(hidden_states.device)

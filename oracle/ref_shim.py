@@ -94,6 +94,8 @@ def install_diffusers_shim() -> None:
     ut.deprecate = lambda *a, **k: None
     ut.is_scipy_available = lambda: True
     ut.BaseOutput = _BaseOutput
+    import logging as _logging
+    ut.logging = types.SimpleNamespace(get_logger=_logging.getLogger)
     sc = mod("diffusers.schedulers"); su = mod("diffusers.schedulers.scheduling_utils")
     su.KarrasDiffusionSchedulers = _Karras
     su.SchedulerMixin = _SchedulerMixin
@@ -250,3 +252,13 @@ def load_longcat_dit_module():
     cpu = importlib.import_module("longcat_video.context_parallel.context_parallel_util")
     cpu.cp_size = 1
     return importlib.import_module("longcat_video.modules.longcat_video_dit")
+
+
+def load_longcat_scheduler_module():
+    assert os.path.isdir(REF_LONGCAT)
+    install_diffusers_shim()
+    spec = importlib.util.spec_from_file_location(
+        "wf_ref_longcat_scheduling", os.path.join(REF_LONGCAT, "longcat_video", "modules", "scheduling_flow_match_euler_discrete.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m

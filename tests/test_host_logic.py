@@ -165,3 +165,27 @@ def test_latent_stats_rounding():
     assert sh[3] == float((1.0 / torch.tensor(wan_vae.LATENTS_STD[3]).bfloat16()).float())
     m32, s32 = wsched.latent_stats(wan_vae.LATENTS_MEAN, wan_vae.LATENTS_STD, torch.float32)
     assert abs(s32[3] - 1 / 2.6558) < 1e-7
+
+
+def test_longcat_host_logic_matches_oracle():
+    from oracle import longcat_sched as ols
+    from worldforge_b200 import longcat, longcat_pipeline as wlp
+    from oracle import longcat_dit as old
+    for n, d in [(50, False), (16, True), (4, True)]:
+        assert torch.equal(wlp.timesteps_sigmas(n, d), ols.timesteps_sigmas(n, d))
+        a, b = ols.OracleEuler(shift=1.0), wlp.WfFlowMatchEulerScheduler(shift=1.0)
+        a.set_timesteps(n, sigmas=ols.timesteps_sigmas(n, d)); b.set_timesteps(n, sigmas=wlp.timesteps_sigmas(n, d))
+        assert torch.equal(a.sigmas, b.sigmas) and torch.equal(a.timesteps, b.timesteps)
+    rng = np.random.RandomState(1)
+    for step in (2, 3, 4, 5, 6, 20):
+        for dist in (False, True):
+            for cap in (None, 1, 3):
+                sc = rng.rand(16).tolist()
+                assert wlp.selection_policy(sc, step, dist, cap) == ols.policy(sc, step, dist, cap)
+    g = torch.Generator().manual_seed(2)
+    x, y = torch.randn(8, 2, 12, 16, generator=g) * 3, torch.randn(8, 2, 12, 16, generator=g) * 3
+    assert wlp.flow_similarity(x, y) == ols.flow_similarity(x.unsqueeze(0), y.unsqueeze(0))
+    fr = old.rope_freqs(128, (2, 3, 4))
+    tab = longcat.rope_table((2, 3, 4))
+    assert torch.equal(tab[..., 0], fr.cos()[:, 0::2]) and torch.equal(tab[..., 1], fr.sin()[:, 0::2])
+    assert longcat.LongCatConfig().ffn_dim == old.LongCatConfig().ffn_dim == 11008

@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(256) minmax_kernel(const void* x, bool bf, siz
     partial[blockIdx.x] = lo; partial[gridDim.x + blockIdx.x] = hi;
   }
 }
-__global__ void __launch_bounds__(256) quantise_u8_kernel(const void* x, bool bf, size_t n, const float* partial, int nparts, uint8_t* out) {
+__global__ void __launch_bounds__(256) quantise_u8_kernel(const void* x, bool bf, size_t n, const float* partial, int nparts, uint8_t* out, int mode) {
   __shared__ float s_lo, s_rng;
   if (threadIdx.x < 32) {
     float lo = INFINITY, hi = -INFINITY;
@@ -279,8 +279,54 @@ __global__ void __launch_bounds__(256) quantise_u8_kernel(const void* x, bool bf
   const float lo = s_lo, rng = s_rng;
   WF_GRID_STRIDE(i, n) {
     const float v = t_load(x, bf, i).v;
-    const float q = __fmul_rn(__fdiv_rn(__fsub_rn(v, lo), rng), 255.0f);
+    const float nrm = __fdiv_rn(__fsub_rn(v, lo), rng);
+    // mode 0 (Wan selector): n*255, truncated.  mode 1 (LongCat selector): the [0,1] value goes through the "[-1,1] video"
+    // branch, ((n + 1) * 127.5).clip(0, 255) truncated - i.e. onto the upper half of the uint8 range
+    float q = mode == 0 ? __fmul_rn(nrm, 255.0f) : fminf(fmaxf(__fmul_rn(__fadd_rn(nrm, 1.0f), 127.5f), 0.0f), 255.0f);
     out[i] = static_cast<uint8_t>(static_cast<int>(q));
+  }
+}
+
+// ------------------------------------------------------------------------- CFG-zero (LongCat)
+// st* = <c,u> / (|u|^2 + 1e-8);  out = -(u*st + s*(c - u*st))   (pipeline_longcat_video.py:374-383, 875-888), fp32
+__global__ void __launch_bounds__(DSG_THREADS) cfgz_reduce_kernel(const float4* c, const float4* u, size_t n4, float* partial) {
+  __shared__ float red[2][DSG_THREADS / 32];
+  float s0 = 0.f, s1 = 0.f;
+  WF_GRID_STRIDE(i, n4) {
+    const float4 a = c[i], b = u[i];
+    s0 += __fmul_rn(a.x, b.x) + __fmul_rn(a.y, b.y) + __fmul_rn(a.z, b.z) + __fmul_rn(a.w, b.w);
+    s1 += __fmul_rn(b.x, b.x) + __fmul_rn(b.y, b.y) + __fmul_rn(b.z, b.z) + __fmul_rn(b.w, b.w);
+  }
+  s0 = warp_sum_f(s0); s1 = warp_sum_f(s1);
+  const int wp = threadIdx.x >> 5, ln = threadIdx.x & 31;
+  if (ln == 0) { red[0][wp] = s0; red[1][wp] = s1; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float t = 0.f;
+    for (int k = 0; k < DSG_THREADS / 32; ++k) t += red[threadIdx.x][k];
+    partial[threadIdx.x * gridDim.x + blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(DSG_THREADS) cfgz_apply_kernel(const float4* c, const float4* u, float4* out, size_t n4,
+                                                                 const float* partial, int nparts, float scale, float* stats) {
+  __shared__ float tot[2];
+  if (threadIdx.x < 64) {
+    const int k = threadIdx.x >> 5, ln = threadIdx.x & 31;
+    float t = 0.f;
+    for (int j = ln; j < nparts; j += 32) t += partial[k * nparts + j];
+    t = warp_sum_f(t);
+    if (ln == 0) tot[k] = t;
+  }
+  __syncthreads();
+  const float st = __fdiv_rn(tot[0], __fadd_rn(tot[1], 1e-8f));
+  if (stats && blockIdx.x == 0 && threadIdx.x == 0) stats[0] = st;
+  auto f = [&](float cv, float uv) {
+    const float t1 = __fmul_rn(uv, st);
+    return -__fadd_rn(t1, __fmul_rn(scale, __fsub_rn(cv, t1)));
+  };
+  WF_GRID_STRIDE(i, n4) {
+    const float4 a = c[i], b = u[i];
+    out[i] = make_float4(f(a.x, b.x), f(a.y, b.y), f(a.z, b.z), f(a.w, b.w));
   }
 }
 
@@ -382,13 +428,29 @@ extern "C" int wf_latent_norm_replace(const float* enc, const void* x0, int is_b
 
 extern "C" long long wf_quantise_workspace_bytes(void) { return 2ll * 1024 * sizeof(float); }
 
-extern "C" int wf_quantise_u8(const void* x, int is_bf16, unsigned char* out, long long n, void* workspace, void* stream) {
+extern "C" int wf_quantise_u8(const void* x, int is_bf16, unsigned char* out, long long n, int mode, void* workspace, void* stream) {
   WF_REQUIRE(x && out && workspace && n > 0, "wf_quantise_u8: bad arguments");
   const int blocks = std::min(grid_for(n, 256, 4), 1024);
   float* partial = static_cast<float*>(workspace);
   minmax_kernel<<<blocks, 256, 0, WF_STREAM>>>(x, is_bf16 != 0, static_cast<size_t>(n), partial);
   WF_LAUNCH_OK();
-  quantise_u8_kernel<<<grid_for(n), 256, 0, WF_STREAM>>>(x, is_bf16 != 0, static_cast<size_t>(n), partial, blocks, out);
+  WF_REQUIRE(mode == 0 || mode == 1, "wf_quantise_u8: mode 0 (Wan) or 1 (LongCat)");
+  quantise_u8_kernel<<<grid_for(n), 256, 0, WF_STREAM>>>(x, is_bf16 != 0, static_cast<size_t>(n), partial, blocks, out, mode);
+  WF_LAUNCH_OK();
+  return WF_OK;
+}
+
+extern "C" int wf_cfg_zero(const float* cond, const float* uncond, float* out, float scale, long long n, void* workspace,
+                           float* stats, void* stream) {
+  WF_REQUIRE(cond && uncond && out && workspace, "wf_cfg_zero: null pointer");
+  WF_VEC4_OK(n, "wf_cfg_zero");
+  const int blocks = std::min(grid_for(n / 4, DSG_THREADS, 4), DSG_MAX_BLOCKS);
+  float* partial = static_cast<float*>(workspace);
+  cfgz_reduce_kernel<<<blocks, DSG_THREADS, 0, WF_STREAM>>>(reinterpret_cast<const float4*>(cond), reinterpret_cast<const float4*>(uncond),
+                                                           static_cast<size_t>(n / 4), partial);
+  WF_LAUNCH_OK();
+  cfgz_apply_kernel<<<grid_for(n / 4, DSG_THREADS), DSG_THREADS, 0, WF_STREAM>>>(reinterpret_cast<const float4*>(cond), reinterpret_cast<const float4*>(uncond),
+                                                                               reinterpret_cast<float4*>(out), static_cast<size_t>(n / 4), partial, blocks, scale, stats);
   WF_LAUNCH_OK();
   return WF_OK;
 }

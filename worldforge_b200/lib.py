@@ -51,7 +51,8 @@ _SIGNATURES = {
     "wf_flf_blend": [_vp, _vp, _vp, _vp, _i, _ll, _vp],
     "wf_latent_denorm": [_vp, _i, _vp, _vp, _vp, _i, _ll, _vp],
     "wf_latent_norm_replace": [_vp, _vp, _i, _vp, _vp, _vp, _u, _i, _ll, _vp],
-    "wf_quantise_u8": [_vp, _i, _vp, _ll, _vp, _vp],
+    "wf_quantise_u8": [_vp, _i, _vp, _ll, _i, _vp, _vp],
+    "wf_cfg_zero": [_vp, _vp, _vp, _f, _ll, _vp, _vp, _vp],
     "wf_conv_tf32": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i,
                      _vp, _i, _ll, _i, _vp],
     "wf_rms_norm_cl": [_vp, _i, _vp, _i, _vp, _ll, _i, _i, _vp],
@@ -359,11 +360,20 @@ def latent_norm_replace(enc, x0, mean_host, inv_std_host, channels):
     return out
 
 
-def quantise_u8(x):
+def quantise_u8(x, mode: int = 0, out=None):
     assert x.is_contiguous()
-    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if out is None else out
     ws = _workspace("quant", load().wf_quantise_workspace_bytes(), x.device)
-    _call("wf_quantise_u8", _p(x), _is_bf16(x), _p(out), x.numel(), _p(ws), _stream())
+    _call("wf_quantise_u8", _p(x), _is_bf16(x), _p(out), x.numel(), mode, _p(ws), _stream())
+    return out
+
+
+def cfg_zero(cond, uncond, scale: float, stats=None):
+    assert cond.dtype == uncond.dtype == torch.float32
+    n = _flat_ok(cond, uncond)
+    out = torch.empty_like(cond)
+    ws = _workspace("dsg", load().wf_dsg_workspace_bytes(), cond.device)
+    _call("wf_cfg_zero", _p(cond), _p(uncond), _p(out), float(scale), n, _p(ws), _p(stats), _stream())
     return out
 
 
