@@ -106,7 +106,7 @@ class OracleEuler:
     step_index = property(lambda self: self._step_index)
 
     def set_timesteps(self, num_inference_steps=None, device=None, sigmas=None):
-        sig = np.array(sigmas).astype(np.float32)
+        sig = (sigmas.detach().cpu().numpy() if isinstance(sigmas, torch.Tensor) else np.asarray(sigmas)).astype(np.float32)
         sig = self.shift * sig / (1 + (self.shift - 1) * sig)
         sig = torch.from_numpy(sig).to(dtype=torch.float32, device=device)
         self.timesteps = sig * self.config.num_train_timesteps

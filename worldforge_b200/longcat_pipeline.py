@@ -123,7 +123,7 @@ class WfFlowMatchEulerScheduler:
     def set_timesteps(self, num_inference_steps=None, device=None, sigmas=None, **kw):
         if sigmas is None:
             raise NotImplementedError("WorldForge's LongCat pipeline always passes its own sigmas (pipeline_longcat_video.py:765-766)")
-        sig = np.array(sigmas.cpu() if isinstance(sigmas, torch.Tensor) else sigmas).astype(np.float32)
+        sig = (sigmas.detach().cpu().numpy() if isinstance(sigmas, torch.Tensor) else np.asarray(sigmas)).astype(np.float32)
         sig = self.shift * sig / (1 + (self.shift - 1) * sig)
         host = torch.from_numpy(sig).to(torch.float32)
         self._sigmas_host = torch.cat([host, torch.zeros(1)])
