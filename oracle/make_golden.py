@@ -22,7 +22,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from oracle import adapters, pipeline, ref_shim, wan_dit, wan_vae  # noqa: E402
+from oracle import adapters, longcat_dit, longcat_sched, pipeline, ref_shim, wan_dit, wan_vae  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden", "wan_golden.pt")
 
@@ -117,6 +117,73 @@ def ref_sched():
                            resample_timesteps=s50.resample_timesteps.clone())
 
 
+LC_DIT = dict(hidden_size=256, depth=2, num_heads=2, caption_channels=64, adaln_tembed_dim=32, frequency_embedding_size=32)
+LC_SCHED_DIT = dict(hidden_size=128, depth=1, num_heads=1, caption_channels=32, adaln_tembed_dim=32, frequency_embedding_size=32)
+LC_KNOBS = dict(guidance_scale=4.0, guided=True, resample_steps=2, guide_steps=6, resample_round=7, omega=4.0, omega_resample=2.0,
+                use_pca_channel_selection=True, max_replace_threshold=3)
+
+
+def longcat_dit_inputs():
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 16, 3, 8, 12, generator=g)
+    ts = torch.tensor([[0.0, 750.0, 750.0]])
+    ctx = torch.randn(1, 1, 10, 64, generator=g)
+    mask = torch.ones(1, 10, dtype=torch.int64); mask[:, 7:] = 0
+    return x, ts, ctx, mask
+
+
+def ref_longcat_dit():
+    """LongCatVideoTransformer3DModel.forward in fp32 (longcat_video/modules/longcat_video_dit.py:280-370), i2v form."""
+    cfg = longcat_dit.LongCatConfig(**LC_DIT)
+    P = longcat_dit.init_params(cfg, 3)
+    mod = ref_shim.load_longcat_dit_module()
+    m = mod.LongCatVideoTransformer3DModel(in_channels=16, out_channels=16, hidden_size=256, depth=2, num_heads=2, caption_channels=64,
+                                           mlp_ratio=4, adaln_tembed_dim=32, frequency_embedding_size=32, enable_xformers=True,
+                                           cp_split_hw=[1, 1]).eval()
+    m.load_state_dict({k: P[k].clone() for k in m.state_dict()})
+    x, ts, ctx, mask = longcat_dit_inputs()
+    with torch.no_grad():
+        return m(x, ts, ctx, encoder_attention_mask=mask, num_cond_latents=1)[0]
+
+
+def longcat_sched_inputs():
+    from worldforge_b200 import synth
+    inp = synth.make_inputs(9, 64, 96, text_len=8, text_dim=32, img_len=3, img_dim=16)
+    g0 = torch.Generator().manual_seed(5)
+    pe = torch.randn(2, 1, 8, 32, generator=g0).to(torch.bfloat16)
+    pm = torch.ones(2, 8, dtype=torch.int64); pm[0, 5:] = 0
+    return inp, pe, pm
+
+
+def run_longcat_sched(sched, distill: bool):
+    cfg, vcfg = longcat_dit.LongCatConfig(**LC_SCHED_DIT), wan_vae.VaeConfig(dim=8)
+    P, PV = longcat_dit.init_params(cfg, 3), wan_vae.init_params(vcfg, 2)
+    inp, pe, pm = longcat_sched_inputs()
+    hist = []
+    longcat_sched.denoise_loop(adapters.OracleLongCatDit(P, cfg, amp=True), adapters.OracleVAE(PV, vcfg), sched, inp.latents.clone(),
+                               pe, pm, 8, use_distill=distill, video_ref=inp.video_ref, mask=inp.mask,
+                               generator=torch.Generator().manual_seed(42), on_step=lambda i, l: hist.append(l.clone()), **LC_KNOBS)
+    return hist
+
+
+def ref_longcat_sched():
+    """8 guided steps through the reference's FlowMatchEulerDiscreteScheduler (standard and distilled schedules)."""
+    sm = ref_shim.load_longcat_scheduler_module()
+    out = {}
+    for distill in (False, True):
+        log = []
+        orig = sm.VideoMotionChannelSelector.select_motion_related_channels
+        def spy(self, *a, _orig=orig, **k):
+            r = _orig(self, *a, **k)
+            log.append((k.get("current_step"), list(r)))
+            return r
+        sm.VideoMotionChannelSelector.select_motion_related_channels = spy
+        hist = run_longcat_sched(sm.FlowMatchEulerDiscreteScheduler(num_train_timesteps=1000, shift=1.0), distill)
+        sm.VideoMotionChannelSelector.select_motion_related_channels = orig
+        out["distill" if distill else "standard"] = dict(latents=torch.stack(hist), flf=log)
+    return out
+
+
 def main():
     assert ref_shim.available(), "/root/reference is not mounted"
     torch.manual_seed(0)
@@ -127,6 +194,7 @@ def main():
         "vae_mu": mu.clone(), "vae_dec": dec.clone(),
         "sched_latents": torch.stack([h.float() for h in hist]), "sched_dtype": str(hist[-1].dtype), "sched_flf": flf_log,
         "sched_tables_50": tables,
+        "longcat_dit_fp32": ref_longcat_dit().clone(), "longcat_sched": ref_longcat_sched(),
         "meta": {"reference_commit": "3314da5", "torch": torch.__version__, "generator": "oracle/make_golden.py"},
     }
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
