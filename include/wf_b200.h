@@ -58,6 +58,29 @@ int wf_attention_bf16(const void* q, int ldq, const void* k, int ldk, const void
                       const void* add_in, int ld_add, int Lq, int Lk, int heads, float softmax_scale,
                       void* stream);
 
+/* ---- LongCat block-sparse attention (the 720p refine pass) ---------------------------------------- */
+
+/* mean_pooling_compression (longcat_video/block_sparse_attention/bsa_interface.py:176-186) of a [T*H*W, heads*128]
+ * bf16 matrix in (t,h,w) token order over ct x ch x cw chunks, WITHOUT the chunk-major re-ordering of
+ * rearrange_THW_to_3d_block (:598-603): out [heads][chunks][128] bf16, chunks in (Nt,Nh,Nw) order. */
+int wf_bsa_mean_pool(const void* x, int ldx, void* out, int T, int H, int W, int ct, int ch, int cw, int heads,
+                     void* stream);
+
+/* get_select_indices_topk (bsa_interface.py:214-232): scores = bf16(q_cmp k_cmp^T) per head, the n_sel best key
+ * chunks of every query chunk.  q_cmp [heads][Nq][128], k_cmp [heads][Nk][128] bf16; idx [heads][Nq][n_sel] int32 in
+ * ascending chunk order (the order topk_sort gives, :530-534); ties at the threshold take the lower chunk index. */
+int wf_bsa_select_topk(const void* q_cmp, const void* k_cmp, int32_t* idx, int Nq, int Nk, int heads, int n_sel,
+                       void* stream);
+
+/* flash_attn_bsa_3d minus the gating (bsa_interface.py:612-659 -> _attn_fwd_bsa_varlen_align,
+ * flash_attn_bsa_varlen_mask.py:174-285): every query chunk attends to the key chunks block_idx[h][chunk][0 ..
+ * len) only (len = block_lens[h][chunk], or max_sel when block_lens is NULL).  q [Tq*H*W, heads*128], k/v
+ * [Tk*H*W, heads*128], out like q: bf16 row-major in (t,h,w) token order - the kernel gathers chunks with 4-D TMA
+ * boxes, no re-ordered copy exists.  ct*ch*cw must be 64 or 128 (the checkpoint's 4x4x4, the code default 4x4x8). */
+int wf_attention_bsa_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
+                          const int32_t* block_idx, const int32_t* block_lens, int max_sel, int Tq, int Tk, int H,
+                          int W, int ct, int ch, int cw, int heads, float softmax_scale, void* stream);
+
 /* ---- DiT HBM-bound kernels ------------------------------------------------------------------------ */
 
 /* WanLayerNorm (+ modulation or affine), model.py:97-102 with :303/:311 (scale,shift = e[1],e[0] /

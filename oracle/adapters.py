@@ -61,10 +61,10 @@ class OracleVAE:
 class OracleLongCatDit:
     """Quacks like ``pipe.dit`` (pipeline_longcat_video.py:867-873) on top of oracle.longcat_dit."""
 
-    def __init__(self, params, cfg, amp: bool = True):
+    def __init__(self, params, cfg, amp: bool = True, bsa=None):
         from . import longcat_dit
         self._ld = longcat_dit
-        self.P, self.cfg, self.amp = params, cfg, amp
+        self.P, self.cfg, self.amp, self.bsa = params, cfg, amp, bsa
         self.dtype = torch.bfloat16
         self.config = SimpleNamespace(in_channels=cfg.in_channels)
         self.cp_split_hw = [1, 1]
@@ -78,5 +78,5 @@ class OracleLongCatDit:
                 ctx = ctx[encoder_attention_mask[s].reshape(-1) != 0]
             self.calls += 1
             outs.append(self._ld.dit_forward(self.P, self.cfg, hidden_states[s].cpu(), timestep[s].cpu(), ctx.cpu(),
-                                             num_cond_latents=num_cond_latents, amp=self.amp))
+                                             num_cond_latents=num_cond_latents, amp=self.amp, bsa=self.bsa))
         return torch.stack(outs).to(hidden_states.device)

@@ -163,8 +163,18 @@ def attention(q, k, v, amp):
     return _att(q, k, v, amp=amp)
 
 
-def block_forward(P, cfg: LongCatConfig, i, x, y, t, grid, num_cond, amp):
-    """x [N, C] (one sample), y [M, C] valid text tokens, t [T, A] fp32."""
+def bsa_attention(q, k, v, grid_q, grid_k, bsa):
+    """Attention._process_attn's block-sparse branch (attention.py:56-67): q [Nq,H,D], k/v [Nk,H,D] in (t,h,w) order."""
+    from . import longcat_bsa
+    t = lambda z: z.permute(1, 0, 2).unsqueeze(0)
+    o = longcat_bsa.bsa_3d(t(q), t(k), t(v), grid_q, grid_k, sparsity=bsa.get("sparsity", 0.875), cdf_threshold=bsa.get("cdf_threshold"),
+                           chunk_q=tuple(bsa.get("chunk_3d_shape_q", (4, 4, 8))), chunk_k=tuple(bsa.get("chunk_3d_shape_k", (4, 4, 8))))
+    return o[0].permute(1, 0, 2)
+
+
+def block_forward(P, cfg: LongCatConfig, i, x, y, t, grid, num_cond, amp, bsa=None):
+    """x [N, C] (one sample), y [M, C] valid text tokens, t [T, A] fp32.  ``bsa``: the checkpoint's bsa_params dict when
+    the block-sparse self-attention of the refine pass is enabled (Attention.enable_bsa, attention.py:56), else None."""
     b = f"blocks.{i}."
     C, Hn, D = cfg.hidden_size, cfg.num_heads, cfg.head_dim
     T = grid[0]
@@ -186,7 +196,14 @@ def block_forward(P, cfg: LongCatConfig, i, x, y, t, grid, num_cond, amp):
     fr = rope_freqs(D, grid)
     q, k = rope_apply(q, fr), rope_apply(k, fr)
     nc = num_cond * per
-    if nc > 0:
+    if bsa is not None and T > 1:                                   # "bsa will not be used in image training / sampling"
+        gH, gW = grid[1], grid[2]
+        if nc > 0:
+            a = torch.cat([bsa_attention(q[:nc], k[:nc], v[:nc], (num_cond, gH, gW), (num_cond, gH, gW), bsa),
+                           bsa_attention(q[nc:], k, v, (T - num_cond, gH, gW), (T, gH, gW), bsa)], dim=0)
+        else:
+            a = bsa_attention(q, k, v, grid, grid, bsa)
+    elif nc > 0:
         a = torch.cat([attention(q[:nc], k[:nc], v[:nc], amp), attention(q[nc:], k, v, amp)], dim=0)
     else:
         a = attention(q, k, v, amp)
@@ -211,7 +228,7 @@ def block_forward(P, cfg: LongCatConfig, i, x, y, t, grid, num_cond, amp):
     return x
 
 
-def dit_forward(P, cfg: LongCatConfig, x, timestep, context, num_cond_latents: int = 1, amp: bool = True):
+def dit_forward(P, cfg: LongCatConfig, x, timestep, context, num_cond_latents: int = 1, amp: bool = True, bsa=None):
     """LongCatVideoTransformer3DModel.forward for one sample.
 
     x [C_in, T, H, W]; timestep [T] (per latent frame, the condition frames at 0, pipeline_longcat_video.py:864-865);
@@ -230,7 +247,7 @@ def dit_forward(P, cfg: LongCatConfig, x, timestep, context, num_cond_latents: i
     y = lin(F.gelu(lin(context.to(dt), P["y_embedder.y_proj.0.weight"], P["y_embedder.y_proj.0.bias"], amp), approximate="tanh"),
             P["y_embedder.y_proj.2.weight"], P["y_embedder.y_proj.2.bias"], amp)
     for i in range(cfg.depth):
-        tok = block_forward(P, cfg, i, tok, y, t, grid, num_cond_latents, amp)
+        tok = block_forward(P, cfg, i, tok, y, t, grid, num_cond_latents, amp, bsa)
     mod = lin_fp32_island(F.silu(t), P["final_layer.adaLN_modulation.1.weight"], P["final_layer.adaLN_modulation.1.bias"], amp)
     shift, scale = [m.unsqueeze(1) for m in mod.chunk(2, dim=-1)]
     per = N // T

@@ -166,6 +166,8 @@ class OracleEuler:
         self.derivative_history.append(model_output)
         prev = (sample + dt * model_output).to(model_output.dtype)
         self._step_index += 1
+        if not return_dict:
+            return (prev,)
         return StepOutput(prev, pred_x0)
 
     def add_noise(self, original_samples, noise, timesteps, use_resample_sigma=False):
@@ -263,6 +265,87 @@ def denoise_loop(dit, vae, scheduler, latents, prompt_embeds, prompt_attention_m
             latents[:, :, 1:] = b.prev_sample
         elif out is not None:
             latents[:, :, 1:] = out.prev_sample
+        if on_step is not None:
+            on_step(i, latents)
+    return latents
+
+
+# ------------------------------------------------------------------------------------------------ refine (720p) pass
+def refine_schedule(scheduler, num_inference_steps: int = 50, t_thresh: float = 0.5, device=None):
+    """generate_refine step 4 (pipeline_longcat_video.py:1382-1391): the standard schedule cut at ``t_thresh``."""
+    scheduler.set_timesteps(num_inference_steps, sigmas=timesteps_sigmas(num_inference_steps), device=device)
+    timesteps = scheduler.timesteps
+    if t_thresh:
+        tt = torch.tensor(t_thresh * 1000, dtype=timesteps.dtype, device=timesteps.device)
+        timesteps = torch.cat([tt.unsqueeze(0), timesteps[timesteps < tt]])
+        scheduler.timesteps = timesteps
+        scheduler.sigmas = torch.cat([timesteps / 1000, torch.zeros(1, device=timesteps.device)])
+    return timesteps
+
+
+def refine_padding(num_frames: int, num_cond_frames: int, temporal: int = 4, granularity: int = 4):
+    """The BSA padding arithmetic of generate_refine (:1406-1421) -> (num_cond_latents, cond_frames_added,
+    num_cond_frames_total, noise_frames_added)."""
+    import math
+    num_noise_frames = num_frames - num_cond_frames
+    ncl = added = 0
+    if num_cond_frames > 0:
+        ncl = 1 + math.ceil((num_cond_frames - 1) / temporal)
+        ncl = math.ceil(ncl / granularity) * granularity
+        added = 1 + (ncl - 1) * temporal - num_cond_frames
+        num_cond_frames = num_cond_frames + added
+    nnl = math.ceil(num_noise_frames / temporal)
+    nnl = math.ceil(nnl / granularity) * granularity
+    return ncl, added, num_cond_frames, nnl * temporal - num_noise_frames
+
+
+def _norm(vae, lat):
+    z = vae.config.z_dim
+    mean = torch.tensor(vae.config.latents_mean).view(1, z, 1, 1, 1).to(lat.device, lat.dtype)
+    inv_std = 1.0 / torch.tensor(vae.config.latents_std).view(1, z, 1, 1, 1).to(lat.device, lat.dtype)
+    return (lat - mean) * inv_std
+
+
+def refine_prepare(stage1_u8: torch.Tensor, image, vae, height: int, width: int, generator, t_thresh: float = 0.5,
+                   num_cond_frames: int = 0, spatial_refine_only: bool = False, dtype=torch.bfloat16):
+    """generate_refine step 5 (:1393-1455).  stage1_u8 uint8 [F, H0, W0, 3]; image: [1,3,height,width] in [-1,1] (already
+    through video_processor.preprocess) or None.  -> (latents fp32 [1,16,T,h,w], num_cond_latents, cond_frames_added, new_frame_size)."""
+    import torch.nn.functional as F
+    nf = stage1_u8.shape[0]
+    new_frames = nf if spatial_refine_only else 2 * nf
+    s1 = stage1_u8.permute(0, 3, 1, 2).to(dtype=dtype)
+    down = F.interpolate(s1, size=(height, width), mode="bilinear", align_corners=True)
+    down = down.permute(1, 0, 2, 3).unsqueeze(0) / 255.0
+    up = F.interpolate(down, size=(new_frames, height, width), mode="trilinear", align_corners=True)
+    up = up * 2 - 1
+    ncl, added, ncf, back = refine_padding(up.shape[2], num_cond_frames)
+    up = torch.cat([up[:, :, 0:1].repeat(1, 1, added, 1, 1), up, up[:, :, -1:].repeat(1, 1, back, 1, 1)], dim=2)
+    lat = _norm(vae, vae.encode(up).latent_dist.mode())
+    noise = torch.randn(lat.shape, generator=generator, dtype=lat.dtype).to(lat.device)
+    lat = (1 - t_thresh) * lat + t_thresh * noise
+    latents = lat.to(torch.float32)                                           # prepare_latents(latents=latent_up, dtype=fp32)
+    if image is not None:
+        enc_in = image.to(dtype).unsqueeze(2)
+        if added > 0:
+            enc_in = torch.cat([enc_in[:, :, 0:1].repeat(1, 1, added, 1, 1), enc_in], dim=2)
+        assert enc_in.shape[2] == ncf
+        cond = _norm(vae, vae.encode(enc_in).latent_dist.mode().to(torch.float32))
+        latents[:, :, : 1 + (ncf - 1) // 4] = cond
+    return latents, ncl, added, new_frames
+
+
+def refine_loop(dit, scheduler, latents, prompt_embeds, prompt_attention_mask, num_cond_latents: int, timesteps,
+                dit_dtype=torch.bfloat16, on_step=None):
+    """generate_refine's loop (:1467-1498): no CFG, no guidance; Euler steps on the noise latents only."""
+    for i, t in enumerate(timesteps):
+        x = latents.to(dit_dtype)
+        ts = t.expand(x.shape[0]).to(dit_dtype).unsqueeze(-1).repeat(1, x.shape[2])
+        ts[:, :num_cond_latents] = 0
+        pred = dit(hidden_states=x, timestep=ts, encoder_hidden_states=prompt_embeds, encoder_attention_mask=prompt_attention_mask,
+                   num_cond_latents=num_cond_latents)
+        pred = -pred
+        latents[:, :, num_cond_latents:] = scheduler.step(pred[:, :, num_cond_latents:], t, latents[:, :, num_cond_latents:],
+                                                          return_dict=False)[0]
         if on_step is not None:
             on_step(i, latents)
     return latents

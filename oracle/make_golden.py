@@ -17,12 +17,15 @@ from __future__ import annotations
 import os
 import sys
 
+os.environ.setdefault("TRITON_INTERPRET", "1")      # the reference's Triton BSA kernels run under Triton's CPU interpreter
+os.environ.setdefault("TORCHDYNAMO_DISABLE", "1")   # ... and its @torch.compile gating helpers eagerly
+
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from oracle import adapters, longcat_dit, longcat_sched, pipeline, ref_shim, wan_dit, wan_vae  # noqa: E402
+from oracle import adapters, longcat_bsa, longcat_dit, longcat_sched, pipeline, ref_shim, wan_dit, wan_vae  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden", "wan_golden.pt")
 
@@ -184,6 +187,78 @@ def ref_longcat_sched():
     return out
 
 
+BSA_CASES = {      # name: (grid_q, grid_k, heads, dtype, kwargs of flash_attn_bsa_3d)
+    "c64_topk_f32": ((4, 8, 8), (4, 8, 8), 1, torch.float32, dict(sparsity=0.5, chunk_3d_shape_q=[4, 4, 4], chunk_3d_shape_k=[4, 4, 4])),
+    "c64_cross_f16": ((4, 4, 8), (8, 4, 8), 2, torch.float16, dict(sparsity=0.5, chunk_3d_shape_q=[4, 4, 4], chunk_3d_shape_k=[4, 4, 4])),
+    "c128_topk_f16": ((8, 8, 8), (8, 8, 8), 2, torch.float16, dict(sparsity=0.5, chunk_3d_shape_q=[4, 4, 8], chunk_3d_shape_k=[4, 4, 8])),
+    "c64_cdf_topk_f16": ((4, 8, 8), (4, 8, 8), 2, torch.float16, dict(sparsity=0.75, cdf_threshold=0.6, chunk_3d_shape_q=[4, 4, 4],
+                                                                      chunk_3d_shape_k=[4, 4, 4])),
+}
+
+
+def bsa_inputs(name):
+    gq, gk, heads, dt, kw = BSA_CASES[name]
+    g = torch.Generator().manual_seed(len(name))
+    mk = lambda grid: torch.randn(1, heads, grid[0] * grid[1] * grid[2], 128, generator=g).to(dt)
+    return mk(gq), mk(gk), mk(gk), gq, gk, kw
+
+
+def ref_bsa():
+    """flash_attn_bsa_3d of the reference (bsa_interface.py:612-659), Triton kernels through Triton's interpreter."""
+    bsa = ref_shim.load_longcat_bsa_module()
+    out = {}
+    for name in BSA_CASES:
+        q, k, v, gq, gk, kw = bsa_inputs(name)
+        out[name] = bsa.flash_attn_bsa_3d(q, k, v, gq, gk, **kw)[0].clone()
+    return out
+
+
+LC_BSA = dict(sparsity=0.5, cdf_threshold=None, chunk_3d_shape_q=[4, 4, 4], chunk_3d_shape_k=[4, 4, 4])
+
+
+def longcat_bsa_dit_inputs():
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(1, 16, 8, 16, 16, generator=g)
+    ts = torch.tensor([[0.0] * 4 + [600.0] * 4])
+    ctx = torch.randn(1, 1, 10, 64, generator=g)
+    mask = torch.ones(1, 10, dtype=torch.int64); mask[:, 8:] = 0
+    return x, ts, ctx, mask
+
+
+def ref_longcat_dit_bsa():
+    """The reference DiT with enable_bsa() (longcat_video_dit.py:272-274), fp32, 4 condition + 4 noise latent frames."""
+    cfg = longcat_dit.LongCatConfig(**LC_DIT)
+    P = longcat_dit.init_params(cfg, 3)
+    mod = ref_shim.load_longcat_dit_module(bsa=True)
+    m = mod.LongCatVideoTransformer3DModel(in_channels=16, out_channels=16, hidden_size=256, depth=2, num_heads=2, caption_channels=64,
+                                           mlp_ratio=4, adaln_tembed_dim=32, frequency_embedding_size=32, enable_xformers=True,
+                                           bsa_params=dict(LC_BSA), cp_split_hw=[1, 1]).eval()
+    m.load_state_dict({k: P[k].clone() for k in m.state_dict()})
+    m.enable_bsa()
+    x, ts, ctx, mask = longcat_bsa_dit_inputs()
+    with torch.no_grad():
+        return m(x, ts, ctx, encoder_attention_mask=mask, num_cond_latents=4)[0]
+
+
+def run_refine(sched):
+    """The refine loop (6 of 10 steps, t_thresh 0.6) on the oracle DiT with BSA, driven through ``sched``."""
+    cfg = longcat_dit.LongCatConfig(**LC_SCHED_DIT)
+    P = longcat_dit.init_params(cfg, 3)
+    g = torch.Generator().manual_seed(21)
+    lat = torch.randn(1, 16, 8, 16, 16, generator=g)
+    pe = torch.randn(1, 1, 8, 32, generator=g).to(torch.bfloat16)
+    pm = torch.ones(1, 8, dtype=torch.int64); pm[0, 6:] = 0
+    ts = longcat_sched.refine_schedule(sched, 10, 0.6)
+    dit = adapters.OracleLongCatDit(P, cfg, amp=True, bsa=dict(LC_BSA))
+    return longcat_sched.refine_loop(dit, sched, lat, pe, pm, 4, ts), ts.clone(), sched.sigmas.clone()
+
+
+def ref_refine():
+    sm = ref_shim.load_longcat_scheduler_module()
+    lat, ts, sig = run_refine(sm.FlowMatchEulerDiscreteScheduler(num_train_timesteps=1000, shift=1.0))
+    return dict(latents=lat.clone(), timesteps=ts, sigmas=sig)
+
+
 def main():
     assert ref_shim.available(), "/root/reference is not mounted"
     torch.manual_seed(0)
@@ -195,6 +270,7 @@ def main():
         "sched_latents": torch.stack([h.float() for h in hist]), "sched_dtype": str(hist[-1].dtype), "sched_flf": flf_log,
         "sched_tables_50": tables,
         "longcat_dit_fp32": ref_longcat_dit().clone(), "longcat_sched": ref_longcat_sched(),
+        "bsa": ref_bsa(), "longcat_dit_bsa_fp32": ref_longcat_dit_bsa().clone(), "longcat_refine": ref_refine(),
         "meta": {"reference_commit": "3314da5", "torch": torch.__version__, "generator": "oracle/make_golden.py"},
     }
     os.makedirs(os.path.dirname(OUT), exist_ok=True)

@@ -232,10 +232,37 @@ def _fake_xformers():
     sys.modules.update({"xformers": xf, "xformers.ops": ops, "xformers.ops.fmha": fmha, "xformers.ops.fmha.attn_bias": ab})
 
 
-def load_longcat_dit_module():
-    """longcat_video.modules.longcat_video_dit, unmodified, importable on the CPU: diffusers stand-in, a stub for the
-    Triton block-sparse package (only reached by the 720p refine pass), SDPA-backed xformers, context-parallel size 1."""
+def load_longcat_bsa_module():
+    """longcat_video.block_sparse_attention.bsa_interface, unmodified.  Its Triton kernels run on the CPU through Triton's
+    interpreter (TRITON_INTERPRET=1, which must be set before triton is first imported) and its @torch.compile helpers
+    eagerly (TORCHDYNAMO_DISABLE=1).  The interpreter has no bf16 (numpy), so fixtures from it are fp32 / fp16."""
     assert os.path.isdir(REF_LONGCAT)
+    assert "triton" not in sys.modules or os.environ.get("TRITON_INTERPRET") == "1", "set TRITON_INTERPRET=1 before importing triton"
+    os.environ["TRITON_INTERPRET"] = "1"
+    os.environ["TORCHDYNAMO_DISABLE"] = "1"
+    if REF_LONGCAT not in sys.path:
+        sys.path.insert(0, REF_LONGCAT)
+    for name in ("longcat_video", "longcat_video.context_parallel", "longcat_video.block_sparse_attention"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = [os.path.join(REF_LONGCAT, *name.split("."))]
+            sys.modules[name] = m
+    name = "longcat_video.block_sparse_attention.bsa_interface"
+    if name in sys.modules and getattr(sys.modules[name], "flash_attn_bsa_3d", None) is None:
+        del sys.modules[name]                                   # the stub of load_longcat_dit_module(bsa=False)
+    return importlib.import_module(name)
+
+
+def load_longcat_dit_module(bsa: bool = False):
+    """longcat_video.modules.longcat_video_dit, unmodified, importable on the CPU: diffusers stand-in, a stub for the
+    Triton block-sparse package (only reached by the 720p refine pass; ``bsa=True`` loads the real one under Triton's
+    interpreter), SDPA-backed xformers, context-parallel size 1."""
+    assert os.path.isdir(REF_LONGCAT)
+    if bsa:
+        real = load_longcat_bsa_module()
+        att = sys.modules.get("longcat_video.modules.attention")
+        if att is not None:                                     # imported earlier against the stub: rebind the one name it took
+            att.flash_attn_bsa_3d = real.flash_attn_bsa_3d
     install_diffusers_shim()
     _fake_xformers()
     if REF_LONGCAT not in sys.path:

@@ -25,6 +25,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "attn_math.cuh"
 #include "host_util.h"
 
 namespace wf {
@@ -48,12 +49,6 @@ struct AttnArgs {
   const bf16* add_in; int ld_add;
   float scale_log2;     // softmax scale * log2(e)
 };
-
-__device__ __forceinline__ float ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -299,21 +294,6 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 // =====================================================================================================================
 constexpr uint32_t AT2_TMEM_O = 256;
 
-__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
-  uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
-}
-__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
-}
-__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
-  uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
-}
-__device__ __forceinline__ float fmax3(float a, float b, float c) {
-  float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d;
-}
 // 2^x for a pair, x <= ~8, on the FMA / ALU pipes: x = n + f, n = round(x), f in [-0.5, 0.5], 2^f by a cubic
 __device__ __forceinline__ void exp2_poly2(uint64_t x2, float& e0, float& e1) {
   float x0, x1; unpack2(x2, x0, x1);
@@ -328,17 +308,6 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x2, float& e0, float& e1) {
   float p0, p1, t0, t1; unpack2(p2, p0, p1); unpack2(t2, t0, t1);
   e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
   e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
-}
-
-// D[tmem] (+)= A[tmem] * B[smem]: the A operand (here the bf16 probabilities, two per 32-bit column) is read from
-// tensor memory instead of shared memory
-__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
 }
 
 // PTMEM: P_t(j) is stored back into the first 32 columns of the S buffer it was computed from (64 bf16 = 32 columns)

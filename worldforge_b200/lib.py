@@ -31,6 +31,9 @@ _vp, _i, _f, _ll, _u = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_uint
 _SIGNATURES = {
     "wf_gemm_bf16": [_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
     "wf_attention_bf16": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _f, _vp],
+    "wf_bsa_mean_pool": [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "wf_bsa_select_topk": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "wf_attention_bsa_bf16": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp],
     "wf_layer_norm": [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _vp],
     "wf_rms_norm_rope": [_vp, _i, _vp, _vp, _i, _i, _f, _vp],
     "wf_patchify": [_vp, _vp, _i, _i, _i, _i, _vp],
@@ -157,6 +160,41 @@ def attention_bf16(q, k, v, out, heads: int, add_in=None, softmax_scale: Optiona
     if ev is not None:
         ev[1].record()
         timed_attention.append(ev)
+    return out
+
+
+def bsa_mean_pool(x, grid, chunk, heads: int):
+    """x [T*H*W, >=heads*128] bf16 in (t,h,w) order -> [heads, chunks, 128] bf16 chunk means."""
+    (T, H, W), (ct, ch, cw) = grid, chunk
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1 and x.shape[0] == T * H * W
+    out = torch.empty(heads, (T // ct) * (H // ch) * (W // cw), 128, dtype=torch.bfloat16, device=x.device)
+    _call("wf_bsa_mean_pool", _p(x), x.stride(0), _p(out), T, H, W, ct, ch, cw, heads, _stream())
+    return out
+
+
+def bsa_select_topk(q_cmp, k_cmp, n_sel: int):
+    """[heads, Nq, 128], [heads, Nk, 128] bf16 -> int32 [heads, Nq, n_sel], ascending."""
+    assert q_cmp.is_contiguous() and k_cmp.is_contiguous() and q_cmp.dtype == k_cmp.dtype == torch.bfloat16
+    heads, Nq, _ = q_cmp.shape
+    idx = torch.empty(heads, Nq, n_sel, dtype=torch.int32, device=q_cmp.device)
+    _call("wf_bsa_select_topk", _p(q_cmp), _p(k_cmp), _p(idx), Nq, k_cmp.shape[1], heads, n_sel, _stream())
+    return idx
+
+
+def attention_bsa_bf16(q, k, v, out, heads: int, block_idx, block_lens, grid_q, grid_k, chunk,
+                       softmax_scale: Optional[float] = None):
+    """Block-sparse attention in (t,h,w) token order; block_idx int32 [heads, q_chunks, max_sel], block_lens int32 or None."""
+    for t in (q, k, v, out):
+        assert t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1
+    (Tq, H, W), (Tk, Hk, Wk), (ct, ch, cw) = grid_q, grid_k, chunk
+    assert (H, W) == (Hk, Wk) and q.shape[0] == Tq * H * W and k.shape[0] == v.shape[0] == Tk * H * W
+    assert block_idx.dtype == torch.int32 and block_idx.is_contiguous() and block_idx.shape[0] == heads
+    assert block_idx.shape[1] == (Tq // ct) * (H // ch) * (W // cw)
+    if block_lens is not None:
+        assert block_lens.dtype == torch.int32 and block_lens.is_contiguous() and block_lens.shape == block_idx.shape[:2]
+    scale = softmax_scale if softmax_scale is not None else 128 ** -0.5
+    _call("wf_attention_bsa_bf16", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
+          _p(block_idx), _p(block_lens), block_idx.shape[2], Tq, Tk, H, W, ct, ch, cw, heads, scale, _stream())
     return out
 
 
