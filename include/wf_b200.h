@@ -164,6 +164,11 @@ int wf_dsg(const void* g, const void* w, void* out, int is_bf16, float omega, lo
  * decoded/ref/out [channels, plane], mask [plane] broadcast over channels. */
 int wf_flf_blend(const float* decoded, const float* ref, const float* mask, float* out, int channels,
                  long long plane, void* stream);
+/* LongCat generate_refine step 5 (longcat_video/pipeline_longcat_video.py:1393-1419): stage-1 video uint8 [F,H0,W0,3]
+ * -> bilinear (align_corners) to [H,W] -> /255 -> trilinear to F2 frames -> *2-1, bf16 intermediates as in the reference,
+ * first / last frame repeated pad_front / pad_back times.  out: planar fp32 [3][pad_front+F2+pad_back][H][W]. */
+int wf_refine_upsample(const unsigned char* video, int F, int H0, int W0, float* out, int F2, int H, int W,
+                       int pad_front, int pad_back, void* stream);
 /* scheduler :1281-1282: out fp32 = x0/inv_std + mean evaluated in x0's dtype ([channels, per_channel]) */
 int wf_latent_denorm(const void* x0, int is_bf16, float* out, const float* mean, const float* inv_std, int channels,
                      long long per_channel, void* stream);

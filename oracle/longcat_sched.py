@@ -320,7 +320,9 @@ def refine_prepare(stage1_u8: torch.Tensor, image, vae, height: int, width: int,
     up = up * 2 - 1
     ncl, added, ncf, back = refine_padding(up.shape[2], num_cond_frames)
     up = torch.cat([up[:, :, 0:1].repeat(1, 1, added, 1, 1), up, up[:, :, -1:].repeat(1, 1, back, 1, 1)], dim=2)
-    lat = _norm(vae, vae.encode(up).latent_dist.mode())
+    # the reference hands the bf16 clip to its bf16 VAE (run_longcat_worldforge_single.py:205); with a VAE of another dtype
+    # the only meaningful reading is a cast to the VAE's dtype
+    lat = _norm(vae, vae.encode(up.to(vae.dtype)).latent_dist.mode())
     noise = torch.randn(lat.shape, generator=generator, dtype=lat.dtype).to(lat.device)
     lat = (1 - t_thresh) * lat + t_thresh * noise
     latents = lat.to(torch.float32)                                           # prepare_latents(latents=latent_up, dtype=fp32)
@@ -329,7 +331,7 @@ def refine_prepare(stage1_u8: torch.Tensor, image, vae, height: int, width: int,
         if added > 0:
             enc_in = torch.cat([enc_in[:, :, 0:1].repeat(1, 1, added, 1, 1), enc_in], dim=2)
         assert enc_in.shape[2] == ncf
-        cond = _norm(vae, vae.encode(enc_in).latent_dist.mode().to(torch.float32))
+        cond = _norm(vae, vae.encode(enc_in.to(vae.dtype)).latent_dist.mode().to(torch.float32))
         latents[:, :, : 1 + (ncf - 1) // 4] = cond
     return latents, ncl, added, new_frames
 

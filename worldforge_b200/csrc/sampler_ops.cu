@@ -216,6 +216,50 @@ __global__ void flf_blend_kernel(const float4* __restrict__ dec, const float4* _
   }
 }
 
+// ---------------------------------------------------------------------- refine-pass input upsampling
+// generate_refine step 5 (longcat_video/pipeline_longcat_video.py:1393-1419) in one pass over the OUTPUT:
+//   uint8 [F,H0,W0,3] -> bf16 -> bilinear (align_corners) to [H,W] -> /255 -> trilinear (align_corners) to F2 frames (the spatial
+//   part of that second resize is the identity) -> *2-1, every intermediate rounded to bf16 as the reference's bf16 tensors
+//   are, then pad_front copies of the first frame and pad_back copies of the last.  out: planar fp32 [3][F_out][H][W].
+// torch's CUDA upsample kernels (UpSampleBilinear2d.cu / UpSampleTrilinear3d.cu) compute in fp32: src = dst*(in-1)/(out-1),
+// lambda1 = src - floor(src), val = h0*(w0*a + w1*b) + h1*(w0*c + w1*d).
+__device__ __forceinline__ float bilerp_u8(const unsigned char* __restrict__ fr, int H0, int W0, int c, float hr, float wr) {
+  const int h1 = static_cast<int>(hr), w1 = static_cast<int>(wr);
+  const int hp = h1 < H0 - 1 ? 1 : 0, wp = w1 < W0 - 1 ? 1 : 0;
+  const float h1l = hr - h1, h0l = 1.f - h1l, w1l = wr - w1, w0l = 1.f - w1l;
+  auto px = [&](int y, int x) { return static_cast<float>(fr[(static_cast<size_t>(y) * W0 + x) * 3 + c]); };
+  const float v = h0l * (w0l * px(h1, w1) + w1l * px(h1, w1 + wp)) + h1l * (w0l * px(h1 + hp, w1) + w1l * px(h1 + hp, w1 + wp));
+  // bf16 result of the resize, then "/ 255.0" on a bf16 tensor: fp32 multiply by the reciprocal, rounded to bf16
+  return bf16_round(__fmul_rn(bf16_round(v), 1.0f / 255.0f));
+}
+
+__global__ void refine_upsample_kernel(const unsigned char* __restrict__ video, int F, int H0, int W0, float* __restrict__ out, int F2,
+                                       int H, int W, int pad_front, int pad_back) {
+  const int F_out = pad_front + F2 + pad_back;
+  const size_t total = static_cast<size_t>(3) * F_out * H * W;
+  const float rh = H > 1 ? static_cast<float>(H0 - 1) / (H - 1) : 0.f;
+  const float rw = W > 1 ? static_cast<float>(W0 - 1) / (W - 1) : 0.f;
+  const float rt = F2 > 1 ? static_cast<float>(F - 1) / (F2 - 1) : 0.f;
+  const size_t frame = static_cast<size_t>(H0) * W0 * 3;
+  WF_GRID_STRIDE(i, total) {
+    const int x = static_cast<int>(i % W), y = static_cast<int>((i / W) % H);
+    const int fo = static_cast<int>((i / (static_cast<size_t>(W) * H)) % F_out), c = static_cast<int>(i / (static_cast<size_t>(W) * H * F_out));
+    const int f2 = min(max(fo - pad_front, 0), F2 - 1);
+    const float tr = rt * f2;
+    const int t1 = static_cast<int>(tr);
+    const int tp = t1 < F - 1 ? 1 : 0;
+    const float t1l = tr - t1, t0l = 1.f - t1l;
+    const float hr = rh * y, wr = rw * x;
+    const float a = bilerp_u8(video + t1 * frame, H0, W0, c, hr, wr);
+    float v = a;
+    if (F2 != F) {
+      const float b = bilerp_u8(video + (t1 + tp) * frame, H0, W0, c, hr, wr);
+      v = bf16_round(t0l * a + t1l * b);
+    }
+    out[i] = bf16_round(__fsub_rn(bf16_round(__fmul_rn(v, 2.0f)), 1.0f));
+  }
+}
+
 // ---------------------------------------------------------------------- latent (de)normalisation
 struct LatentStats { float mean[16]; float inv_std[16]; };   // values already rounded to the latent dtype by the host
 
@@ -451,6 +495,16 @@ extern "C" int wf_cfg_zero(const float* cond, const float* uncond, float* out, f
   WF_LAUNCH_OK();
   cfgz_apply_kernel<<<grid_for(n / 4, DSG_THREADS), DSG_THREADS, 0, WF_STREAM>>>(reinterpret_cast<const float4*>(cond), reinterpret_cast<const float4*>(uncond),
                                                                                reinterpret_cast<float4*>(out), static_cast<size_t>(n / 4), partial, blocks, scale, stats);
+  WF_LAUNCH_OK();
+  return WF_OK;
+}
+
+extern "C" int wf_refine_upsample(const unsigned char* video, int F, int H0, int W0, float* out, int F2, int H, int W, int pad_front,
+                                  int pad_back, void* stream) {
+  WF_REQUIRE(video && out, "wf_refine_upsample: null pointer");
+  WF_REQUIRE(F > 0 && H0 > 0 && W0 > 0 && F2 > 0 && H > 0 && W > 0 && pad_front >= 0 && pad_back >= 0, "wf_refine_upsample: bad sizes");
+  const long long total = 3ll * (pad_front + F2 + pad_back) * H * W;
+  refine_upsample_kernel<<<grid_for(total), 256, 0, WF_STREAM>>>(video, F, H0, W0, out, F2, H, W, pad_front, pad_back);
   WF_LAUNCH_OK();
   return WF_OK;
 }

@@ -55,6 +55,7 @@ _SIGNATURES = {
     "wf_latent_denorm": [_vp, _i, _vp, _vp, _vp, _i, _ll, _vp],
     "wf_latent_norm_replace": [_vp, _vp, _i, _vp, _vp, _vp, _u, _i, _ll, _vp],
     "wf_quantise_u8": [_vp, _i, _vp, _ll, _i, _vp, _vp],
+    "wf_refine_upsample": [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp],
     "wf_cfg_zero": [_vp, _vp, _vp, _f, _ll, _vp, _vp, _vp],
     "wf_conv_tf32": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i,
                      _vp, _i, _ll, _i, _vp],
@@ -412,6 +413,15 @@ def cfg_zero(cond, uncond, scale: float, stats=None):
     out = torch.empty_like(cond)
     ws = _workspace("dsg", load().wf_dsg_workspace_bytes(), cond.device)
     _call("wf_cfg_zero", _p(cond), _p(uncond), _p(out), float(scale), n, _p(ws), _p(stats), _stream())
+    return out
+
+
+def refine_upsample(video_u8, F2: int, H: int, W: int, pad_front: int = 0, pad_back: int = 0):
+    """uint8 [F,H0,W0,3] on the device -> fp32 [3, pad_front+F2+pad_back, H, W] in [-1,1] (bf16-representable values)."""
+    assert video_u8.dtype == torch.uint8 and video_u8.is_contiguous() and video_u8.dim() == 4 and video_u8.shape[3] == 3
+    F, H0, W0, _ = video_u8.shape
+    out = torch.empty(3, pad_front + F2 + pad_back, H, W, dtype=torch.float32, device=video_u8.device)
+    _call("wf_refine_upsample", _p(video_u8), F, H0, W0, _p(out), F2, H, W, pad_front, pad_back, _stream())
     return out
 
 

@@ -63,6 +63,37 @@ def rope_table(grid, head_dim: int = 128) -> torch.Tensor:
     return torch.stack([a.cos(), a.sin()], dim=-1).contiguous()
 
 
+def merge_lora(sd: Dict[str, torch.Tensor], lora_sd: Dict[str, torch.Tensor], multiplier: float = 1.0, rank: int = 128,
+               alpha: float = 64.0) -> Dict[str, torch.Tensor]:
+    """Fold a LongCat LoRA (lora_utils.py:27-75; key scheme ``lora___lorahyphen___<module path with ___lorahyphen___>``)
+    into the Linear weights it decorates: W' = W + multiplier * alpha/rank * up @ down, ``up`` block-diagonal over
+    ``lora_up.blocks.i`` for the fused qkv / kv projections (LoRAUPParallel, :15-24).  The reference evaluates the LoRA
+    branch as two bf16 side GEMMs at run time (longcat_video_dit.py:234-249); folding differs from that by bf16
+    rounding of the branch only and removes the side GEMMs from every step of the refine pass."""
+    out = dict(sd)
+    scale = multiplier * (alpha / rank if alpha else 1.0)
+    names = sorted(k[: -len(".lora_down.weight")] for k in lora_sd if k.endswith(".lora_down.weight"))
+    for name in names:
+        module = name.replace("lora___lorahyphen___", "").replace("___lorahyphen___", ".")
+        wkey = module + ".weight"
+        if wkey not in out:
+            continue
+        down = lora_sd[name + ".lora_down.weight"].float()                     # [n*rank, in]
+        if name + ".lora_up.weight" in lora_sd:
+            delta = lora_sd[name + ".lora_up.weight"].float() @ down
+        else:
+            blocks = []
+            i = 0
+            while f"{name}.lora_up.blocks.{i}.weight" in lora_sd:
+                blocks.append(lora_sd[f"{name}.lora_up.blocks.{i}.weight"].float())
+                i += 1
+            r = down.shape[0] // len(blocks)
+            delta = torch.cat([u @ down[j * r:(j + 1) * r] for j, u in enumerate(blocks)], dim=0)
+        w = out[wkey]
+        out[wkey] = (w.float() + scale * delta.to(w.device)).to(w.dtype)
+    return out
+
+
 class WfLongCatTransformer:
     def __init__(self, cfg: LongCatConfig, device):
         assert cfg.hidden_size // cfg.num_heads == 128 and cfg.patch == (1, 2, 2)
@@ -73,9 +104,40 @@ class WfLongCatTransformer:
         self.blocks = []
         self._buf, self._rope, self._ctx_cache = {}, {}, {}
         self.calls = 0
+        self.bsa_params = None          # the checkpoint's bsa_params (longcat_video_dit.py:32,56)
+        self._bsa_on = False
 
     def to(self, *a, **k):
         return self
+
+    # block-sparse self-attention of the 720p refine pass (longcat_video_dit.py:272-278, attention.py:56-67)
+    def enable_bsa(self):
+        if self.bsa_params is None:
+            raise lib.WfError("enable_bsa(): no bsa_params (set .bsa_params to the checkpoint's dict first)")
+        if self.bsa_params.get("cdf_threshold") is not None:
+            raise lib.WfError("BSA selection by cdf_threshold is not implemented on the device (top-k sparsity only)")
+        self._bsa_on = True
+
+    def disable_bsa(self):
+        self._bsa_on = False
+
+    def _self_attention(self, q, k, v, out, grid_q, grid_k, sparse: bool):
+        """One _process_attn call (attention.py:49-103): dense, or gating + block-sparse when BSA is enabled."""
+        Hn = self.cfg.num_heads
+        if not sparse:
+            return lib.attention_bf16(q, k, v, out, Hn)
+        bp = self.bsa_params
+        chunk = tuple(bp.get("chunk_3d_shape_q", (4, 4, 8)))
+        if tuple(bp.get("chunk_3d_shape_k", (4, 4, 8))) != chunk:
+            raise lib.WfError("BSA with different query / key chunk shapes is not implemented")
+        q_cmp = lib.bsa_mean_pool(q, grid_q, chunk, Hn)
+        k_cmp = lib.bsa_mean_pool(k, grid_k, chunk, Hn)
+        n_sel = int((1 - bp.get("sparsity", 0.875)) * k_cmp.shape[1])           # bsa_interface.py:223
+        if n_sel < 1:
+            out.zero_()                                                        # nothing selected: the kernel's acc = 0, l = 1
+            return out
+        idx = lib.bsa_select_topk(q_cmp, k_cmp, n_sel)
+        return lib.attention_bsa_bf16(q, k, v, out, Hn, idx, None, grid_q, grid_k, chunk)
 
     @classmethod
     def from_state_dict(cls, sd: Dict[str, torch.Tensor], cfg: LongCatConfig, device) -> "WfLongCatTransformer":
@@ -198,11 +260,14 @@ class WfLongCatTransformer:
             lib.rms_norm_head_rope_(Bf.qkv[:, :C], b.qn, 1e-6, rope)
             lib.rms_norm_head_rope_(Bf.qkv[:, C:2 * C], b.kn, 1e-6, rope)
             q, k, v = Bf.qkv[:, :C], Bf.qkv[:, C:2 * C], Bf.qkv[:, 2 * C:]
+            # in the reference BSA is skipped for single-frame inputs as a whole (shape[0] > 1, attention.py:56)
+            sparse = self._bsa_on and T > 1
+            gq = lambda t: (t, grid[1], grid[2])
             if nc > 0:      # condition tokens see only condition tokens; noise tokens see everything (attention.py:124-135)
-                lib.attention_bf16(q[:nc], k[:nc], v[:nc], Bf.att[:nc], Hn)
-                lib.attention_bf16(q[nc:], k, v, Bf.att[nc:], Hn)
+                self._self_attention(q[:nc], k[:nc], v[:nc], Bf.att[:nc], gq(num_cond), gq(num_cond), sparse)
+                self._self_attention(q[nc:], k, v, Bf.att[nc:], gq(T - num_cond), gq(T), sparse)
             else:
-                lib.attention_bf16(q, k, v, Bf.att, Hn)
+                self._self_attention(q, k, v, Bf.att, gq(T), gq(T), sparse)
             lib.gemm_bf16(Bf.att, b.proj_w, b.proj_b, Bf.x, lib.EPI_RESID_BF16, gate=tab[2], gate_rows=per)
             # cross attention, noise tokens only
             lib.layer_norm(Bf.x, Bf.h, 1e-6, weight=b.n_w, bias=b.n_b)

@@ -20,6 +20,7 @@ the two boundary roundings the reference has, can round the decoder input and th
 """
 from __future__ import annotations
 
+import math
 import os
 from concurrent.futures import ThreadPoolExecutor
 from types import SimpleNamespace
@@ -117,6 +118,26 @@ class WfFlowMatchEulerScheduler:
     step_index = property(lambda self: self._step_index)
     begin_index = property(lambda self: self._begin_index)
 
+    # generate_refine assigns scheduler.timesteps / scheduler.sigmas directly (pipeline_longcat_video.py:1390-1391): the
+    # host copies the step arithmetic reads follow such assignments
+    @property
+    def timesteps(self):
+        return self._timesteps
+
+    @timesteps.setter
+    def timesteps(self, value):
+        self._timesteps = value
+        self._timesteps_host = value.detach().to("cpu", torch.float32)
+
+    @property
+    def sigmas(self):
+        return self._sigmas
+
+    @sigmas.setter
+    def sigmas(self, value):
+        self._sigmas = value
+        self._sigmas_host = value.detach().to("cpu", torch.float32)
+
     def set_begin_index(self, begin_index: int = 0):
         self._begin_index = begin_index
 
@@ -126,10 +147,9 @@ class WfFlowMatchEulerScheduler:
         sig = (sigmas.detach().cpu().numpy() if isinstance(sigmas, torch.Tensor) else np.asarray(sigmas)).astype(np.float32)
         sig = self.shift * sig / (1 + (self.shift - 1) * sig)
         host = torch.from_numpy(sig).to(torch.float32)
-        self._sigmas_host = torch.cat([host, torch.zeros(1)])
-        self._timesteps_host = host * self.config.num_train_timesteps
-        self.sigmas = self._sigmas_host.to(device) if device is not None else self._sigmas_host
-        self.timesteps = self._timesteps_host.to(device) if device is not None else self._timesteps_host
+        sig_h, ts_h = torch.cat([host, torch.zeros(1)]), host * self.config.num_train_timesteps
+        self.sigmas = sig_h.to(device) if device is not None else sig_h
+        self.timesteps = ts_h.to(device) if device is not None else ts_h
         self.num_inference_steps = len(sig)
         self._step_index = None
         self._begin_index = None
@@ -276,6 +296,79 @@ def denoise_loop(dit, vae, scheduler, latents, prompt_embeds, prompt_attention_m
             latents[:, :, 1:] = b.prev_sample
         elif out is not None:
             latents[:, :, 1:] = out.prev_sample
+        if on_step is not None:
+            on_step(i, latents)
+    return latents
+
+
+# ------------------------------------------------------------------------------------------------ refine (720p) pass
+def refine_schedule(scheduler, num_inference_steps: int = 50, t_thresh: float = 0.5, device=None):
+    """generate_refine step 4 (pipeline_longcat_video.py:1382-1391): the standard schedule cut at ``t_thresh``."""
+    scheduler.set_timesteps(num_inference_steps, sigmas=timesteps_sigmas(num_inference_steps), device=device)
+    timesteps = scheduler.timesteps
+    if t_thresh:
+        tt = torch.tensor(t_thresh * 1000, dtype=timesteps.dtype, device=timesteps.device)
+        timesteps = torch.cat([tt.unsqueeze(0), timesteps[timesteps < tt]])
+        scheduler.timesteps = timesteps
+        scheduler.sigmas = torch.cat([timesteps / 1000, torch.zeros(1, device=timesteps.device)])
+    return timesteps
+
+
+def refine_padding(num_frames: int, num_cond_frames: int, temporal: int = 4, granularity: int = 4):
+    """BSA padding of generate_refine (:1406-1421) -> (num_cond_latents, cond_frames_added, num_cond_frames, noise_frames_added)."""
+    num_noise_frames = num_frames - num_cond_frames
+    ncl = added = 0
+    if num_cond_frames > 0:
+        ncl = 1 + math.ceil((num_cond_frames - 1) / temporal)
+        ncl = math.ceil(ncl / granularity) * granularity
+        added = 1 + (ncl - 1) * temporal - num_cond_frames
+        num_cond_frames = num_cond_frames + added
+    nnl = math.ceil(num_noise_frames / temporal)
+    nnl = math.ceil(nnl / granularity) * granularity
+    return ncl, added, num_cond_frames, nnl * temporal - num_noise_frames
+
+
+@torch.no_grad()
+def refine_prepare(stage1_u8: torch.Tensor, image, vae, height: int, width: int, generator, t_thresh: float = 0.5,
+                   num_cond_frames: int = 0, spatial_refine_only: bool = False, device="cuda"):
+    """generate_refine step 5 (:1393-1455).  stage1_u8: uint8 [F,H0,W0,3] (the stage-1 frames); image: [1,3,height,width] in
+    [-1,1] (after video_processor.preprocess) or None.  -> (latents fp32 [1,16,T,h,w] on the device, num_cond_latents,
+    cond_frames_added, new_frame_size).  The resize chain is one kernel (wf_refine_upsample); the noise comes from the CPU
+    generator as in the reference (:1427)."""
+    nf = stage1_u8.shape[0]
+    new_frames = nf if spatial_refine_only else 2 * nf
+    ncl, added, ncf, back = refine_padding(new_frames, num_cond_frames)
+    up = lib.refine_upsample(stage1_u8.to(device).contiguous(), new_frames, height, width, added, back).unsqueeze(0)
+    mean_h, inv_std_h = latent_stats(vae.config.latents_mean, vae.config.latents_std, torch.float32)
+    enc = vae.encode(up).latent_dist.mode().contiguous()
+    lat = lib.latent_norm_replace(enc, enc, mean_h, inv_std_h, [])
+    noise = torch.randn(lat.shape, generator=generator, dtype=lat.dtype).pin_memory().to(device=device, non_blocking=True)
+    latents = lib.renoise(lat, noise, float(1 - t_thresh), float(t_thresh))
+    if image is not None:
+        enc_in = image.to(device=device, dtype=torch.float32).unsqueeze(2)
+        if added > 0:
+            enc_in = torch.cat([enc_in[:, :, 0:1].repeat(1, 1, added, 1, 1), enc_in], dim=2)
+        assert enc_in.shape[2] == ncf
+        cenc = vae.encode(enc_in.contiguous()).latent_dist.mode().contiguous()
+        latents[:, :, : 1 + (ncf - 1) // 4] = lib.latent_norm_replace(cenc, cenc, mean_h, inv_std_h, [])
+    return latents, ncl, added, new_frames
+
+
+@torch.no_grad()
+def refine_loop(dit, scheduler, latents, prompt_embeds, prompt_attention_mask, num_cond_latents: int, timesteps, on_step=None):
+    """generate_refine's loop (:1467-1498): one DiT forward (block-sparse self-attention when dit.enable_bsa() was called),
+    sign flip, Euler step on the noise latents only; no CFG, no IRR / FLF / DSG."""
+    dit_dtype = dit.dtype
+    for i, t in enumerate(timesteps):
+        x = latents.to(dit_dtype)
+        ts = t.expand(x.shape[0]).to(dit_dtype).unsqueeze(-1).repeat(1, x.shape[2])
+        ts[:, :num_cond_latents] = 0
+        pred = dit(hidden_states=x, timestep=ts, encoder_hidden_states=prompt_embeds, encoder_attention_mask=prompt_attention_mask,
+                   num_cond_latents=num_cond_latents)
+        # -pred, then sample + dt*(-pred): x0_convert(sample, pred, dt) = sample - dt*pred has the same two roundings
+        noise_pred = -pred
+        latents[:, :, num_cond_latents:] = scheduler.step(noise_pred[:, :, num_cond_latents:], t, latents[:, :, num_cond_latents:],
+                                                          return_dict=False)[0]
         if on_step is not None:
             on_step(i, latents)
     return latents
