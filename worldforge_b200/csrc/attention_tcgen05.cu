@@ -313,7 +313,7 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x2, float& e0, float& e1) {
 // PTMEM: P_t(j) is stored back into the first 32 columns of the S buffer it was computed from (64 bf16 = 32 columns)
 // and consumed by the PV product as a TMEM operand: no shared-memory round trip for P, which with 64-key blocks is
 // what pushes shared-memory reads (Q 32 KB + K 16 KB per S product, P 16 KB + V 16 KB per PV product) past the MMA time.
-template <bool POLY, bool PTMEM>
+template <int POLY, bool PTMEM>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tcgen05_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, AttnArgs p) {
@@ -472,7 +472,7 @@ attention_tcgen05_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       for (int i = 0; i < 32; ++i) {
         const uint64_t x2 = ffma2(pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), c2, nm2);
         float e0, e1;
-        if (POLY && (i & 3) == 3 && valid >= AT_BN) {
+        if (((POLY == 1 && (i & 3) == 3) || (POLY == 2 && (i & 1))) && valid >= AT_BN) {
           exp2_poly2(x2, e0, e1);
         } else {
           float x0, x1; unpack2(x2, x0, x1);
@@ -589,20 +589,24 @@ extern "C" int wf_attention_bf16(const void* q, int ldq, const void* k, int ldk,
   if (variant == 0) {
     const char* e = getenv("WF_ATTN");
     variant = e ? atoi(e) : 4;
-    if (variant < 1 || variant > 4) variant = 4;
+    if (variant < 1 || variant > 6) variant = 4;
     WF_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-    WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)));
-    WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)));
-    WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)));
+    WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v2<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)));
+    WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v2<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)));
+    WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v2<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)));
+    WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v2<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)));
+    WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v2<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)));
   }
   AttnArgs args{Lq, Lk, static_cast<bf16*>(out), ldo, static_cast<const bf16*>(add_in), ld_add,
                 softmax_scale * 1.4426950408889634f};
   dim3 grid((Lq + 2 * AT_BM - 1) / (2 * AT_BM), heads);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (variant == 1) attention_tcgen05<<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);
-  else if (variant == 2) attention_tcgen05_v2<false, false><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);
-  else if (variant == 3) attention_tcgen05_v2<true, false><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);
-  else attention_tcgen05_v2<false, true><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);   // 4: P through TMEM
+  else if (variant == 2) attention_tcgen05_v2<0, false><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);
+  else if (variant == 3) attention_tcgen05_v2<1, false><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);
+  else if (variant == 5) attention_tcgen05_v2<1, true><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);   // 4 + 25% polynomial ex2
+  else if (variant == 6) attention_tcgen05_v2<2, true><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);   // 4 + 50% polynomial ex2
+  else attention_tcgen05_v2<0, true><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);   // 4: P through TMEM
   WF_LAUNCH_OK();
   return WF_OK;
 }
