@@ -147,7 +147,7 @@ def run_reference(args):
     f, h, w = (args.frames - 1) // 4 + 1, args.height // 8, args.width // 8
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"Wan2.1-I2V-14B {args.height}x{args.width} {args.frames}f, IRR+FLF+DSG, guided:plain 3:7 "
                                "(CPU port of the reference, bounded sample extrapolated)", "tokens": f * (h // 2) * (w // 2)},
