@@ -179,6 +179,8 @@ def run_ours(args):
         from worldforge_b200 import ulysses
         ulysses.enable(tr, dist.group.WORLD)
     vae = wvae.WfWanVAE.random_init(dev, seed=4321)
+    if world > 1:
+        vae.enable_row_sharding(dist.group.WORLD)      # encode / decode split by image rows; FLF scoring by channels
     inp = synth.make_inputs(args.frames, args.height, args.width, seed=42)
     f, h, w = (args.frames - 1) // 4 + 1, args.height // 8, args.width // 8
     L = f * (h // 2) * (w // 2)
@@ -278,7 +280,7 @@ def run_ours(args):
         "config": {"workload": f"Wan2.1-I2V-14B {args.height}x{args.width} {args.frames}f guided sampling (IRR+FLF+DSG), "
                                f"{k_guided} guided + {K - k_guided} plain timed steps (the 15:35 mix of the 50-step run)",
                    "tokens": L, "dit_layers": args.layers, "dit_forwards_timed": fwd - 4 * W,
-                   "vae": "fp32 storage, tf32 tensor-core convs", "parallelism": "single GPU" if world == 1 else f"ulysses{world}",
+                   "vae": "fp32 storage, tf32 tensor-core convs", "parallelism": "single GPU" if world == 1 else f"ulysses{world} (DiT tokens) + vae-rows{world} + flf-channels{world}",
                    "l2_policy": "inputs larger than L2 (33 GB of weights, 0.67 GB activations streamed per GEMM)"},
         "clocks": clk, "gpu_launches": launches, "e2e": e2e, "roofline": roof,
         "dit_forwards_per_sec": (fwd - 4 * W) / (ms / 1000.0),

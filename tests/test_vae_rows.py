@@ -1,0 +1,110 @@
+"""Host logic of the VAE's row sharding (no GPU): the backwards walk that finds which input rows a rank's output rows
+depend on, checked against torch convolutions standing in for the layers, and the gather of uneven row slabs over gloo."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn.functional as F
+
+from worldforge_b200 import vae as wvae
+
+
+def _layer(kind, x, w):
+    """A stand-in with the same spatial footprint as the VAE layer kinds (x: [1,1,H,W])."""
+    conv = lambda t: F.conv2d(t, w, padding=1)
+    if kind in ("conv", "head"):
+        return conv(x)
+    if kind == "res":
+        return x + conv(torch.tanh(conv(x)))
+    if kind in ("up2d", "up3d"):
+        return conv(F.interpolate(x, scale_factor=2.0, mode="nearest-exact"))
+    if kind in ("down2d", "down3d"):
+        return F.conv2d(F.pad(x, (0, 1, 0, 1)), w, stride=2)
+    raise ValueError(kind)
+
+
+def _run(seg, x, w):
+    for kind, *_ in seg:
+        x = _layer(kind, x, w)
+    return x
+
+
+ENC = [("conv", "c", 0, 0), ("res", "r", 0, 0), ("res", "r", 0, 0), ("down2d", "d", 0, 0), ("res", "r", 0, 0), ("down3d", "d", 0, 0),
+       ("res", "r", 0, 0), ("down3d", "d", 0, 0)]
+DEC = [("up3d", "u", 0, 0), ("res", "r", 0, 0), ("res", "r", 0, 0), ("up3d", "u", 0, 0), ("res", "r", 0, 0), ("up2d", "u", 0, 0),
+       ("res", "r", 0, 0), ("head", "h", 0, 0)]
+
+
+class _StandIn(wvae.WfWanVAE):
+    """WfWanVAE's row-slab driver (_run_rows) over torch stand-ins of the layers; activations are [1, H, W, 1]."""
+
+    def __init__(self, w):
+        self.wt = w
+
+    def _run(self, plan, x, final_planar=None):
+        y = x.permute(0, 3, 1, 2)
+        for kind, *_ in plan:
+            y = _layer(kind, y, self.wt)
+        return y.permute(0, 2, 3, 1)
+
+
+@pytest.mark.parametrize("seg,h_in,out_scale", [(ENC, 96, 1), (DEC, 12, 8)])
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_row_slabs_reproduce_the_full_evaluation(seg, h_in, out_scale, world):
+    """A rank's slab - the rows need[0] with zero padding at the slab edges (what the conv kernels do), re-cut before
+    every resampling layer - yields the rank's output rows exactly."""
+    torch.manual_seed(0)
+    x = torch.randn(1, h_in, 16, 1, dtype=torch.float64)
+    m = _StandIn(torch.randn(1, 1, 3, 3, dtype=torch.float64))
+    full = m._run(seg, x)
+    b = m.row_bounds(12, world)
+    for r in range(world):
+        lo, hi = out_scale * b[r], out_scale * b[r + 1]
+        need, hs = m._needed_rows(seg, (lo, hi), h_in)
+        assert hs[-1] == full.shape[1] and need[-1] == (lo, hi)
+        a, e = need[0]
+        y, first = m._run_rows(seg, x[:, a:e], a, need)
+        assert first == lo and torch.equal(y, full[:, lo:hi]), (r, need)
+        for kind, (nlo, nhi) in zip([s[0] for s in seg], need):
+            if kind in m.DOWNS:
+                assert nlo % 2 == 0 and (nhi - nlo) % 2 == 0      # space-to-depth needs aligned, even slabs
+
+
+def test_row_bounds_partition():
+    for h in (60, 90, 7, 8):
+        for world in (1, 2, 4, 8):
+            if world > h:
+                continue
+            b = wvae.WfWanVAE.row_bounds(h, world)
+            assert b[0] == 0 and b[-1] == h and len(b) == world + 1
+            sizes = [b[i + 1] - b[i] for i in range(world)]
+            assert min(sizes) >= 1 and max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        m = wvae.WfWanVAE.__new__(wvae.WfWanVAE)
+        m.enable_row_sharding()
+        assert (m.shard.world, m.shard.rank) == (world, rank)
+        full = torch.arange(2 * 7 * 3, dtype=torch.float32).reshape(2, 7, 3)
+        b = m.row_bounds(7, world)                                   # uneven: 3 + 4 rows
+        got = m._all_gather_rows(full[:, b[rank]:b[rank + 1]].contiguous(), 1, b)
+        ret[rank] = torch.equal(got, full)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_of_uneven_row_slabs_gloo():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]

@@ -1,4 +1,5 @@
-"""torchrun --nproc-per-node 2 tools/ulysses_check.py : sequence-parallel DiT forward == single-GPU forward (tiny widths)."""
+"""torchrun --nproc-per-node N tools/ulysses_check.py : sequence-parallel DiT forward == single-GPU forward (tiny widths),
+row-sharded VAE encode / decode == single-GPU encode / decode (bit for bit), rank-sharded FLF scoring == single-rank scoring."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
@@ -23,6 +24,20 @@ torch.cuda.synchronize()
 same = torch.equal(single, par)
 md = (single.float() - par.float()).abs().max().item()
 print(f"rank {rank}/{world}: sequence-parallel forward equal to single-GPU: {same} (max diff {md}), a2a calls {sp.a2a_calls}", flush=True)
+from worldforge_b200 import flf_select, vae as wvae
+v = wvae.WfWanVAE.random_init(dev, dim=16, seed=3)
+video = (torch.rand(1, 3, 9, 128, 96, generator=g) * 2 - 1).to(dev)
+z = torch.randn(1, 16, 3, 16, 12, generator=g).to(dev)
+mu1, dec1 = v.encode(video).latent_dist.mode().clone(), v.decode(z)[0].clone()
+v.enable_row_sharding(dist.group.WORLD)
+mu2, dec2 = v.encode(video).latent_dist.mode(), v.decode(z)[0]
+torch.cuda.synchronize()
+vae_ok = torch.equal(mu1, mu2) and torch.equal(dec1, dec2)
+print(f"rank {rank}/{world}: row-sharded VAE equal to single-GPU: encode {torch.equal(mu1, mu2)} decode {torch.equal(dec1, dec2)}", flush=True)
+a, b = torch.randn(1, 16, 6, 30, 52, generator=g).to(dev), torch.randn(1, 16, 6, 30, 52, generator=g).to(dev)
+s1 = flf_select.FlowChannelSelector().scores(a, b)
+s2 = flf_select.FlowChannelSelector(group=dist.group.WORLD, world=world, rank=rank).scores(a, b)
+print(f"rank {rank}/{world}: rank-sharded FLF scores equal: {s1 == s2}", flush=True)
 dist.barrier()
 dist.destroy_process_group()
-sys.exit(0 if md < 1e-2 else 1)
+sys.exit(0 if md < 1e-2 and vae_ok and s1 == s2 else 1)

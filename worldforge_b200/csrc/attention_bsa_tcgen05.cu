@@ -80,8 +80,9 @@ attention_bsa_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* v_full = k_empty + BS_STAGES;
   uint64_t* v_empty = v_full + BS_STAGES;
   uint64_t* s_full = v_empty + BS_STAGES;    // [tile][buf] -> 4
-  uint64_t* p_full = s_full + 4;             // 2
-  uint64_t* o_done = p_full + 2;             // 2
+  uint64_t* p_full = s_full + 4;             // [tile][buf] -> 4 (a tile may signal P(j) and P(j+1) before the issuer looks:
+                                             // one barrier per S buffer, or the phase parity would wrap)
+  uint64_t* o_done = p_full + 4;             // 2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -113,7 +114,8 @@ attention_bsa_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
     }
     for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1);
-    for (int t = 0; t < 2; ++t) { mbar_init(&p_full[t], 4); mbar_init(&o_done[t], 1); }
+    for (int i = 0; i < 4; ++i) mbar_init(&p_full[i], 4);
+    for (int t = 0; t < 2; ++t) mbar_init(&o_done[t], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -223,7 +225,7 @@ attention_bsa_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       for (int t = 0; t < 2; ++t) {
         const int seq = 2 * j + t;
         mbar_wait(&v_full[seq % BS_STAGES], (seq / BS_STAGES) & 1);
-        mbar_wait(&p_full[t], j & 1);
+        mbar_wait(&p_full[2 * t + (j & 1)], (j >> 1) & 1);
         tc_fence_after();
         if (elect_one()) issue_pv(t, j);
         __syncwarp();
@@ -325,7 +327,7 @@ attention_bsa_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane_id() == 0) mbar_arrive(&p_full[t]);
+      if (lane_id() == 0) mbar_arrive(&p_full[2 * t + buf]);
     }
     if (nsteps > 0) {
       mbar_wait(&o_done[t], (nsteps - 1) & 1);

@@ -324,8 +324,11 @@ attention_tcgen05_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* kv_full = bars + 1;
   uint64_t* kv_empty = kv_full + AT_STAGES;
   uint64_t* s_full = kv_empty + AT_STAGES;   // [tile][buf] -> 4
-  uint64_t* p_full = s_full + 4;             // 2
-  uint64_t* o_done = p_full + 2;             // 2
+  uint64_t* p_full = s_full + 4;             // [tile][buf] -> 4: with P in TMEM the softmax of block j+1 does not wait for
+                                             // PV(j), so a tile can signal P(j) and P(j+1) before the issuer looks - one
+                                             // barrier per S buffer keeps the two completions apart (a single barrier
+                                             // would wrap its phase parity and the issuer would wait forever)
+  uint64_t* o_done = p_full + 4;             // 2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -339,7 +342,8 @@ attention_tcgen05_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_init(q_full, 1);
     for (int s = 0; s < AT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1);
-    for (int t = 0; t < 2; ++t) { mbar_init(&p_full[t], 4); mbar_init(&o_done[t], 1); }
+    for (int i = 0; i < 4; ++i) mbar_init(&p_full[i], 4);
+    for (int t = 0; t < 2; ++t) mbar_init(&o_done[t], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -414,11 +418,11 @@ attention_tcgen05_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (elect_one()) { issue_s(0, nstage, (j + 1) & 1); issue_s(1, nstage, (j + 1) & 1); }
         __syncwarp();
       }
-      mbar_wait(&p_full[0], j & 1);
+      mbar_wait(&p_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
       if (elect_one()) issue_pv(0, stage, j);
       __syncwarp();
-      mbar_wait(&p_full[1], j & 1);
+      mbar_wait(&p_full[2 + (j & 1)], (j >> 1) & 1);
       tc_fence_after();
       if (elect_one()) { issue_pv(1, stage, j); umma_commit(&kv_empty[stage]); }
       __syncwarp();
@@ -514,9 +518,291 @@ attention_tcgen05_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
       tc_fence_before();
       __syncwarp();
-      if (lane_id() == 0) mbar_arrive(&p_full[t]);
+      if (lane_id() == 0) mbar_arrive(&p_full[2 * t + buf]);
     }
     mbar_wait(&o_done[t], (nblk - 1) & 1);
+    tc_fence_after();
+    const int q = q0 + t * AT_BM + row;
+    const float inv_l = 1.0f / l;
+#pragma unroll 1
+    for (int cc = 0; cc < AT_D; cc += 32) {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(o_tmem + cc, o);
+      tmem_ld_wait();
+      if (q < p.Lq) {
+        bf16* dst = p.out + static_cast<size_t>(q) * p.ldo + col0 + cc;
+        const bf16* add = p.add_in ? p.add_in + static_cast<size_t>(q) * p.ld_add + col0 + cc : nullptr;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          float w[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) w[u] = __uint_as_float(o[i + u]) * inv_l;
+          if (add) {
+            uint4 a = *reinterpret_cast<const uint4*>(add + i);
+            const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float2 f = __bfloat1622float2(a2[u]);
+              w[2 * u] = __fadd_rn(bf16_round(w[2 * u]), f.x);
+              w[2 * u + 1] = __fadd_rn(bf16_round(w[2 * u + 1]), f.y);
+            }
+          }
+          uint4 v = make_uint4(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]), pack_bf16x2(w[4], w[5]),
+                               pack_bf16x2(w[6], w[7]));
+          *reinterpret_cast<uint4*>(dst + i) = v;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+
+// =====================================================================================================================
+// v3: 128-key blocks.  With 64-key blocks every S product re-reads the 32 KB query tile from shared memory for 64 keys'
+// worth of math - the UMMA operand fetch (Q 32 KB + K 16 KB per 256 MMA clocks = 192 B/clk against the 128 B/clk shared
+// memory delivers) is what holds v2's tensor pipe at 58 %.  At 128 keys the S product reads 64 KB per 512 MMA clocks and
+// the PV product (P from TMEM) 32 KB per 512: the tensor core is fed.  TMEM cannot hold two S buffers per tile at that
+// width (2 tiles x 2 x 128 + 2 x 128 columns of O = 768 > 512), so the two query tiles ping-pong instead: S_t lives in
+// 128 columns, P_t (bf16) overwrites its first 64, and the issuer's order  PV_0(j) S_0(j+1) PV_1(j) S_1(j+1)  leaves each
+// tile's softmax the time of the other tile's two products.  tcgen05.mma retires in issue order, so S_t(j+1) cannot
+// overwrite P_t(j) before PV_t(j) has read it, and "S_t(j+1) complete" tells the softmax that O_t is quiescent.
+// K and V travel separately through one 5-slot ring of 32 KB boxes in consumption order K0 V0 K1 V1 ...
+// The softmax warpgroups hold a whole 128-score row in registers (setmaxnreg moves the producer warps' registers to
+// them), and POLY of every 8 exponential pairs are evaluated on the FMA pipe (Cody-Waite + cubic) because 128x128
+// MUFU.EX2 per tile-block cost exactly the 1024 clocks the two products take.
+// TMEM columns: S_t / P_t at 128 t, O_t at 256 + 128 t.
+// =====================================================================================================================
+constexpr int A3_BN = 128, A3_SLOTS = 5;
+constexpr int A3_SLOT_BYTES = A3_BN * AT_D * 2;          // 32 KB: one K or one V block
+constexpr int A3_OFF_RING = 2 * AT_Q_BYTES;
+constexpr int A3_OFF_BAR = A3_OFF_RING + A3_SLOTS * A3_SLOT_BYTES;
+constexpr int A3_SMEM = A3_OFF_BAR + 256 + 1024;
+constexpr int A3_REGS_PRODUCER = 40, A3_REGS_SOFTMAX = 232;   // (2*232 + 40) * 128 = 168 * 384
+
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+template <uint32_t POLY_MASK>
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attention_tcgen05_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, AttnArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A3_OFF_BAR);
+  uint64_t* q_full = bars;                       // 1
+  uint64_t* ring_full = bars + 1;                // A3_SLOTS
+  uint64_t* ring_empty = ring_full + A3_SLOTS;   // A3_SLOTS
+  uint64_t* s_full = ring_empty + A3_SLOTS;      // 2
+  uint64_t* p_full = s_full + 2;                 // 2
+  uint64_t* o_done = p_full + 2;                 // 2 (final PV of each tile)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int head = blockIdx.y;
+  const int q0 = blockIdx.x * (2 * AT_BM);
+  const int nblk = (p.Lk + A3_BN - 1) / A3_BN;
+  const int col0 = head * AT_D;
+
+  if (warp == 0 && elect_one()) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); }
+  if (warp == 1 && elect_one()) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < A3_SLOTS; ++s) { mbar_init(&ring_full[s], 1); mbar_init(&ring_empty[s], 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 4); mbar_init(&o_done[t], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    setmaxnreg_dec<A3_REGS_PRODUCER>();
+    if (warp == 0) {
+      // ---------------------------------------------------------- TMA producer: Q, then K0 V0 K1 V1 ...
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, 2 * AT_Q_BYTES);
+        for (int t = 0; t < 2; ++t)
+          for (int half = 0; half < 2; ++half)
+            tma_load_2d(smem + t * AT_Q_BYTES + half * (AT_Q_BYTES / 2), &tmQ, q_full, col0 + half * 64, q0 + t * AT_BM);
+      }
+      __syncwarp();
+      int slot = 0; uint32_t phase = 0;
+      for (int i = 0; i < 2 * nblk; ++i) {
+        mbar_wait_trap(&ring_empty[slot], phase ^ 1);
+        if (elect_one()) {
+          uint8_t* dst = smem + A3_OFF_RING + slot * A3_SLOT_BYTES;
+          const CUtensorMap* tm = (i & 1) ? &tmV : &tmK;
+          mbar_arrive_expect_tx(&ring_full[slot], A3_SLOT_BYTES);
+          tma_load_2d(dst, tm, &ring_full[slot], col0, (i >> 1) * A3_BN);
+          tma_load_2d(dst + A3_SLOT_BYTES / 2, tm, &ring_full[slot], col0 + 64, (i >> 1) * A3_BN);
+        }
+        __syncwarp();
+        if (++slot == A3_SLOTS) { slot = 0; phase ^= 1; }
+      }
+    } else if (warp == 1) {
+      // ------------------------------------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc_s = umma_idesc(1, AT_BM, A3_BN, 0, 0);   // S = Q K^T, both K-major
+      constexpr uint32_t idesc_o = umma_idesc(1, AT_BM, AT_D, 0, 1);    // O += P V, V MN-major
+      const uint32_t q_addr = smem_u32(smem);
+      const uint32_t ring_addr = smem_u32(smem + A3_OFF_RING);
+      auto issue_s = [&](int t, int slot) {
+        const uint32_t k_addr = ring_addr + slot * A3_SLOT_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < AT_D / 16; ++ks) {
+          uint64_t da = umma_desc_sw128(q_addr + t * AT_Q_BYTES + (ks >> 2) * (AT_Q_BYTES / 2) + (ks & 3) * 32, 16, 1024);
+          uint64_t db = umma_desc_sw128(k_addr + (ks >> 2) * (A3_SLOT_BYTES / 2) + (ks & 3) * 32, 16, 1024);
+          umma_f16_ss(tmem_base + t * A3_BN, da, db, idesc_s, ks != 0);
+        }
+        umma_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](int t, int slot, int j) {
+        const uint32_t v_addr = ring_addr + slot * A3_SLOT_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < A3_BN / 16; ++ks) {
+          uint64_t db = umma_desc_sw128(v_addr + ks * 2048, A3_SLOT_BYTES / 2, 1024);
+          umma_f16_ts(tmem_base + AT2_TMEM_O + t * AT_D, tmem_base + t * A3_BN + ks * 8, db, idesc_o, (j | ks) != 0);
+        }
+      };
+      int slot = 0; uint32_t phase = 0;          // ring position of the next block to consume
+      auto advance = [&]() { if (++slot == A3_SLOTS) { slot = 0; phase ^= 1; } };
+      mbar_wait_trap(q_full, 0);
+      mbar_wait_trap(&ring_full[slot], phase);        // K0
+      tc_fence_after();
+      if (elect_one()) { issue_s(0, slot); issue_s(1, slot); umma_commit(&ring_empty[slot]); }
+      __syncwarp();
+      advance();
+      for (int j = 0; j < nblk; ++j) {
+        const bool more = (j + 1 < nblk);
+        const int v_slot = slot; const uint32_t v_phase = phase;
+        advance();
+        const int k_slot = slot; const uint32_t k_phase = phase;
+        if (more) advance();
+        mbar_wait_trap(&ring_full[v_slot], v_phase);                 // V_j
+        mbar_wait_trap(&p_full[0], j & 1);
+        tc_fence_after();
+        if (elect_one()) issue_pv(0, v_slot, j);
+        __syncwarp();
+        if (more) {
+          mbar_wait_trap(&ring_full[k_slot], k_phase);               // K_{j+1}
+          tc_fence_after();
+          if (elect_one()) issue_s(0, k_slot);
+          __syncwarp();
+        } else if (elect_one()) {
+          umma_commit(&o_done[0]);
+        }
+        mbar_wait_trap(&p_full[1], j & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_pv(1, v_slot, j);
+          umma_commit(&ring_empty[v_slot]);
+          if (more) { issue_s(1, k_slot); umma_commit(&ring_empty[k_slot]); }
+          else umma_commit(&o_done[1]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------------- softmax + epilogue
+    setmaxnreg_inc<A3_REGS_SOFTMAX>();
+    const int t = (warp - 4) >> 2;
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane_id();
+    const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t s_tmem = tmem_base + lane_addr + t * A3_BN;
+    const uint32_t o_tmem = tmem_base + lane_addr + AT2_TMEM_O + t * AT_D;
+    const float c = p.scale_log2;
+    const uint64_t c2 = pack2(c, c);
+    float m_ref = 0.f, l = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait_trap(&s_full[t], j & 1);
+      tc_fence_after();
+      uint32_t r[128];
+      {
+        uint32_t (&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+        uint32_t (&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
+        uint32_t (&r2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[64]);
+        uint32_t (&r3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[96]);
+        tmem_ld_32x32b_x32(s_tmem, r0);
+        tmem_ld_32x32b_x32(s_tmem + 32, r1);
+        tmem_ld_32x32b_x32(s_tmem + 64, r2);
+        tmem_ld_32x32b_x32(s_tmem + 96, r3);
+        tmem_ld_wait();
+      }
+      const int valid = p.Lk - j * A3_BN;
+      if (valid < A3_BN) {
+#pragma unroll
+        for (int i = 0; i < A3_BN; ++i) if (i >= valid) r[i] = 0xff800000u;   // -inf
+      }
+      // four independent max chains (3-input max), then combine
+      float mx[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        mx[u] = fmax3(__uint_as_float(r[32 * u]), __uint_as_float(r[32 * u + 1]), __uint_as_float(r[32 * u + 2]));
+#pragma unroll
+        for (int i = 3; i < 31; i += 2) mx[u] = fmax3(mx[u], __uint_as_float(r[32 * u + i]), __uint_as_float(r[32 * u + i + 1]));
+        mx[u] = fmaxf(mx[u], __uint_as_float(r[32 * u + 31]));
+      }
+      const float m_blk = fmaxf(fmax3(mx[0], mx[1], mx[2]), mx[3]) * c;
+      float alpha = 1.0f;
+      bool grow = false;
+      if (j == 0) {
+        m_ref = m_blk;
+      } else if (m_blk - m_ref > AT_RESCALE_THRESHOLD) {
+        alpha = ex2(m_ref - m_blk);
+        m_ref = m_blk;
+        grow = true;
+      }
+      if (j > 0 && __any_sync(0xffffffffu, grow)) {
+        // O_t is quiescent: S_t(j) was issued after PV_t(j-1) and the MMA pipe retires in order
+#pragma unroll 1
+        for (int cc = 0; cc < AT_D; cc += 32) {
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(o_tmem + cc, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_32x32b_x32(o_tmem + cc, o);
+        }
+        tmem_st_wait();
+      }
+      const uint64_t nm2 = pack2(-m_ref, -m_ref);
+      uint64_t sum2 = pack2(0.f, 0.f), sum2b = pack2(0.f, 0.f);
+      const bool full_blk = valid >= A3_BN;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int e = 64 * h + 2 * i;
+          const uint64_t x2 = ffma2(pack2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), c2, nm2);
+          float e0, e1;
+          if (((POLY_MASK >> (i & 7)) & 1u) && full_blk) {
+            exp2_poly2(x2, e0, e1);
+          } else {
+            float x0, x1; unpack2(x2, x0, x1);
+            e0 = ex2(x0); e1 = ex2(x1);
+          }
+          if (i & 1) sum2b = fadd2(sum2b, pack2(e0, e1)); else sum2 = fadd2(sum2, pack2(e0, e1));
+          pk[i] = pack_bf16x2(e0, e1);
+        }
+        tmem_st_32x32b_x32(s_tmem + 32 * h, pk);     // P_t: bf16 pairs over the first 64 columns of S_t
+      }
+      float s_lo, s_hi; unpack2(fadd2(sum2, sum2b), s_lo, s_hi);
+      l = l * alpha + (s_lo + s_hi);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&p_full[t]);
+    }
+    mbar_wait_trap(&o_done[t], 0);
     tc_fence_after();
     const int q = q0 + t * AT_BM + row;
     const float inv_l = 1.0f / l;
@@ -589,7 +875,10 @@ extern "C" int wf_attention_bf16(const void* q, int ldq, const void* k, int ldk,
   if (variant == 0) {
     const char* e = getenv("WF_ATTN");
     variant = e ? atoi(e) : 4;
-    if (variant < 1 || variant > 6) variant = 4;
+    if (variant < 1 || variant > 9) variant = 4;
+    WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v3<0x00u>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM)));
+    WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v3<0x88u>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM)));
+    WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v3<0xa4u>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM)));
     WF_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
     WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v2<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)));
     WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v2<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)));
@@ -601,6 +890,16 @@ extern "C" int wf_attention_bf16(const void* q, int ldq, const void* k, int ldk,
                 softmax_scale * 1.4426950408889634f};
   dim3 grid((Lq + 2 * AT_BM - 1) / (2 * AT_BM), heads);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (variant >= 7) {
+    // 7..9: 128-key blocks (v3); K and V boxes are 128 rows.  8: 2 of 8 exponential pairs on the FMA pipe, 9: 3 of 8
+    if ((rc = mk(&tmK, k, ldk, Lk, A3_BN))) return rc;
+    if ((rc = mk(&tmV, v, ldv, Lk, A3_BN))) return rc;
+    if (variant == 7) attention_tcgen05_v3<0x00u><<<grid, AT_THREADS, A3_SMEM, st>>>(tmQ, tmK, tmV, args);
+    else if (variant == 8) attention_tcgen05_v3<0x88u><<<grid, AT_THREADS, A3_SMEM, st>>>(tmQ, tmK, tmV, args);
+    else attention_tcgen05_v3<0xa4u><<<grid, AT_THREADS, A3_SMEM, st>>>(tmQ, tmK, tmV, args);
+    WF_LAUNCH_OK();
+    return WF_OK;
+  }
   if (variant == 1) attention_tcgen05<<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);
   else if (variant == 2) attention_tcgen05_v2<0, false><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);
   else if (variant == 3) attention_tcgen05_v2<1, false><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);

@@ -82,6 +82,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same watchdog without a function call (no printf): kernels that re-partition registers with setmaxnreg cannot
+// contain calls - ptxas then holds the whole kernel to the smallest register count.
+__device__ __forceinline__ void mbar_wait_trap(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint64_t t0 = 0;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3ff) == 0) {
+      uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > WF_WATCHDOG_NS) asm volatile("trap;");
+    }
+  }
+}
+
 // -------------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

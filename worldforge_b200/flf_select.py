@@ -72,8 +72,13 @@ def selection_policy(scores, step: int) -> List[int]:
 
 
 class FlowChannelSelector:
-    def __init__(self, threads: int = 0):
-        self.threads = threads or min(32, os.cpu_count() or 8)
+    """``group``: when the sampler runs one process per GPU, the 16 channels are scored by different ranks (the host
+    cores are shared by all ranks of the box) and the scores are summed into every rank - each rank then takes the
+    same decision from the same 16 numbers."""
+
+    def __init__(self, threads: int = 0, group=None, world: int = 1, rank: int = 0):
+        self.group, self.world, self.rank = group, world, rank
+        self.threads = threads or max(1, min(32, (os.cpu_count() or 8) // max(world, 1)))
         self._pool = None
         self.last_scores = None
 
@@ -94,9 +99,19 @@ class FlowChannelSelector:
     def scores(self, pred_x0: torch.Tensor, fused: torch.Tensor) -> List[float]:
         ref_u8 = lib.quantise_u8(fused.contiguous())
         pred_u8 = lib.quantise_u8(pred_x0.contiguous())
-        both = torch.stack([ref_u8[0], pred_u8[0]]).cpu().numpy()       # one D2H copy, [2,C,T,H,W]
+        nc = ref_u8.shape[1]
+        c0, c1 = (self.rank * nc) // self.world, ((self.rank + 1) * nc) // self.world
+        both = torch.stack([ref_u8[0, c0:c1], pred_u8[0, c0:c1]]).cpu().numpy()       # one D2H copy, [2,C',T,H,W]
         ref_fl, pred_fl = self._flows(both[0]), self._flows(both[1])
-        self.last_scores = [flow_similarity(ref_fl[c], pred_fl[c]) for c in range(ref_fl.shape[0])]
+        mine = [flow_similarity(ref_fl[c], pred_fl[c]) for c in range(ref_fl.shape[0])]
+        if self.world > 1:
+            import torch.distributed as dist
+            t = torch.zeros(nc, dtype=torch.float64)
+            t[c0:c1] = torch.tensor(mine, dtype=torch.float64)
+            t = t.to(pred_x0.device)
+            dist.all_reduce(t, group=self.group)                 # x + 0 is exact: every rank holds the same 16 scores
+            mine = t.cpu().tolist()
+        self.last_scores = mine
         return self.last_scores
 
     def select(self, pred_x0: torch.Tensor, fused: torch.Tensor, step: int) -> List[int]:

@@ -269,7 +269,9 @@ class WfUniPCScheduler:
                 # the selector looks at the normalised fused latents in x0's dtype (:1397)
                 fused_lat = lib.latent_norm_replace(enc, x0, mean_h, inv_std_h, [])
                 if self._selector is None:
-                    self._selector = flf_select.FlowChannelSelector()
+                    sh = getattr(vae, "shard", None)      # one process per GPU: the ranks share the scoring work too
+                    self._selector = flf_select.FlowChannelSelector() if sh is None or sh.world == 1 else \
+                        flf_select.FlowChannelSelector(group=sh.group, world=sh.world, rank=sh.rank)
                 chans = self._selector.select(x0, fused_lat, step)
             self.flf_log.append((step, list(chans)))
         return lib.latent_norm_replace(enc, x0, mean_h, inv_std_h, chans)

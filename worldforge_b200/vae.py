@@ -18,6 +18,14 @@ few dozen full-grid launches:
   low-resolution tensor (one per output parity) with pre-summed weights;
 * pad(0,1,0,1) + stride-2 3x3 conv = a 2x2-tap convolution on the space-to-depth tensor;
 * RMS-norm + SiLU is one fused pass (``wf_rms_norm_cl``).
+
+Multi-GPU (``enable_row_sharding``): the causal feature caches forbid a split along frames, but every layer outside
+the mid block is local in space, so the P ranks of one box split the image ROWS.  Each rank evaluates the sharded
+part of the network on its rows plus the halo its outputs depend on (found by walking the layer plan backwards:
++1 row per 3x3 conv on each side, halved/doubled by the resampling layers) - the halo is recomputed, not exchanged,
+so the convolution kernels are untouched and per-pixel arithmetic is identical to the single-GPU evaluation (the
+stitched result is bit-identical).  The mid block (full-frame attention at 1/8 resolution, ~5 % of the work) is
+replicated.  One all-gather per encode (1/8-resolution features) and per decode (the decoded rows).
 """
 from __future__ import annotations
 
@@ -93,6 +101,11 @@ def _w_s2d(w: torch.Tensor) -> torch.Tensor:
     return out.reshape(4 * co, 4 * ci).contiguous()
 
 
+def assemble_rows(parts: List[torch.Tensor], dim: int) -> torch.Tensor:
+    """Stitch the per-rank row slabs (in rank order) back into one tensor."""
+    return torch.cat(parts, dim=dim)
+
+
 class _Dist:
     def __init__(self, mean):
         self._mean = mean
@@ -117,6 +130,8 @@ class WfWanVAE:
         self.temperal_downsample = list(temporal_downsample)
         self.dim, self.dim_mult, self.num_res_blocks = dim, tuple(dim_mult), num_res_blocks
         self.enc_plan, self.dec_plan = self._plans()
+        self.spatial_scale = 2 ** (len(self.dim_mult) - 1)
+        self.shard = None                  # set by enable_row_sharding
         sd = {k: v.to(device=self.device, dtype=F32) for k, v in state_dict.items()}
         self.w: Dict[str, torch.Tensor] = {}
         self._prepare(sd)
@@ -285,6 +300,105 @@ class WfWanVAE:
                     x = self._conv(y, name + ".2", TAPS_333, cout)
         return x
 
+
+    # ------------------------------------------------------------------------------ row sharding
+    UPS, DOWNS = ("up2d", "up3d"), ("down2d", "down3d")
+
+    def enable_row_sharding(self, group=None, world: int = None, rank: int = None):
+        """Split encode / decode across the ranks of ``group`` by image rows (see the module docstring)."""
+        import torch.distributed as dist
+        self.shard = SimpleNamespace(group=group, world=dist.get_world_size(group) if world is None else world,
+                                     rank=dist.get_rank(group) if rank is None else rank)
+        return self.shard
+
+    @staticmethod
+    def row_bounds(h: int, world: int) -> List[int]:
+        """Latent-resolution row ranges of the ranks: rank r owns [b[r], b[r+1])."""
+        return [(r * h) // world for r in range(world + 1)]
+
+    @classmethod
+    def _needed_rows(cls, seg, out_range: Tuple[int, int], h_in: int):
+        """Walk ``seg`` backwards: need[i] = rows of layer i's INPUT (clamped to the image) that rows ``out_range`` of
+        the segment's output depend on; need[len(seg)] = out_range.  Also returns the image height at every layer."""
+        hs = [h_in]
+        for kind, *_ in seg:
+            hs.append(hs[-1] * 2 if kind in cls.UPS else hs[-1] // 2 if kind in cls.DOWNS else hs[-1])
+        need = [None] * (len(seg) + 1)
+        need[-1] = (max(out_range[0], 0), min(out_range[1], hs[-1]))
+        for i in range(len(seg) - 1, -1, -1):
+            lo, hi = need[i + 1]
+            kind = seg[i][0]
+            if kind in ("conv", "head"):
+                lo, hi = lo - 1, hi + 1                       # one 3x3(x3) convolution
+            elif kind == "res":
+                lo, hi = lo - 2, hi + 2                       # two 3x3x3 convolutions (the shortcut is 1x1)
+            elif kind in cls.UPS:
+                lo, hi = lo // 2 - 1, (hi + 1) // 2 + 1       # out row 2y+p reads rows y-1..y (p=0) / y..y+1 (p=1)
+            elif kind in cls.DOWNS:
+                lo, hi = 2 * lo, 2 * hi + 2                   # out row y reads rows 2y..2y+2 (+ the zero pad row)
+            else:
+                raise ValueError(f"layer kind {kind!r} is not local in space")
+            need[i] = (max(lo, 0), min(hi, hs[i]))
+        return need, hs
+
+    def _run_rows(self, seg, x, a: int, need, final_planar_rows=None):
+        """Run ``seg`` on a row slab: ``x`` [T, rows, W, C] holds image rows a.. of the segment's input.  Before every
+        resampling layer the slab is cut down to the rows still needed.  Returns (output slab, its first image row)."""
+        for i, (kind, name, cin, cout) in enumerate(seg):
+            lo, hi = need[i]
+            if i == 0 or kind in self.UPS or kind in self.DOWNS:
+                if lo > a or hi < a + x.shape[1]:
+                    x = x[:, lo - a:hi - a].contiguous()
+                    a = lo
+            if kind == "head" and final_planar_rows is not None:
+                T, H, Wd, _ = x.shape
+                y = lib.rms_norm_cl(x, self.w[name + ".0.gamma"])
+                out = torch.empty(cout, T, H, Wd, dtype=F32, device=x.device)
+                lib.conv_tf32(y, self.w[name + ".2.w"], self.w[name + ".2.b"], TAPS_333, out, T=T, H=H, W=Wd, Cout=cout,
+                              planar_clamp=True, tile_w=self._tile_w(Wd))
+                lo, hi = final_planar_rows
+                return out[:, :, lo - a:hi - a], lo
+            x = self._run([(kind, name, cin, cout)], x)
+            a = a * 2 if kind in self.UPS else a // 2 if kind in self.DOWNS else a
+        lo, hi = need[-1]
+        return x[:, lo - a:hi - a], lo
+
+    def _split_plans(self):
+        """encoder: (row-sharded layers up to the last downsample, replicated tail); decoder: (replicated layers up to
+        the first upsample, row-sharded rest)."""
+        e = max(i for i, p in enumerate(self.enc_plan) if p[0] in self.DOWNS) + 1
+        d = min(i for i, p in enumerate(self.dec_plan) if p[0] in self.UPS)
+        return (self.enc_plan[:e], self.enc_plan[e:]), (self.dec_plan[:d], self.dec_plan[d:])
+
+    def encode_rows(self, x_planar: torch.Tensor, lo: int, hi: int) -> torch.Tensor:
+        """x_planar [3,F,H,W] -> features [T', hi-lo, W/8, C] of latent rows [lo, hi) after the last downsample."""
+        (seg, _), _ = self._split_plans()
+        need, _ = self._needed_rows(seg, (lo, hi), x_planar.shape[2])
+        a, b = need[0]
+        cl = lib.planar_to_cl(x_planar[:, :, a:b].to(F32).contiguous(), 4)
+        y, _ = self._run_rows(seg, cl, a, need)
+        return y
+
+    def decode_rows(self, x_mid: torch.Tensor, lo: int, hi: int) -> torch.Tensor:
+        """x_mid [T, h, w, C] (output of the replicated decoder head part) -> planar [3, F, hi-lo, W] of the decoded
+        rows [lo, hi) (full resolution)."""
+        _, (_, seg) = self._split_plans()
+        need, _ = self._needed_rows(seg, (lo, hi), x_mid.shape[1])
+        y, _ = self._run_rows(seg, x_mid, 0, need, final_planar_rows=(lo, hi))
+        return y
+
+    def _all_gather_rows(self, local: torch.Tensor, dim: int, bounds: List[int]) -> torch.Tensor:
+        """``local`` holds rows [bounds[r], bounds[r+1]) along ``dim``; returns the tensor with all rows, same on every rank."""
+        import torch.distributed as dist
+        sh = self.shard
+        mx = max(bounds[r + 1] - bounds[r] for r in range(sh.world))
+        shape = list(local.shape); shape[dim] = mx
+        send = torch.zeros(shape, dtype=local.dtype, device=local.device)
+        send.narrow(dim, 0, local.shape[dim]).copy_(local)
+        recv = torch.empty([sh.world] + shape, dtype=local.dtype, device=local.device)
+        dist.all_gather(list(recv.unbind(0)), send, group=sh.group)
+        return assemble_rows([recv[r].narrow(dim, 0, bounds[r + 1] - bounds[r]) for r in range(sh.world)], dim)
+
     # ------------------------------------------------------------------------------ public surface
     @torch.no_grad()
     def encode(self, x: torch.Tensor):
@@ -292,8 +406,13 @@ class WfWanVAE:
         if not x.is_cuda:
             raise lib.WfError("WfWanVAE runs on CUDA tensors only (no CPU fallback)")
         assert x.shape[0] == 1 and x.shape[1] == 3
-        cl = lib.planar_to_cl(x[0].to(F32).contiguous(), 4)
-        h = self._run(self.enc_plan, cl)
+        if self.shard is not None and self.shard.world > 1:
+            b = self.row_bounds(x.shape[3] // self.spatial_scale, self.shard.world)
+            part = self.encode_rows(x[0], b[self.shard.rank], b[self.shard.rank + 1])
+            h = self._run(self._split_plans()[0][1], self._all_gather_rows(part, 1, b))
+        else:
+            cl = lib.planar_to_cl(x[0].to(F32).contiguous(), 4)
+            h = self._run(self.enc_plan, cl)
         h = self._conv(h, "conv1", TAPS_1, 2 * self.z_dim)
         mu = lib.cl_to_planar(h, self.z_dim)
         return SimpleNamespace(latent_dist=_Dist(mu.unsqueeze(0)))
@@ -311,6 +430,12 @@ class WfWanVAE:
         for i, up in enumerate(self.temperal_downsample):
             nt += 1 if up else 0
         F_out = (f - 1) * (2 ** nt) + 1
+        if self.shard is not None and self.shard.world > 1:
+            sc = self.spatial_scale
+            b = [sc * v for v in self.row_bounds(h, self.shard.world)]
+            x = self._run(self._split_plans()[1][0], x)
+            part = self.decode_rows(x, b[self.shard.rank], b[self.shard.rank + 1])
+            return (self._all_gather_rows(part, 2, b).unsqueeze(0),)
         out = torch.empty(3, F_out, 8 * h, 8 * w, dtype=F32, device=z.device)
         self._run(self.dec_plan, x, final_planar=out)
         return (out.unsqueeze(0),)
