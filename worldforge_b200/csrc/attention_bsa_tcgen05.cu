@@ -32,7 +32,7 @@ constexpr int BS_T_BYTES = BS_BN * BS_D * 2;      // 16 KB: one K (or V) step
 constexpr int BS_OFF_K = 2 * BS_Q_BYTES;
 constexpr int BS_OFF_V = BS_OFF_K + BS_STAGES * BS_T_BYTES;
 constexpr int BS_OFF_BAR = BS_OFF_V + BS_STAGES * BS_T_BYTES;
-constexpr int BS_SMEM = BS_OFF_BAR + 256 + 1024;
+constexpr int BS_SMEM = BS_OFF_BAR + 512 + 1024;
 constexpr int BS_THREADS = 384;
 constexpr uint32_t BS_TMEM_O = 256;
 constexpr float BS_RESCALE_THRESHOLD = 8.0f;
@@ -82,8 +82,11 @@ attention_bsa_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* s_full = v_empty + BS_STAGES;    // [tile][buf] -> 4
   uint64_t* p_full = s_full + 4;             // [tile][buf] -> 4 (a tile may signal P(j) and P(j+1) before the issuer looks:
                                              // one barrier per S buffer, or the phase parity would wrap)
-  uint64_t* o_done = p_full + 4;             // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* o_done = p_full + 4;             // 2: one completion per PV product; a waiter may be at most ONE phase behind
+  uint64_t* o_final = o_done + 2;            // 2: completes once, after the tile's last PV product (the epilogue's wait: after
+                                             // the last softmax step only PV(nsteps-3) is known complete, and a parity wait two
+                                             // phases behind is satisfied by the wrong completion - with 4-6 steps that is most of O)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 2);
 
   const int warp = threadIdx.x >> 5;
   const int head = blockIdx.y;
@@ -115,7 +118,7 @@ attention_bsa_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
     for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1);
     for (int i = 0; i < 4; ++i) mbar_init(&p_full[i], 4);
-    for (int t = 0; t < 2; ++t) mbar_init(&o_done[t], 1);
+    for (int t = 0; t < 2; ++t) { mbar_init(&o_done[t], 1); mbar_init(&o_final[t], 1); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -227,7 +230,7 @@ attention_bsa_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         mbar_wait(&v_full[seq % BS_STAGES], (seq / BS_STAGES) & 1);
         mbar_wait(&p_full[2 * t + (j & 1)], (j >> 1) & 1);
         tc_fence_after();
-        if (elect_one()) issue_pv(t, j);
+        if (elect_one()) { issue_pv(t, j); if (j + 1 == nsteps) umma_commit(&o_final[t]); }
         __syncwarp();
       }
     }
@@ -330,7 +333,7 @@ attention_bsa_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       if (lane_id() == 0) mbar_arrive(&p_full[2 * t + buf]);
     }
     if (nsteps > 0) {
-      mbar_wait(&o_done[t], (nsteps - 1) & 1);
+      mbar_wait(&o_final[t], 0);
       tc_fence_after();
     }
     // this row's token: chunk c, position i inside the chunk in (t,h,w) order

@@ -328,8 +328,11 @@ attention_tcgen05_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                                              // PV(j), so a tile can signal P(j) and P(j+1) before the issuer looks - one
                                              // barrier per S buffer keeps the two completions apart (a single barrier
                                              // would wrap its phase parity and the issuer would wait forever)
-  uint64_t* o_done = p_full + 4;             // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* o_done = p_full + 4;             // 2: one completion per PV product; a waiter may be at most ONE phase behind
+  uint64_t* o_final = o_done + 2;            // 2: completes once, after the last PV product of the tile.  The epilogue cannot
+                                             // use o_done: after its last softmax step only PV(nblk-3) is known complete, and a
+                                             // parity wait two phases behind is satisfied by the wrong completion
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 2);
 
   const int warp = threadIdx.x >> 5;
   const int head = blockIdx.y;
@@ -343,7 +346,7 @@ attention_tcgen05_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     for (int s = 0; s < AT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1);
     for (int i = 0; i < 4; ++i) mbar_init(&p_full[i], 4);
-    for (int t = 0; t < 2; ++t) mbar_init(&o_done[t], 1);
+    for (int t = 0; t < 2; ++t) { mbar_init(&o_done[t], 1); mbar_init(&o_final[t], 1); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -420,11 +423,11 @@ attention_tcgen05_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
       mbar_wait(&p_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      if (elect_one()) issue_pv(0, stage, j);
+      if (elect_one()) { issue_pv(0, stage, j); if (j + 1 == nblk) umma_commit(&o_final[0]); }
       __syncwarp();
       mbar_wait(&p_full[2 + (j & 1)], (j >> 1) & 1);
       tc_fence_after();
-      if (elect_one()) { issue_pv(1, stage, j); umma_commit(&kv_empty[stage]); }
+      if (elect_one()) { issue_pv(1, stage, j); umma_commit(&kv_empty[stage]); if (j + 1 == nblk) umma_commit(&o_final[1]); }
       __syncwarp();
     }
   } else if (warp >= 4) {
@@ -520,7 +523,7 @@ attention_tcgen05_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       __syncwarp();
       if (lane_id() == 0) mbar_arrive(&p_full[2 * t + buf]);
     }
-    mbar_wait(&o_done[t], (nblk - 1) & 1);
+    mbar_wait(&o_final[t], 0);
     tc_fence_after();
     const int q = q0 + t * AT_BM + row;
     const float inv_l = 1.0f / l;
