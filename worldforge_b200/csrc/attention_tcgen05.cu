@@ -24,6 +24,8 @@
 // than 2^8 (lazy rescaling), so the common path never touches O.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "attn_math.cuh"
 #include "host_util.h"
@@ -440,7 +442,10 @@ attention_tcgen05_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const float c = p.scale_log2;
     const uint64_t c2 = pack2(c, c);
     float m_ref = 0.f, l = 0.f;
-    for (int j = 0; j < nblk; ++j) {
+    // MASKED = the last, partial key block.  Two instantiations behind a warp-uniform branch: as a predicate inside one
+    // body the mask costs an ISETP + SEL per score in EVERY block
+    auto softmax_block = [&](int j, auto masked_tag) {
+      constexpr bool MASKED = decltype(masked_tag)::value;
       const int buf = j & 1;
       mbar_wait(&s_full[2 * t + buf], (j >> 1) & 1);
       tc_fence_after();
@@ -453,8 +458,8 @@ attention_tcgen05_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tmem_ld_32x32b_x32(s_tmem + 32, r1);
         tmem_ld_wait();
       }
-      const int valid = p.Lk - j * AT_BN;
-      if (valid < AT_BN) {
+      if (MASKED) {
+        const int valid = p.Lk - j * AT_BN;
 #pragma unroll
         for (int i = 0; i < 64; ++i) if (i >= valid) r[i] = 0xff800000u;   // -inf
       }
@@ -479,7 +484,7 @@ attention_tcgen05_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       for (int i = 0; i < 32; ++i) {
         const uint64_t x2 = ffma2(pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), c2, nm2);
         float e0, e1;
-        if (((POLY == 1 && (i & 3) == 3) || (POLY == 2 && (i & 1))) && valid >= AT_BN) {
+        if (((POLY == 1 && (i & 3) == 3) || (POLY == 2 && (i & 1))) && !MASKED) {
           exp2_poly2(x2, e0, e1);
         } else {
           float x0, x1; unpack2(x2, x0, x1);
@@ -522,7 +527,11 @@ attention_tcgen05_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane_id() == 0) mbar_arrive(&p_full[2 * t + buf]);
-    }
+    };
+    const int nfull = p.Lk / AT_BN;
+#pragma unroll 1
+    for (int j = 0; j < nfull; ++j) softmax_block(j, std::false_type{});
+    if (nfull < nblk) softmax_block(nfull, std::true_type{});
     mbar_wait(&o_final[t], 0);
     tc_fence_after();
     const int q = q0 + t * AT_BM + row;
@@ -724,7 +733,10 @@ attention_tcgen05_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const float c = p.scale_log2;
     const uint64_t c2 = pack2(c, c);
     float m_ref = 0.f, l = 0.f;
-    for (int j = 0; j < nblk; ++j) {
+    // one key block; MASKED = the last, partial block (scores of keys >= Lk become -inf).  Two instantiations behind a
+    // warp-uniform branch: as a predicate inside one body the mask costs an ISETP + SEL per score in EVERY block
+    auto softmax_block = [&](int j, auto masked_tag) {
+      constexpr bool MASKED = decltype(masked_tag)::value;
       mbar_wait_trap(&s_full[t], j & 1);
       tc_fence_after();
       uint32_t r[128];
@@ -739,8 +751,8 @@ attention_tcgen05_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tmem_ld_32x32b_x32(s_tmem + 96, r3);
         tmem_ld_wait();
       }
-      const int valid = p.Lk - j * A3_BN;
-      if (valid < A3_BN) {
+      if (MASKED) {
+        const int valid = p.Lk - j * A3_BN;
 #pragma unroll
         for (int i = 0; i < A3_BN; ++i) if (i >= valid) r[i] = 0xff800000u;   // -inf
       }
@@ -778,7 +790,6 @@ attention_tcgen05_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
       const uint64_t nm2 = pack2(-m_ref, -m_ref);
       uint64_t sum2 = pack2(0.f, 0.f), sum2b = pack2(0.f, 0.f);
-      const bool full_blk = valid >= A3_BN;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t pk[32];
@@ -787,7 +798,7 @@ attention_tcgen05_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const int e = 64 * h + 2 * i;
           const uint64_t x2 = ffma2(pack2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), c2, nm2);
           float e0, e1;
-          if (((POLY_MASK >> (i & 7)) & 1u) && full_blk) {
+          if (((POLY_MASK >> (i & 7)) & 1u) && !MASKED) {
             exp2_poly2(x2, e0, e1);
           } else {
             float x0, x1; unpack2(x2, x0, x1);
@@ -804,7 +815,11 @@ attention_tcgen05_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane_id() == 0) mbar_arrive(&p_full[t]);
-    }
+    };
+    const int nfull = p.Lk / A3_BN;               // blocks whose 128 keys all exist
+#pragma unroll 1
+    for (int j = 0; j < nfull; ++j) softmax_block(j, std::false_type{});
+    if (nfull < nblk) softmax_block(nfull, std::true_type{});
     mbar_wait_trap(&o_done[t], 0);
     tc_fence_after();
     const int q = q0 + t * AT_BM + row;
