@@ -612,8 +612,9 @@ attention_tcgen05_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* ring_full = bars + 1;                // A3_SLOTS
   uint64_t* ring_empty = ring_full + A3_SLOTS;   // A3_SLOTS
   uint64_t* s_full = ring_empty + A3_SLOTS;      // 2
-  uint64_t* p_full = s_full + 2;                 // 2
-  uint64_t* o_done = p_full + 2;                 // 2 (final PV of each tile)
+  uint64_t* p_full = s_full + 2;                 // [tile][half] -> 4: P is handed over in two 64-key halves so that the first
+                                                 // half of the PV product runs while the second half is still being exponentiated
+  uint64_t* o_done = p_full + 4;                 // 2 (final PV of each tile)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -626,7 +627,8 @@ attention_tcgen05_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (warp == 1 && elect_one()) {
     mbar_init(q_full, 1);
     for (int s = 0; s < A3_SLOTS; ++s) { mbar_init(&ring_full[s], 1); mbar_init(&ring_empty[s], 1); }
-    for (int t = 0; t < 2; ++t) { mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 4); mbar_init(&o_done[t], 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(&s_full[t], 1); mbar_init(&o_done[t], 1); }
+    for (int i = 0; i < 4; ++i) mbar_init(&p_full[i], 4);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -675,10 +677,10 @@ attention_tcgen05_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
         umma_commit(&s_full[t]);
       };
-      auto issue_pv = [&](int t, int slot, int j) {
+      auto issue_pv = [&](int t, int slot, int j, int half) {
         const uint32_t v_addr = ring_addr + slot * A3_SLOT_BYTES;
 #pragma unroll
-        for (int ks = 0; ks < A3_BN / 16; ++ks) {
+        for (int ks = 4 * half; ks < 4 * half + 4; ++ks) {
           uint64_t db = umma_desc_sw128(v_addr + ks * 2048, A3_SLOT_BYTES / 2, 1024);
           umma_f16_ts(tmem_base + AT2_TMEM_O + t * AT_D, tmem_base + t * A3_BN + ks * 8, db, idesc_o, (j | ks) != 0);
         }
@@ -700,7 +702,11 @@ attention_tcgen05_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_wait_trap(&ring_full[v_slot], v_phase);                 // V_j
         mbar_wait_trap(&p_full[0], j & 1);
         tc_fence_after();
-        if (elect_one()) issue_pv(0, v_slot, j);
+        if (elect_one()) issue_pv(0, v_slot, j, 0);
+        __syncwarp();
+        mbar_wait_trap(&p_full[1], j & 1);
+        tc_fence_after();
+        if (elect_one()) issue_pv(0, v_slot, j, 1);
         __syncwarp();
         if (more) {
           mbar_wait_trap(&ring_full[k_slot], k_phase);               // K_{j+1}
@@ -710,10 +716,14 @@ attention_tcgen05_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         } else if (elect_one()) {
           umma_commit(&o_done[0]);
         }
-        mbar_wait_trap(&p_full[1], j & 1);
+        mbar_wait_trap(&p_full[2], j & 1);
+        tc_fence_after();
+        if (elect_one()) issue_pv(1, v_slot, j, 0);
+        __syncwarp();
+        mbar_wait_trap(&p_full[3], j & 1);
         tc_fence_after();
         if (elect_one()) {
-          issue_pv(1, v_slot, j);
+          issue_pv(1, v_slot, j, 1);
           umma_commit(&ring_empty[v_slot]);
           if (more) { issue_s(1, k_slot); umma_commit(&ring_empty[k_slot]); }
           else umma_commit(&o_done[1]);
@@ -808,13 +818,13 @@ attention_tcgen05_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           pk[i] = pack_bf16x2(e0, e1);
         }
         tmem_st_32x32b_x32(s_tmem + 32 * h, pk);     // P_t: bf16 pairs over the first 64 columns of S_t
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(&p_full[2 * t + h]);
       }
       float s_lo, s_hi; unpack2(fadd2(sum2, sum2b), s_lo, s_hi);
       l = l * alpha + (s_lo + s_hi);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane_id() == 0) mbar_arrive(&p_full[t]);
     };
     const int nfull = p.Lk / A3_BN;               // blocks whose 128 keys all exist
 #pragma unroll 1
@@ -887,13 +897,16 @@ extern "C" int wf_attention_bf16(const void* q, int ldq, const void* k, int ldk,
   if ((rc = mk(&tmK, k, ldk, Lk, AT_BN))) return rc;
   if ((rc = mk(&tmV, v, ldv, Lk, AT_BN))) return rc;
   // WF_ATTN=1: v1 (single S buffer, P through smem); 2: v2 (double-buffered S, packed fp32x2 softmax, P through smem);
-  // 3: v2 + polynomial ex2 offload (measured slower on B200: the extra FMA-pipe instructions cost more issue slots than
-  // the MUFU time they free); 4 (default): v2 with P kept in TMEM as the A operand of the PV product
+  // 3: v2 + polynomial ex2 offload; 4: v2 with P kept in TMEM as the A operand of the PV product; 5/6: 4 + polynomial ex2;
+  // 7/8/9: v3 (128-key blocks, P handed over in halves) with 0 / 2 / 3 of every 8 exponential pairs on the FMA pipe.
+  // Default 9: 26.0 M SM cycles per launch at the 480p shape against 31.9 M for variant 4 (tensor pipe 71 % vs 58 % active).
   static int variant = 0;
+  static bool forced = false;        // WF_ATTN set: every call runs that variant (development / A-B measurements)
   if (variant == 0) {
     const char* e = getenv("WF_ATTN");
-    variant = e ? atoi(e) : 4;
-    if (variant < 1 || variant > 9) variant = 4;
+    forced = e != nullptr;
+    variant = e ? atoi(e) : 9;
+    if (variant < 1 || variant > 9) variant = 9;
     WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v3<0x00u>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM)));
     WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v3<0x88u>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM)));
     WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v3<0xa4u>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM)));
@@ -908,6 +921,14 @@ extern "C" int wf_attention_bf16(const void* q, int ldq, const void* k, int ldk,
                 softmax_scale * 1.4426950408889634f};
   dim3 grid((Lq + 2 * AT_BM - 1) / (2 * AT_BM), heads);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // short key sequences whose tail would leave a 128-key block nearly empty (the 257 image tokens of the cross-attention)
+  // run the 64-key kernel
+  const bool short_tail = Lk < 2048 && (Lk % A3_BN) != 0 && (Lk % A3_BN) <= AT_BN;
+  if (variant >= 7 && short_tail && !forced) {
+    attention_tcgen05_v2<0, true><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);
+    WF_LAUNCH_OK();
+    return WF_OK;
+  }
   if (variant >= 7) {
     // 7..9: 128-key blocks (v3); K and V boxes are 128 rows.  8: 2 of 8 exponential pairs on the FMA pipe, 9: 3 of 8
     if ((rc = mk(&tmK, k, ldk, Lk, A3_BN))) return rc;
