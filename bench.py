@@ -30,6 +30,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's own log (the box exports NCCL_DEBUG, whose "NCCL version ..." banner goes to
+# stdout by default) is sent to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "denoising_steps_per_sec_wan2.1_i2v_14b_480p_81f_irr_flf_dsg"
 UNIT = "steps/s"
@@ -177,7 +180,9 @@ def run_ours(args):
     tr = wtr.WfWanTransformer.random_init(cfg, dev, seed=1234)
     if world > 1:
         from worldforge_b200 import ulysses
-        ulysses.enable(tr, dist.group.WORLD)
+        # WF_ULYSSES=nccl: the all-to-all form (A/B measurements); default: q|k|v and attention output stored straight into the
+        # peers' memory over NVLink by the producing kernels
+        ulysses.enable(tr, dist.group.WORLD, peer=os.environ.get("WF_ULYSSES", "peer") != "nccl")
     vae = wvae.WfWanVAE.random_init(dev, seed=4321)
     if world > 1:
         vae.enable_row_sharding(dist.group.WORLD)      # encode / decode split by image rows; FLF scoring by channels
@@ -280,7 +285,7 @@ def run_ours(args):
         "config": {"workload": f"Wan2.1-I2V-14B {args.height}x{args.width} {args.frames}f guided sampling (IRR+FLF+DSG), "
                                f"{k_guided} guided + {K - k_guided} plain timed steps (the 15:35 mix of the 50-step run)",
                    "tokens": L, "dit_layers": args.layers, "dit_forwards_timed": fwd - 4 * W,
-                   "vae": "fp32 storage, tf32 tensor-core convs", "parallelism": "single GPU" if world == 1 else f"ulysses{world} (DiT tokens) + vae-rows{world} + flf-channels{world}",
+                   "vae": "fp32 storage, tf32 tensor-core convs", "parallelism": "single GPU" if world == 1 else f"ulysses{world} (DiT tokens, {os.environ.get('WF_ULYSSES', 'peer')} exchange) + vae-rows{world} + flf-channels{world}",
                    "l2_policy": "inputs larger than L2 (33 GB of weights, 0.67 GB activations streamed per GEMM)"},
         "clocks": clk, "gpu_launches": launches, "e2e": e2e, "roofline": roof,
         "dit_forwards_per_sec": (fwd - 4 * W) / (ms / 1000.0),

@@ -90,6 +90,29 @@ int wf_layer_norm(const void* x, int ldx, int x_is_bf16, void* out, int ldo, int
                   const float* shift, const float* weight, const float* bias, int rows, int D, float eps,
                   int round_norm_bf16, int rows_per_group, void* stream);   /* rows_per_group > 0: scale/shift are [groups, D] */
 
+/* ---- one process per GPU: heads <-> tokens exchange of Ulysses attention through NVLink peer memory ------------------
+ * (reference pattern: longcat_video/context_parallel/ulysses_wrapper.py:87-105 = four NCCL all-to-alls + staging copies
+ * per attention; wan/distributed/xdit_context_parallel.py:160-176 for the token split.)  Here the kernels that PRODUCE
+ * the data store it straight into the consuming rank's buffer: wf_qkv_norm_rope_scatter (RMSNorm + RoPE of q and k, and
+ * v) writes [all tokens, this peer's heads], wf_attention_bf16_peers writes each output row to the rank that owns the
+ * token.  Buffers come from wf_peer_alloc (cudaMalloc + CUDA IPC handle); peers map them with wf_peer_open.  The caller
+ * orders producers and consumers with a barrier across the ranks (any stream-ordered collective). */
+int wf_peer_alloc(long long bytes, void** ptr, void* handle64);       /* handle64: 64 bytes to send to the peers */
+int wf_peer_open(const void* handle64, void** ptr);
+int wf_peer_close(void* ptr);
+int wf_peer_free(void* ptr);
+/* qkv: bf16 [rows, 3*D] (q|k|v of this rank's tokens, all heads).  For which in {q,k}: WanRMSNorm over D with weight_q /
+ * weight_k, then RoPE (same arithmetic as wf_rms_norm_rope); v is copied.  Head h of row r goes to peer h / (heads/n_peers):
+ * dst_peers[peer][(row0 + r) * ld_dst + (which*(heads/n_peers) + h % (heads/n_peers))*128 ...]. */
+int wf_qkv_norm_rope_scatter(const void* qkv, int ldx, const float* weight_q, const float* weight_k, const double* rope,
+                             int rows, int D, float eps, void* const* dst_peers, int n_peers, int ld_dst, int row0,
+                             void* stream);
+/* wf_attention_bf16 whose output row q goes to out_peers[q / rows_per_peer] + (q % rows_per_peer)*ldo + head*128
+ * (each pointer already includes the column offset of this rank's head block). */
+int wf_attention_bf16_peers(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* const* out_peers,
+                            int n_peers, int rows_per_peer, int ldo, int Lq, int Lk, int heads, float softmax_scale,
+                            void* stream);
+
 /* WanRMSNorm over the full model dim (model.py:81-89) followed by rope_apply (:43-70), in place on a
  * bf16 [rows, D] slice (leading dimension ldx).  rope: fp64 [rows, 64, 2] (cos, sin) per token and
  * complex pair, or NULL for the cross-attention q/k, which carry no RoPE. */

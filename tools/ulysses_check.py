@@ -24,6 +24,15 @@ torch.cuda.synchronize()
 same = torch.equal(single, par)
 md = (single.float() - par.float()).abs().max().item()
 print(f"rank {rank}/{world}: sequence-parallel forward equal to single-GPU: {same} (max diff {md}), a2a calls {sp.a2a_calls}", flush=True)
+sp.peer = True                                   # the same exchange through NVLink peer memory (no collective on the data path)
+par2 = m(x, t, ctx, clip)[0]
+par3 = m(x, t, ctx, clip)[0]                     # second forward: buffers and layer parity are reused
+torch.cuda.synchronize()
+psp = next(iter(m._psp.values()))
+peer_ok = torch.equal(single, par2) and torch.equal(single, par3)
+print(f"rank {rank}/{world}: peer-memory forward equal to single-GPU: {peer_ok} (max diff {(single.float() - par2.float()).abs().max().item()}), "
+      f"barriers {psp.barriers}, a2a calls still {sp.a2a_calls}", flush=True)
+md = max(md, 0.0 if peer_ok else 1.0)
 from worldforge_b200 import flf_select, vae as wvae
 v = wvae.WfWanVAE.random_init(dev, dim=16, seed=3)
 video = (torch.rand(1, 3, 9, 128, 96, generator=g) * 2 - 1).to(dev)

@@ -45,9 +45,13 @@ constexpr int AT_THREADS = 384;
 constexpr uint32_t AT_TMEM_S = 0, AT_TMEM_O = 128;
 constexpr float AT_RESCALE_THRESHOLD = 8.0f;
 
+constexpr int AT_MAX_PEERS = 8;
+
 struct AttnArgs {
   int Lq, Lk;
   bf16* out; int ldo;
+  // one process per GPU: query row q is stored to out_peer[q / rows_per_peer] + (q % rows_per_peer) * ldo (n_peers > 0)
+  bf16* out_peer[AT_MAX_PEERS]; int n_peers; int rows_per_peer;
   const bf16* add_in; int ld_add;
   float scale_log2;     // softmax scale * log2(e)
 };
@@ -542,7 +546,8 @@ attention_tcgen05_v2(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tmem_ld_32x32b_x32(o_tmem + cc, o);
       tmem_ld_wait();
       if (q < p.Lq) {
-        bf16* dst = p.out + static_cast<size_t>(q) * p.ldo + col0 + cc;
+        bf16* dst = (p.n_peers > 0 ? p.out_peer[q / p.rows_per_peer] + static_cast<size_t>(q % p.rows_per_peer) * p.ldo
+                                   : p.out + static_cast<size_t>(q) * p.ldo) + col0 + cc;
         const bf16* add = p.add_in ? p.add_in + static_cast<size_t>(q) * p.ld_add + col0 + cc : nullptr;
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
@@ -840,7 +845,8 @@ attention_tcgen05_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tmem_ld_32x32b_x32(o_tmem + cc, o);
       tmem_ld_wait();
       if (q < p.Lq) {
-        bf16* dst = p.out + static_cast<size_t>(q) * p.ldo + col0 + cc;
+        bf16* dst = (p.n_peers > 0 ? p.out_peer[q / p.rows_per_peer] + static_cast<size_t>(q % p.rows_per_peer) * p.ldo
+                                   : p.out + static_cast<size_t>(q) * p.ldo) + col0 + cc;
         const bf16* add = p.add_in ? p.add_in + static_cast<size_t>(q) * p.ld_add + col0 + cc : nullptr;
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
@@ -875,11 +881,12 @@ attention_tcgen05_v3(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
 }  // namespace wf
 
-extern "C" int wf_attention_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out,
-                                 int ldo, const void* add_in, int ld_add, int Lq, int Lk, int heads,
-                                 float softmax_scale, void* stream) {
+static int attention_launch(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
+                            const void* add_in, int ld_add, int Lq, int Lk, int heads, float softmax_scale,
+                            void* const* out_peers, int n_peers, int rows_per_peer, void* stream) {
   using namespace wf;
-  WF_REQUIRE(q && k && v && out, "wf_attention_bf16: null pointer");
+  WF_REQUIRE(q && k && v && (out || n_peers > 0), "wf_attention_bf16: null pointer");
+  WF_REQUIRE(n_peers >= 0 && n_peers <= AT_MAX_PEERS, "wf_attention_bf16_peers: at most 8 peers");
   WF_REQUIRE(Lq > 0 && Lk > 0 && heads > 0, "wf_attention_bf16: empty problem");
   WF_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && ld_add % 8 == 0,
              "wf_attention_bf16: leading dimensions must be multiples of 8");
@@ -917,8 +924,11 @@ extern "C" int wf_attention_bf16(const void* q, int ldq, const void* k, int ldk,
     WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v2<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)));
     WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v2<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)));
   }
-  AttnArgs args{Lq, Lk, static_cast<bf16*>(out), ldo, static_cast<const bf16*>(add_in), ld_add,
-                softmax_scale * 1.4426950408889634f};
+  AttnArgs args{};
+  args.Lq = Lq; args.Lk = Lk; args.out = static_cast<bf16*>(out); args.ldo = ldo;
+  args.add_in = static_cast<const bf16*>(add_in); args.ld_add = ld_add; args.scale_log2 = softmax_scale * 1.4426950408889634f;
+  args.n_peers = n_peers; args.rows_per_peer = rows_per_peer > 0 ? rows_per_peer : 1;
+  for (int i = 0; i < n_peers; ++i) args.out_peer[i] = static_cast<bf16*>(out_peers[i]);
   dim3 grid((Lq + 2 * AT_BM - 1) / (2 * AT_BM), heads);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // short key sequences whose tail would leave a 128-key block nearly empty (the 257 image tokens of the cross-attention)
@@ -939,6 +949,7 @@ extern "C" int wf_attention_bf16(const void* q, int ldq, const void* k, int ldk,
     WF_LAUNCH_OK();
     return WF_OK;
   }
+  WF_REQUIRE(!(variant == 1 && n_peers > 0), "wf_attention_bf16_peers: variant 1 has no peer epilogue");
   if (variant == 1) attention_tcgen05<<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);
   else if (variant == 2) attention_tcgen05_v2<0, false><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);
   else if (variant == 3) attention_tcgen05_v2<1, false><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);
@@ -947,4 +958,20 @@ extern "C" int wf_attention_bf16(const void* q, int ldq, const void* k, int ldk,
   else attention_tcgen05_v2<0, true><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);   // 4: P through TMEM
   WF_LAUNCH_OK();
   return WF_OK;
+}
+
+extern "C" int wf_attention_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out,
+                                 int ldo, const void* add_in, int ld_add, int Lq, int Lk, int heads,
+                                 float softmax_scale, void* stream) {
+  return attention_launch(q, ldq, k, ldk, v, ldv, out, ldo, add_in, ld_add, Lq, Lk, heads, softmax_scale, nullptr, 0, 0, stream);
+}
+
+extern "C" int wf_attention_bf16_peers(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv,
+                                       void* const* out_peers, int n_peers, int rows_per_peer, int ldo, int Lq, int Lk,
+                                       int heads, float softmax_scale, void* stream) {
+  WF_REQUIRE(out_peers && n_peers >= 1 && rows_per_peer > 0, "wf_attention_bf16_peers: bad peer table");
+  WF_REQUIRE(static_cast<long long>(n_peers) * rows_per_peer >= Lq, "wf_attention_bf16_peers: the peers do not cover every query row");
+  for (int i = 0; i < n_peers; ++i) WF_REQUIRE(out_peers[i] != nullptr, "wf_attention_bf16_peers: null peer pointer");
+  return attention_launch(q, ldq, k, ldk, v, ldv, nullptr, ldo, nullptr, 0, Lq, Lk, heads, softmax_scale, out_peers, n_peers,
+                          rows_per_peer, stream);
 }

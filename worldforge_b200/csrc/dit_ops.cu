@@ -170,6 +170,74 @@ __global__ void __launch_bounds__(RMS_THREADS) rms_norm_rope_kernel(RmsArgs p) {
   }
 }
 
+// ---------------------------------------------------------- q|k|v: RMSNorm + RoPE + scatter to the peers (Ulysses)
+// Same per-element arithmetic as rms_norm_rope_kernel (the results are bit-identical); instead of writing in place the
+// 8-element vectors go to the rank that owns their head: blockIdx.y = 0 (q), 1 (k), 2 (v, copied).
+constexpr int QS_MAX_PEERS = 8;
+
+struct QkvScatterArgs {
+  const bf16* qkv; int ldx;
+  const float* weight_q; const float* weight_k;
+  const double* rope;
+  int D; float eps;
+  bf16* dst[QS_MAX_PEERS]; int n_peers; int ld_dst; int row0;
+};
+
+__global__ void __launch_bounds__(RMS_THREADS) qkv_norm_rope_scatter_kernel(QkvScatterArgs p) {
+  __shared__ float red[32];
+  const int row = blockIdx.x, which = blockIdx.y;
+  const int nvec = p.D >> 3;
+  const bf16* xr = p.qkv + static_cast<size_t>(row) * p.ldx + static_cast<size_t>(which) * p.D;
+  const float* weight = which == 0 ? p.weight_q : p.weight_k;
+  const int hpp = (p.D >> 7) / p.n_peers;                        // heads per peer
+  uint4 raw[RMS_MAXV];
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < RMS_MAXV; ++i) {
+    const int idx = threadIdx.x + i * RMS_THREADS;
+    if (idx < nvec) {
+      raw[i] = *reinterpret_cast<const uint4*>(xr + idx * 8);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float2 f = __bfloat1622float2(h[u]);
+        sq += f.x * f.x + f.y * f.y;
+      }
+    }
+  }
+  float rstd = 0.f;
+  if (which < 2) rstd = rsqrtf(block_sum<RMS_THREADS>(sq, red) / p.D + p.eps);
+#pragma unroll
+  for (int i = 0; i < RMS_MAXV; ++i) {
+    const int idx = threadIdx.x + i * RMS_THREADS;
+    if (idx < nvec) {
+      const int c = idx * 8;
+      uint4 outv = raw[i];
+      if (which < 2) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
+        uint32_t o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float2 f = __bfloat1622float2(h[u]);
+          float a = __fmul_rn(bf16_round(__fmul_rn(f.x, rstd)), weight[c + 2 * u]);
+          float b = __fmul_rn(bf16_round(__fmul_rn(f.y, rstd)), weight[c + 2 * u + 1]);
+          const int pair = ((c + 2 * u) & 127) >> 1;
+          const double2 cs = *reinterpret_cast<const double2*>(p.rope + (static_cast<size_t>(row) * 64 + pair) * 2);
+          const double da = a, db = b;
+          const float re = static_cast<float>(da * cs.x - db * cs.y);
+          const float im = static_cast<float>(da * cs.y + db * cs.x);
+          o[u] = pack_bf16x2(re, im);
+        }
+        outv = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+      const int head = c >> 7;
+      const int peer = head / hpp;
+      bf16* d = p.dst[peer] + static_cast<size_t>(p.row0 + row) * p.ld_dst + (which * hpp + head % hpp) * 128 + (c & 127);
+      *reinterpret_cast<uint4*>(d) = outv;
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------- patchify
 // hidden [C, F, H, W] bf16 -> rows [F*(H/2)*(W/2), C*4] bf16, column = c*4 + ph*2 + pw
 __global__ void patchify_kernel(const bf16* __restrict__ x, bf16* __restrict__ cols, int C, int F, int H, int W) {
@@ -448,6 +516,26 @@ extern "C" int wf_rms_norm_rope(void* x, int ldx, const float* weight, const dou
   WF_REQUIRE(rope == nullptr || D % 128 == 0, "wf_rms_norm_rope: RoPE needs head_dim 128");
   RmsArgs a{static_cast<bf16*>(x), ldx, weight, rope, D, eps};
   rms_norm_rope_kernel<<<rows, RMS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  WF_LAUNCH_OK();
+  return WF_OK;
+}
+
+extern "C" int wf_qkv_norm_rope_scatter(const void* qkv, int ldx, const float* weight_q, const float* weight_k,
+                                        const double* rope, int rows, int D, float eps, void* const* dst_peers, int n_peers,
+                                        int ld_dst, int row0, void* stream) {
+  WF_REQUIRE(qkv && weight_q && weight_k && rope && dst_peers && rows > 0, "wf_qkv_norm_rope_scatter: bad arguments");
+  WF_REQUIRE(D % 128 == 0 && D <= 8 * RMS_THREADS * RMS_MAXV && ldx % 8 == 0 && ldx >= 3 * D,
+             "wf_qkv_norm_rope_scatter: dim must be a multiple of 128 and <= 8192, qkv rows 3*D wide");
+  WF_REQUIRE(n_peers >= 1 && n_peers <= QS_MAX_PEERS && (D / 128) % n_peers == 0, "wf_qkv_norm_rope_scatter: heads must split over the peers");
+  WF_REQUIRE(ld_dst % 8 == 0 && ld_dst >= 3 * D / n_peers && row0 >= 0, "wf_qkv_norm_rope_scatter: bad destination layout");
+  QkvScatterArgs a{};
+  a.qkv = static_cast<const bf16*>(qkv); a.ldx = ldx; a.weight_q = weight_q; a.weight_k = weight_k; a.rope = rope;
+  a.D = D; a.eps = eps; a.n_peers = n_peers; a.ld_dst = ld_dst; a.row0 = row0;
+  for (int i = 0; i < n_peers; ++i) {
+    WF_REQUIRE(dst_peers[i] != nullptr, "wf_qkv_norm_rope_scatter: null peer pointer");
+    a.dst[i] = static_cast<bf16*>(dst_peers[i]);
+  }
+  qkv_norm_rope_scatter_kernel<<<dim3(rows, 3), RMS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a);
   WF_LAUNCH_OK();
   return WF_OK;
 }

@@ -1,6 +1,8 @@
 // worldforge_b200 - C-ABI plumbing: error reporting, device queries, TMA descriptor encoding.
 #include <cudaTypedefs.h>
 
+#include <string.h>
+
 #include <mutex>
 #include <string>
 
@@ -65,3 +67,35 @@ int make_tmap(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, int
 extern "C" const char* wf_last_error(void) { return wf::g_last_error.c_str(); }
 extern "C" int wf_abi_version(void) { return WF_ABI_VERSION; }
 extern "C" int wf_sm_count(void) { return wf::sm_count(); }
+
+// ---- peer memory (one process per GPU on one box): cudaMalloc + CUDA IPC ---------------------------------------------
+extern "C" int wf_peer_alloc(long long bytes, void** ptr, void* handle64) {
+  WF_REQUIRE(bytes > 0 && ptr && handle64, "wf_peer_alloc: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  WF_CUDA_OK(cudaMalloc(&p, static_cast<size_t>(bytes)));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return wf::fail(WF_ECUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+  }
+  memcpy(handle64, &h, 64);
+  *ptr = p;
+  return WF_OK;
+}
+extern "C" int wf_peer_open(const void* handle64, void** ptr) {
+  WF_REQUIRE(handle64 && ptr, "wf_peer_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  WF_CUDA_OK(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return WF_OK;
+}
+extern "C" int wf_peer_close(void* ptr) {
+  WF_CUDA_OK(cudaIpcCloseMemHandle(ptr));
+  return WF_OK;
+}
+extern "C" int wf_peer_free(void* ptr) {
+  WF_CUDA_OK(cudaFree(ptr));
+  return WF_OK;
+}

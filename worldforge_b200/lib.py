@@ -36,6 +36,12 @@ _SIGNATURES = {
     "wf_attention_bsa_bf16": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp],
     "wf_layer_norm": [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _vp],
     "wf_rms_norm_rope": [_vp, _i, _vp, _vp, _i, _i, _f, _vp],
+    "wf_qkv_norm_rope_scatter": [_vp, _i, _vp, _vp, _vp, _i, _i, _f, _vp, _i, _i, _i, _vp],
+    "wf_attention_bf16_peers": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _f, _vp],
+    "wf_peer_alloc": [_ll, _vp, _vp],
+    "wf_peer_open": [_vp, _vp],
+    "wf_peer_close": [_vp],
+    "wf_peer_free": [_vp],
     "wf_patchify": [_vp, _vp, _i, _i, _i, _i, _vp],
     "wf_dit_head": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _f, _i, _i, _i, _vp],
     "wf_rms_norm_head_rope": [_vp, _i, _vp, _vp, _ll, _i, _f, _vp],
@@ -211,6 +217,66 @@ def layer_norm(x, out, eps: float, scale=None, shift=None, weight=None, bias=Non
     _call("wf_layer_norm", _p(x), x.stride(0), _is_bf16(x), _p(out), out.stride(0), _is_bf16(out), _p(scale), _p(shift),
           _p(weight), _p(bias), rows, D, eps, int(round_norm_bf16), rows_per_group, _stream())
     return out
+
+
+def attention_bf16_peers(q, k, v, peer_ptrs, rows_per_peer: int, ldo: int, heads: int, softmax_scale: Optional[float] = None):
+    """Attention whose output row r is stored into peer_ptrs[r // rows_per_peer] (raw device pointers of the ranks'
+    buffers, column offset of this rank's head block included) at row r % rows_per_peer, leading dimension ldo."""
+    for t in (q, k, v):
+        assert t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1
+    scale = softmax_scale if softmax_scale is not None else 128 ** -0.5
+    ev = None
+    if timed_attention is not None and q.shape[0] == k.shape[0]:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    tab = (C.c_void_p * len(peer_ptrs))(*peer_ptrs)
+    _call("wf_attention_bf16_peers", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), C.cast(tab, _vp), len(peer_ptrs),
+          rows_per_peer, ldo, q.shape[0], k.shape[0], heads, scale, _stream())
+    if ev is not None:
+        ev[1].record()
+        timed_attention.append(ev)
+
+
+def qkv_norm_rope_scatter(qkv, weight_q, weight_k, rope, eps: float, peer_ptrs, ld_dst: int, row0: int):
+    """qkv bf16 [rows, 3*D] -> RMSNorm + RoPE of q and k, v copied, each head written to the peer that owns it."""
+    rows, W3 = qkv.shape
+    D = W3 // 3
+    assert qkv.dtype == torch.bfloat16 and qkv.stride(1) == 1
+    assert rope.dtype == torch.float64 and rope.shape == (rows, 64, 2) and rope.is_contiguous()
+    tab = (C.c_void_p * len(peer_ptrs))(*peer_ptrs)
+    _call("wf_qkv_norm_rope_scatter", _p(qkv), qkv.stride(0), _p(weight_q), _p(weight_k), _p(rope), rows, D, eps, C.cast(tab, _vp),
+          len(peer_ptrs), ld_dst, row0, _stream())
+
+
+class PeerBuffer:
+    """Device memory other ranks of the box can map (cudaMalloc + CUDA IPC): ``ptr`` / ``handle`` here, ``open`` there."""
+
+    def __init__(self, nbytes: int):
+        lib = load()
+        ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        rc = lib.wf_peer_alloc(nbytes, C.byref(ptr), handle)
+        if rc != 0:
+            raise WfError(f"wf_peer_alloc failed ({rc}): {lib.wf_last_error().decode()}")
+        self.ptr, self.handle, self.nbytes = ptr.value, handle.raw, nbytes
+
+    def tensor(self, shape, dtype, device):
+        """A torch view of the allocation (no ownership)."""
+        n = 1
+        for d in shape:
+            n *= d
+        iface = {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 2}
+        holder = type("_Raw", (), {"__cuda_array_interface__": iface})()
+        flat = torch.as_tensor(holder, device=device)
+        return flat[:n * torch.empty((), dtype=dtype).element_size()].view(dtype).view(*shape)
+
+    @staticmethod
+    def open(handle: bytes) -> int:
+        lib = load()
+        ptr = C.c_void_p()
+        rc = lib.wf_peer_open(C.create_string_buffer(handle, 64), C.byref(ptr))
+        if rc != 0:
+            raise WfError(f"wf_peer_open failed ({rc}): {lib.wf_last_error().decode()}")
+        return ptr.value
 
 
 def rms_norm_rope_(x, weight, eps: float, rope=None):

@@ -144,6 +144,7 @@ class WfWanTransformer:
         self.cache_context = True
         self.calls = 0
         self.sp = None
+        self._psp = {}
 
     def to(self, *a, **k):          # survives pipe.to("cuda")
         return self
@@ -305,6 +306,12 @@ class WfWanTransformer:
         if (grid, P, rk) not in self._rope:
             self._rope[(grid, P, rk)] = rope_table(grid)[rk * Ll:(rk + 1) * Ll].contiguous().to(self.device)
         rope = self._rope[(grid, P, rk)]
+        psp = None
+        if sp is not None and getattr(sp, "peer", False):
+            if (L, Ll) not in self._psp:
+                from . import ulysses
+                self._psp[(L, Ll)] = ulysses.PeerSequenceParallel(sp.group, L, Ll, nh, self.device)
+            psp = self._psp[(L, Ll)]
 
         # patch embedding (bf16 token stream, held in fp32 storage)
         lib.patchify(hs, B.cols)
@@ -323,13 +330,16 @@ class WfWanTransformer:
             # self attention
             lib.layer_norm(B.x, B.h, c.eps, scale=e[1], shift=e[0], round_norm_bf16=(i == 0))
             lib.gemm_bf16(B.h, b.qkv_w, b.qkv_b, B.qkv, lib.EPI_BF16)
-            lib.rms_norm_rope_(B.qkv[:, :D], b.norm_q, c.eps, rope)
-            lib.rms_norm_rope_(B.qkv[:, D:2 * D], b.norm_k, c.eps, rope)
-            if sp is None:
-                lib.attention_bf16(B.qkv[:, :D], B.qkv[:, D:2 * D], B.qkv[:, 2 * D:], B.att, nh)
-                att = B.att
+            if psp is not None:                        # Ulysses through NVLink peer memory: norm+RoPE+scatter, attention -> peers
+                att = psp.exchange_attention(B.qkv, b.norm_q, b.norm_k, rope, c.eps)
             else:
-                att = sp.attention(B.qkv, nh)          # Ulysses: heads <-> tokens all-to-all around the same kernel
+                lib.rms_norm_rope_(B.qkv[:, :D], b.norm_q, c.eps, rope)
+                lib.rms_norm_rope_(B.qkv[:, D:2 * D], b.norm_k, c.eps, rope)
+                if sp is None:
+                    lib.attention_bf16(B.qkv[:, :D], B.qkv[:, D:2 * D], B.qkv[:, 2 * D:], B.att, nh)
+                    att = B.att
+                else:
+                    att = sp.attention(B.qkv, nh)      # Ulysses: heads <-> tokens all-to-all (NCCL) around the same kernel
             lib.gemm_bf16(att, b.o_w, b.o_b, B.x, lib.EPI_RESID_F32, gate=e[2])
             # cross attention: image keys, then text keys with the image result added
             lib.layer_norm(B.x, B.h, c.eps, weight=b.n3_w, bias=b.n3_b)

@@ -44,6 +44,7 @@ class SequenceParallel:
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         self.a2a_calls = 0
+        self.peer = False
 
     def all_to_all(self, send: torch.Tensor) -> torch.Tensor:
         recv = torch.empty_like(send)
@@ -71,7 +72,60 @@ class SequenceParallel:
         return tokens_to_heads_layout(back)
 
 
-def enable(transformer, group=None) -> SequenceParallel:
+class PeerSequenceParallel(SequenceParallel):
+    """The same exchange without collectives on the data path: the kernels that produce q|k|v and the attention output
+    store straight into the consuming rank's memory over NVLink (CUDA IPC peer mappings of ``wf_peer_alloc`` buffers).
+
+      wf_qkv_norm_rope_scatter   RMSNorm + RoPE of q and k (and v) -> peer d's  full[L, 3*(H/P)*128]   (rows of this rank)
+      barrier
+      wf_attention_bf16_peers    attention over all tokens, this rank's heads -> row q to the rank owning token q,
+                                 att[Ll, H*128] columns of this rank's heads
+      barrier
+
+    against NCCL's version of the reference pattern: two all-to-alls, three layout copies and two RMSNorm passes per
+    layer.  The barrier is a 1-element all-reduce on the compute stream (stream-ordered after the producer kernel, so a
+    rank's peers have finished writing when it returns).  ``att`` is double-buffered by layer parity: a rank may start
+    writing layer l+1's output into a peer that is still reading layer l's (it cannot be two layers ahead - the barriers
+    of layer l+1 need every rank's layer-l attention)."""
+
+    def __init__(self, group, L: int, Ll: int, heads: int, device):
+        super().__init__(group)
+        from . import lib
+        P, hl = self.world, heads // self.world
+        self.L, self.Ll, self.heads, self.hl, self.device = L, Ll, heads, hl, device
+        self.ld_full, self.ld_att = 3 * hl * 128, heads * 128
+        self._bufs = [lib.PeerBuffer(L * self.ld_full * 2), lib.PeerBuffer(Ll * self.ld_att * 2), lib.PeerBuffer(Ll * self.ld_att * 2)]
+        handles = [None] * P
+        dist.all_gather_object(handles, [b.handle for b in self._bufs], group=self.group)
+        self._ptrs = [[self._bufs[i].ptr if r == self.rank else lib.PeerBuffer.open(handles[r][i]) for r in range(P)] for i in range(3)]
+        self.full = self._bufs[0].tensor((L, self.ld_full), torch.bfloat16, device)
+        self.att = [self._bufs[1 + i].tensor((Ll, self.ld_att), torch.bfloat16, device) for i in range(2)]
+        self._flag = torch.zeros(1, device=device)
+        self.layer = 0
+        self.barriers = 0
+
+    def barrier(self):
+        dist.all_reduce(self._flag, group=self.group)
+        self.barriers += 1
+
+    def exchange_attention(self, qkv: torch.Tensor, norm_q, norm_k, rope, eps: float) -> torch.Tensor:
+        """qkv [Ll, 3*H*128] bf16 straight from the projection (NOT yet normalised) -> attention output [Ll, H*128]."""
+        from . import lib
+        par = self.layer & 1
+        self.layer += 1
+        lib.qkv_norm_rope_scatter(qkv, norm_q, norm_k, rope, eps, self._ptrs[0], self.ld_full, self.rank * self.Ll)
+        self.barrier()
+        w = self.hl * 128
+        col = self.rank * w * 2                                        # byte offset of this rank's head block in a row of att
+        lib.attention_bf16_peers(self.full[:, :w], self.full[:, w:2 * w], self.full[:, 2 * w:],
+                                 [p + col for p in self._ptrs[1 + par]], self.Ll, self.ld_att, self.hl)
+        self.barrier()
+        return self.att[par]
+
+
+def enable(transformer, group=None, peer: bool = False) -> SequenceParallel:
+    """``peer=True``: exchange through NVLink peer memory (built lazily at the first forward, when the token count is known)."""
     sp = SequenceParallel(group)
+    sp.peer = peer
     transformer.sp = sp
     return sp
