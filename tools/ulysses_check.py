@@ -10,7 +10,8 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 world = dist.get_world_size()
-cfg = wtr.WanDitConfig(dim=512, ffn_dim=1024, num_heads=4, num_layers=2, text_dim=64, text_len=16, img_dim=64, img_len=5, freq_dim=32)
+nh = max(4, world)                                # heads and tokens must split over the ranks
+cfg = wtr.WanDitConfig(dim=128 * nh, ffn_dim=1024, num_heads=nh, num_layers=2, text_dim=64, text_len=16, img_dim=64, img_len=5, freq_dim=32)
 m = wtr.WfWanTransformer.random_init(cfg, dev, seed=5)
 g = torch.Generator().manual_seed(0)
 x = torch.randn(1, 36, 3, 8, 16, generator=g).to(torch.bfloat16).to(dev)
