@@ -25,6 +25,8 @@
 // Structure is the GEMM's: persistent CTAs, warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
 // warps 4-7 epilogue (smem transpose -> 128-byte coalesced row stores), 4-stage mbarrier ring, two TMEM
 // accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -48,7 +50,9 @@ constexpr int CV_MAX_TAPS = 27;
 struct ConvArgs {
   // iteration space of the output tiles
   int T, H, W;              // output frames / rows / columns this launch produces
-  int TH, TW;               // tile shape, TH*TW == 128
+  int TH, TW;               // tile shape, TH*TW == 128 (TW a power of two)
+  int tw_shift;             // log2(TW)
+  int a_stages, b_stages, b_slot;   // halo kernel: ring depths and the byte size of one B slot (BN*128 rounded to 1 KB)
   int Cin, Cout, BN;        // Cin % 32 == 0 (padded), BN in {16,32,48,...,192}
   int ntaps;
   int t_stride, t_off;      // input frame = t*t_stride + t_off + dt
@@ -62,6 +66,74 @@ struct ConvArgs {
   int planar_clamp;         // 1: out is planar [c_split][frames][out_H][out_W], values clamped to [-1,1]
   long long planar_cstride; // elements between channels in planar mode
 };
+
+// Epilogue of one 128-pixel x BN tile for epilogue warp q (rows 32q..32q+31 of the tile): TMEM -> registers -> shared-memory
+// transpose -> 128-byte coalesced row stores (bias, residual, placement, clamp).  The per-row part of the output address
+// ((y*sy+oy)*out_W + x*sx+ox) is computed once per tile with shifts (TW is a power of two); per 32-column chunk a row costs
+// one multiply-add - the addressing used to be two integer divisions and 64-bit products per row and chunk, which made the
+// four epilogue warps the busiest part of the kernel.
+__device__ __forceinline__ void conv_epilogue_tile(const ConvArgs& p, float* tile_s, uint32_t t_row, int q, int lane, int t,
+                                                   int y0, int x0, int n0) {
+  int row_part[32];
+  uint32_t row_ok = 0;
+#pragma unroll
+  for (int rr = 0; rr < 32; ++rr) {
+    const int r_in_tile = q * 32 + rr;
+    const int y = y0 + (r_in_tile >> p.tw_shift), x = x0 + (r_in_tile & (p.TW - 1));
+    row_part[rr] = (y * p.sy + p.oy) * p.out_W + (x * p.sx + p.ox);
+    row_ok |= (y < p.H && x < p.W) ? (1u << rr) : 0u;
+  }
+  const size_t frame_elems = static_cast<size_t>(p.out_H) * p.out_W;
+#pragma unroll 1
+  for (int c = 0; c < p.BN; c += 32) {
+    const int n = n0 + c;
+    if (n >= p.Cout) break;
+    if (p.BN - c >= 32) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(t_row + c, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) tile_s[lane * CV_EPI_LD + j] = __uint_as_float(r[j]);
+    } else {   // BN = 16 or 48: the last chunk has 16 valid columns; TMEM beyond BN is not ours to read
+      uint32_t r[16];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "r"(t_row + c) : "memory");
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) tile_s[lane * CV_EPI_LD + j] = __uint_as_float(r[j]);
+    }
+    __syncwarp();
+    const int col = n + lane;
+    const bool col_ok = col < p.Cout && (c + lane) < p.BN;
+    const float b0 = (col_ok && p.bias) ? p.bias[col] : 0.f;
+    const int fo = col_ok ? col / p.c_split : 0, ch = col_ok ? col % p.c_split : 0;
+    const size_t frame_off = static_cast<size_t>(t * p.t_mul + fo) * frame_elems;
+    // element (row rr, this lane's column): base + row_part[rr] * pitch
+    const size_t base = p.planar_clamp ? static_cast<size_t>(ch) * p.planar_cstride + frame_off : frame_off * p.ldc + ch;
+    const int pitch = p.planar_clamp ? 1 : p.ldc;
+    const uint32_t okm = col_ok ? row_ok : 0u;
+    float rv[32];
+    if (p.resid) {
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr)
+        rv[rr] = ((okm >> rr) & 1u) ? p.resid[base + static_cast<size_t>(row_part[rr]) * pitch] : 0.f;
+    }
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) {
+      if ((okm >> rr) & 1u) {
+        float v = tile_s[rr * CV_EPI_LD + lane] + b0;
+        if (p.resid) v += rv[rr];
+        if (p.planar_clamp) v = fminf(fmaxf(v, -1.0f), 1.0f);
+        p.out[base + static_cast<size_t>(row_part[rr]) * pitch] = v;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvArgs p) {
@@ -124,34 +196,33 @@ conv_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // -------------------------------------------------------------- MMA issuer
-    const uint32_t idesc = umma_idesc(2, CV_BM, static_cast<uint32_t>(p.BN), 0, 0);   // tf32 x tf32 -> fp32
-    int stage = 0; uint32_t phase = 0;
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(&acc_empty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * 256;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full[stage], phase);
+    // -------------------------------------------------------------- MMA issuer (one lane runs the whole loop)
+    if (lane_id() == 0) {
+      const uint32_t idesc = umma_idesc(2, CV_BM, static_cast<uint32_t>(p.BN), 0, 0);   // tf32 x tf32 -> fp32
+      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(smem), 16, 1024);
+      const uint64_t b_desc0 = umma_desc_sw128(smem_u32(smem + CV_A_BYTES), 16, 1024);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t a_addr = smem_u32(smem + stage * CV_STAGE_BYTES);
-          const uint32_t b_addr = a_addr + CV_A_BYTES;
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t off = static_cast<uint64_t>((stage * CV_STAGE_BYTES) >> 4);
 #pragma unroll
-          for (int k = 0; k < CV_BK / 8; ++k) {
-            uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
-            uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_tf32_ss(d_tmem, da, db, idesc, (kb | k) != 0);
-          }
+          for (int k = 0; k < CV_BK / 8; ++k)
+            umma_tf32_ss(d_tmem, a_desc0 + off + static_cast<uint64_t>((k * 32) >> 4), b_desc0 + off + static_cast<uint64_t>((k * 32) >> 4),
+                         idesc, (kb | k) != 0);
           umma_commit(&empty[stage]);
           if (kb == num_kb - 1) umma_commit(&acc_full[acc]);
+          if (++stage == CV_STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == CV_STAGES) { stage = 0; phase ^= 1; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    __syncwarp();
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
     const int q = warp & 3, lane = lane_id();
@@ -162,59 +233,7 @@ conv_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
-#pragma unroll 1
-      for (int c = 0; c < p.BN; c += 32) {
-        const int n = n0 + c;
-        if (n >= p.Cout) break;
-        if (p.BN - c >= 32) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(t_row + c, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) tile_s[lane * CV_EPI_LD + j] = __uint_as_float(r[j]);
-        } else {   // BN = 16 or 48: the last chunk has 16 valid columns; TMEM beyond BN is not ours to read
-          uint32_t r[32];
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-              : "r"(t_row + c) : "memory");
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) tile_s[lane * CV_EPI_LD + j] = __uint_as_float(r[j]);
-        }
-        __syncwarp();
-        const int col = n + lane;
-        const bool col_ok = col < p.Cout && (c + lane) < p.BN;
-        const float b0 = (col_ok && p.bias) ? p.bias[col] : 0.f;
-        const int fo = col_ok ? col / p.c_split : 0, ch = col_ok ? col % p.c_split : 0;
-        const int frame = t * p.t_mul + fo;
-        // 32 rows of this warp = pixels q*32 .. q*32+31 of the TH x TW tile
-        size_t off[32]; bool ok[32];
-#pragma unroll
-        for (int rr = 0; rr < 32; ++rr) {
-          const int r_in_tile = q * 32 + rr;
-          const int y = y0 + r_in_tile / p.TW, x = x0 + r_in_tile % p.TW;
-          ok[rr] = col_ok && y < p.H && x < p.W;
-          const size_t pix = (static_cast<size_t>(frame) * p.out_H + (y * p.sy + p.oy)) * p.out_W + (x * p.sx + p.ox);
-          off[rr] = p.planar_clamp ? static_cast<size_t>(ch) * p.planar_cstride + pix : pix * p.ldc + ch;
-        }
-        float rv[32];
-        if (p.resid) {
-#pragma unroll
-          for (int rr = 0; rr < 32; ++rr) rv[rr] = ok[rr] ? p.resid[off[rr]] : 0.f;
-        }
-#pragma unroll
-        for (int rr = 0; rr < 32; ++rr) {
-          if (ok[rr]) {
-            float v = tile_s[rr * CV_EPI_LD + lane] + b0;
-            if (p.resid) v += rv[rr];
-            if (p.planar_clamp) v = fminf(fmaxf(v, -1.0f), 1.0f);
-            p.out[off[rr]] = v;
-          }
-        }
-        __syncwarp();
-      }
+      conv_epilogue_tile(p, tile_s, t_row, q, lane, t, y0, x0, n0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
@@ -228,6 +247,220 @@ conv_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+
+// =====================================================================================================================
+// 3x3x3 causal convolution: one halo tile per (frame, 32-channel chunk), several pixel tiles per CTA.
+//
+// Two measurements shape this kernel (tools/umma_offset_probe.cu, tools/umma_rate_probe.cu; profiles/):
+//  * tcgen05.mma instructions that accumulate into the SAME TMEM tile issue ~157 clocks apart whatever their width (N = 48
+//    .. 256, tf32 or bf16): a single accumulator chain only reaches the tensor-pipe floor (N/2 clocks) at N = 256.  The VAE's
+//    convolutions are N = 96 / 192 wide, so one chain runs at 31 % / 61 % - which is where the per-tap kernel above sat
+//    (39 %), and neither cheaper addressing, nor a leaner issue loop, nor deeper TMA rings moved it.  Independent chains DO
+//    overlap: the CTA therefore owns MT pixel tiles (MT x BN = 384 accumulator columns) and issues their MMAs round-robin.
+//  * a SWIZZLE_128B K-major operand may start at any 128-byte row and use any row-group pitch (the swizzle follows absolute
+//    address bits).  The MT tiles of 16 x 8 pixels form one block (2 x 2 or 2 x 1 tiles) whose halo is ONE 4-D TMA box per
+//    (dt, chunk) (out-of-bounds zero fill = padding and causal history); the A operand of tile (ty, tx) and tap (dy, dx) is
+//    that box read through a descriptor starting at halo row (16 ty + dy + 1) * PW + 8 tx + dx + 1 with group pitch PW rows.
+// One B tile (a tap's [BN, 32] weight slice) feeds all MT tiles: B traffic per MMA drops MT-fold, A traffic ~6-fold.
+// K loop order (dt, chunk, in-plane tap); A and B in separate rings fed by two producer warps; one lane issues every MMA.
+// The accumulators fill TMEM, so the epilogue of a block is not overlapped with the next block's main loop (it is ~10 %
+// of a block now that its addressing is cheap).
+// =====================================================================================================================
+constexpr int CH_TH = 16, CH_TW = 8;
+constexpr int CH_MAX_A_STAGES = 2, CH_MAX_B_STAGES = 16;
+constexpr int CH_BAR_BYTES = 512;
+constexpr int CH_SMEM_MAX = 232448;
+constexpr int CH_RING_BUDGET = CH_SMEM_MAX - 1024 - CH_BAR_BYTES - CV_EPI_BYTES;
+
+template <int MT> struct ChGeom {
+  static constexpr int TX = MT == 4 ? 2 : 1, TY = MT == 1 ? 1 : 2;        // tiles per block along x / y
+  static constexpr int BW = TX * CH_TW, BH = TY * CH_TH;                   // block of output pixels
+  static constexpr int PW = BW + 2, PH = BH + 2;                           // halo box
+  static constexpr int A_BYTES = PW * PH * CV_BK * 4;
+  static constexpr int A_SLOT = (A_BYTES + 1023) / 1024 * 1024;
+};
+
+template <int MT>
+__global__ void __launch_bounds__(CV_THREADS, 1)
+conv333_halo_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvArgs p) {
+  using G = ChGeom<MT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int off_b = p.a_stages * G::A_SLOT;
+  const int off_bar = off_b + p.b_stages * p.b_slot;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + off_bar);
+  uint64_t* a_empty = a_full + CH_MAX_A_STAGES;
+  uint64_t* b_full = a_empty + CH_MAX_A_STAGES;
+  uint64_t* b_empty = b_full + CH_MAX_B_STAGES;
+  uint64_t* acc_full = b_empty + CH_MAX_B_STAGES;
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+  float* epi_tile = reinterpret_cast<float*>(smem + off_bar + CH_BAR_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const int blocks_x = (p.W + G::BW - 1) / G::BW, blocks_y = (p.H + G::BH - 1) / G::BH;
+  const int tiles_n = (p.Cout + p.BN - 1) / p.BN;
+  const int num_blocks = blocks_x * blocks_y * p.T * tiles_n;
+  const int kchunks = p.Cin / CV_BK;
+  const int num_ab = 3 * kchunks;                 // (dt, chunk) pairs = halo boxes per block
+  const uint32_t b_tx = static_cast<uint32_t>(p.BN) * CV_BK * 4;
+  const int acc_cols = (p.BN + 31) / 32 * 32;     // TMEM columns per tile accumulator
+
+  if (warp == 0 && elect_one()) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < p.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    mbar_init(acc_full, 1); mbar_init(acc_empty, 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // block -> (n-tile fastest: the n-tiles of one pixel block run back to back and share the A traffic in L2)
+  auto decode = [&](int blk, int& t, int& y0, int& x0, int& n0) {
+    const int nt = blk % tiles_n; int pb = blk / tiles_n;
+    const int xb = pb % blocks_x; pb /= blocks_x;
+    const int yb = pb % blocks_y; t = pb / blocks_y;
+    y0 = yb * G::BH; x0 = xb * G::BW; n0 = nt * p.BN;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ A producer: one halo box per (dt, chunk)
+    int stage = 0; uint32_t phase = 0;
+    for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x) {
+      int t, y0, x0, n0; decode(blk, t, y0, x0, n0);
+      for (int dt = 0; dt < 3; ++dt)
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&a_empty[stage], phase ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&a_full[stage], G::A_BYTES);
+            tma_load_4d(smem + stage * G::A_SLOT, &tmA, &a_full[stage], kc * CV_BK, x0 - 1, y0 - 1, t + dt - 2);
+          }
+          __syncwarp();
+          if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
+        }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------ B producer: the nine in-plane taps of (dt, chunk)
+    int stage = 0; uint32_t phase = 0;
+    for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x) {
+      int t, y0, x0, n0; decode(blk, t, y0, x0, n0);
+      for (int dt = 0; dt < 3; ++dt)
+        for (int kc = 0; kc < kchunks; ++kc)
+          for (int s = 0; s < 9; ++s) {
+            mbar_wait(&b_empty[stage], phase ^ 1);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&b_full[stage], b_tx);
+              tma_load_2d(smem + off_b + stage * p.b_slot, &tmB, &b_full[stage], kc * CV_BK, (dt * 9 + s) * p.Cout + n0);
+            }
+            __syncwarp();
+            if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
+          }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer: one lane, MT accumulator chains round-robin
+    if (lane_id() == 0) {
+      const uint32_t idesc = umma_idesc(2, CV_BM, static_cast<uint32_t>(p.BN), 0, 0);
+      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(smem), 16, G::PW * 128);
+      const uint64_t b_desc0 = umma_desc_sw128(smem_u32(smem + off_b), 16, 1024);
+      int as = 0; uint32_t aph = 0;
+      int bs = 0; uint32_t bph = 0;
+      uint32_t acc_phase = 0;
+      for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x) {
+        mbar_wait(acc_empty, acc_phase ^ 1);
+        tc_fence_after();
+        for (int ab = 0; ab < num_ab; ++ab) {
+          mbar_wait(&a_full[as], aph);
+          const uint64_t da_s = a_desc0 + static_cast<uint64_t>((as * G::A_SLOT) >> 4);
+#pragma unroll
+          for (int s = 0; s < 9; ++s) {
+            mbar_wait(&b_full[bs], bph);
+            tc_fence_after();
+            const uint64_t db_s = b_desc0 + static_cast<uint64_t>((bs * p.b_slot) >> 4);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+#pragma unroll
+              for (int k = 0; k < CV_BK / 8; ++k) {
+                // tile m = (ty, tx) of the block; tap s = (dy + 1, dx + 1): halo row (16 ty + dy + 1) * PW + 8 tx + dx + 1
+                const int ty = m / G::TX, tx = m % G::TX;
+                const int row = (ty * CH_TH + s / 3) * G::PW + tx * CH_TW + s % 3;
+                umma_tf32_ss(tmem_base + m * acc_cols, da_s + static_cast<uint64_t>((row * 128 + k * 32) >> 4),
+                             db_s + static_cast<uint64_t>((k * 32) >> 4), idesc, (ab | s | k) != 0);
+              }
+            }
+            umma_commit(&b_empty[bs]);
+            if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+          }
+          umma_commit(&a_empty[as]);
+          if (ab == num_ab - 1) umma_commit(acc_full);
+          if (++as == p.a_stages) { as = 0; aph ^= 1; }
+        }
+        acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue: the MT tiles one after the other
+    const int q = warp & 3, lane = lane_id();
+    float* tile_s = epi_tile + q * (32 * CV_EPI_LD);
+    uint32_t acc_phase = 0;
+    for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x) {
+      int t, y0, x0, n0; decode(blk, t, y0, x0, n0);
+      mbar_wait(acc_full, acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int m = 0; m < MT; ++m) {
+        const int ty = m / G::TX, tx = m % G::TX;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + m * acc_cols;
+        if (y0 + ty * CH_TH < p.H && x0 + tx * CH_TW < p.W)
+          conv_epilogue_tile(p, tile_s, t_row, q, lane, t, y0 + ty * CH_TH, x0 + tx * CH_TW, n0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+      acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int MT>
+static int launch_conv333(const float* in, int in_T, int in_H, int in_W, int Cin, const CUtensorMap& tmB, ConvArgs a, void* stream,
+                          int grid_cap) {
+  using G = ChGeom<MT>;
+  CUtensorMap tmH;
+  uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(in_W), static_cast<uint64_t>(in_H), static_cast<uint64_t>(in_T)};
+  uint64_t strides[3] = {static_cast<uint64_t>(Cin) * 4, static_cast<uint64_t>(in_W) * Cin * 4, static_cast<uint64_t>(in_H) * in_W * Cin * 4};
+  uint32_t box[4] = {CV_BK, G::PW, G::PH, 1};
+  int rc = make_tmap(&tmH, in, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  a.TW = CH_TW; a.TH = CH_TH; a.tw_shift = 3;
+  a.b_slot = (a.BN * CV_BK * 4 + 1023) / 1024 * 1024;
+  a.a_stages = CH_MAX_A_STAGES;                     // an A slot feeds nine B slots
+  a.b_stages = std::min(CH_MAX_B_STAGES, (CH_RING_BUDGET - a.a_stages * G::A_SLOT) / a.b_slot);
+  if (a.b_stages < 2) return fail(WF_EINVAL, "wf_conv_tf32: no room for the B ring");
+  const int smem = a.a_stages * G::A_SLOT + a.b_stages * a.b_slot + CH_BAR_BYTES + CV_EPI_BYTES + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    WF_CUDA_OK(cudaFuncSetAttribute(conv333_halo_tcgen05<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_MAX));
+    attr_set = true;
+  }
+  const long long blocks = static_cast<long long>((a.W + G::BW - 1) / G::BW) * ((a.H + G::BH - 1) / G::BH) * a.T * ((a.Cout + a.BN - 1) / a.BN);
+  const int grid = static_cast<int>(std::min<long long>(blocks, grid_cap));
+  conv333_halo_tcgen05<MT><<<grid, CV_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tmH, tmB, a);
+  WF_LAUNCH_OK();
+  return WF_OK;
 }
 
 }  // namespace wf
@@ -248,6 +481,8 @@ extern "C" int wf_conv_tf32(const float* in, int in_T, int in_H, int in_W, int C
   WF_REQUIRE(reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(weights) % 16 == 0, "wf_conv_tf32: 16-byte alignment");
   ConvArgs a{};
   a.T = T; a.H = H; a.W = W; a.TW = tile_w; a.TH = CV_BM / tile_w;
+  a.tw_shift = 0;
+  while ((1 << a.tw_shift) < tile_w) ++a.tw_shift;
   a.Cin = (Cin + CV_BK - 1) / CV_BK * CV_BK;   // the K loop runs over whole 32-channel chunks; TMA zero-fills the tail
   a.Cout = Cout;
   // widest N tile that divides the work evenly enough: 192 for the wide layers, Cout rounded up to 16 otherwise
@@ -275,10 +510,24 @@ extern "C" int wf_conv_tf32(const float* in, int in_T, int in_H, int in_W, int C
     if (rc) return rc;
   }
   static bool attr_set = false;
+  static int use_halo = 1, grid_cap = 0;
   if (!attr_set) {
     WF_CUDA_OK(cudaFuncSetAttribute(conv_tf32_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM));
+    const char* e = getenv("WF_CONV_HALO");            // 0: always the per-tap kernel (A/B measurements)
+    use_halo = e ? atoi(e) : 1;
+    const char* g = getenv("WF_CONV_GRID");            // cap on the number of CTAs (development)
+    grid_cap = g ? atoi(g) : 0;
+    if (grid_cap <= 0) grid_cap = sm_count();
     attr_set = true;
   }
+  // the plain 3x3x3 causal convolution (taps in (dt, dy, dx) order, unit strides) runs the halo / multi-tile kernel:
+  // MT tiles x BN accumulator columns = 384 independent columns in flight
+  bool is333 = use_halo && ntaps == 27 && t_stride == 1 && t_off == 0 && in_H == H && in_W == W;
+  for (int i = 0; is333 && i < 27; ++i)
+    is333 = taps[3 * i] == i / 9 - 2 && taps[3 * i + 1] == (i / 3) % 3 - 1 && taps[3 * i + 2] == i % 3 - 1;
+  if (is333)
+    return a.BN <= 96 ? launch_conv333<4>(in, in_T, in_H, in_W, Cin, tmB, a, stream, grid_cap)
+                      : launch_conv333<2>(in, in_T, in_H, in_W, Cin, tmB, a, stream, grid_cap);
   const long long tiles = static_cast<long long>((W + a.TW - 1) / a.TW) * ((H + a.TH - 1) / a.TH) * T * ((Cout + a.BN - 1) / a.BN);
   const int grid = static_cast<int>(std::min<long long>(tiles, sm_count()));
   conv_tf32_tcgen05<<<grid, CV_THREADS, CV_SMEM, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, a);
