@@ -321,11 +321,14 @@ conv333_halo_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // block -> (n-tile fastest: the n-tiles of one pixel block run back to back and share the A traffic in L2)
+  // block -> (n-tile fastest, then the FRAME, then x, y): the CTAs running at one time work on the same pixel block of
+  // consecutive frames, so the three input frames a temporal tap set touches are shared through L2 instead of being read from
+  // DRAM once per tap (frame-major order: 5.25 GB of DRAM reads for a 1.38 GB input)
   auto decode = [&](int blk, int& t, int& y0, int& x0, int& n0) {
     const int nt = blk % tiles_n; int pb = blk / tiles_n;
-    const int xb = pb % blocks_x; pb /= blocks_x;
-    const int yb = pb % blocks_y; t = pb / blocks_y;
+    t = pb % p.T; pb /= p.T;
+    const int xb = pb % blocks_x;
+    const int yb = pb / blocks_x;
     y0 = yb * G::BH; x0 = xb * G::BW; n0 = nt * p.BN;
   };
 
