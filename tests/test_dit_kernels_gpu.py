@@ -114,7 +114,7 @@ def test_attention_add_in_and_strided(cuda):
     torch.testing.assert_close(out.cpu().float(), want.float(), rtol=2e-2, atol=1e-2)
 
 
-@pytest.mark.parametrize("rows,D", [(37, 256), (300, 5120), (5, 1280)])
+@pytest.mark.parametrize("rows,D", [(37, 256), (300, 5120), (5, 1280), (700, 5120), (1500, 256)])   # >= 592 rows: the persistent row-ring form
 def test_layer_norm_modulate(cuda, rows, D):
     from worldforge_b200 import lib
     x = torch.randn(rows, D, generator=g(17)) * 2 + 0.3

@@ -54,59 +54,111 @@ struct LnArgs {
   int rows_per_group;   // > 0: scale/shift are [groups, D] tables, row r uses group r / rows_per_group (per-frame adaLN)
 };
 
-__global__ void __launch_bounds__(LN_THREADS) layer_norm_kernel(LnArgs p) {
+// One row per iteration.  RING = false: one CTA per row, the row is loaded straight into registers.  RING = true: a
+// persistent CTA walks rows blockIdx.x, blockIdx.x + gridDim.x, ... and one thread keeps the next NORM_RING - 1 rows in
+// flight with cp.async.bulk into a shared-memory ring: a row's CTA spends more than half of its life in the two block
+// reductions and the stores, with no loads outstanding, and register pressure allows only four CTAs per SM - too few bytes
+// in flight to keep HBM busy (the one-row-per-CTA form measured 3.0 TB/s of 6.4).  Same arithmetic, same element-to-thread
+// mapping, same reduction order: bit-identical results.
+constexpr int NORM_RING = 3;
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <bool RING>
+__global__ void __launch_bounds__(LN_THREADS) layer_norm_kernel(LnArgs p, int rows) {
+  extern __shared__ __align__(128) uint8_t norm_ring[];
   __shared__ float red[32];
-  const int row = blockIdx.x;
+  __shared__ uint64_t full[NORM_RING];
   const int nvec = p.D >> 2;
-  const size_t goff = p.rows_per_group > 0 ? static_cast<size_t>(row / p.rows_per_group) * p.D : 0;
-  float4 v[LN_MAXV];
-  float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int idx = threadIdx.x + i * LN_THREADS;
-    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (idx < nvec) {
-      if (p.x_is_bf16) {
-        const uint2 raw = *reinterpret_cast<const uint2*>(static_cast<const bf16*>(p.x) + static_cast<size_t>(row) * p.ldx + idx * 4);
-        float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-        float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
-        v[i] = make_float4(a.x, a.y, b.x, b.y);
-      } else {
-        v[i] = *reinterpret_cast<const float4*>(static_cast<const float*>(p.x) + static_cast<size_t>(row) * p.ldx + idx * 4);
-      }
-      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const uint32_t row_bytes = static_cast<uint32_t>(p.D) * (p.x_is_bf16 ? 2 : 4);
+  const uint32_t slot_bytes = (row_bytes + 127u) & ~127u;
+  const size_t src_pitch = static_cast<size_t>(p.ldx) * (p.x_is_bf16 ? 2 : 4);
+  auto issue = [&](int i) {
+    const long long r = blockIdx.x + static_cast<long long>(i) * gridDim.x;
+    if (r < rows) {
+      const int sl = i % NORM_RING;
+      mbar_arrive_expect_tx(&full[sl], row_bytes);
+      bulk_g2s(norm_ring + sl * slot_bytes, static_cast<const uint8_t*>(p.x) + r * src_pitch, row_bytes, &full[sl]);
     }
+  };
+  if (RING) {
+    if (threadIdx.x == 0) {
+      for (int sl = 0; sl < NORM_RING; ++sl) mbar_init(&full[sl], 1);
+      fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) for (int i = 0; i < NORM_RING - 1; ++i) issue(i);
   }
-  const float mean = block_sum<LN_THREADS>(sum, red) / p.D;
-  float sq = 0.f;
-#pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int idx = threadIdx.x + i * LN_THREADS;
-    if (idx < nvec) {
-      float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-      sq += (a * a + b * b) + (c * c + d * d);
+  for (int it = 0;; ++it) {
+    const long long row_ll = blockIdx.x + static_cast<long long>(it) * gridDim.x;
+    if (row_ll >= rows) break;
+    const int row = static_cast<int>(row_ll);
+    const uint8_t* src = static_cast<const uint8_t*>(p.x) + row * src_pitch;
+    if (RING) {
+      // slot (it - 1) % NORM_RING was read by the previous row, whose block reductions every thread has passed
+      if (threadIdx.x == 0) issue(it + NORM_RING - 1);
+      mbar_wait(&full[it % NORM_RING], (it / NORM_RING) & 1);
+      src = norm_ring + (it % NORM_RING) * slot_bytes;
     }
-  }
-  const float rstd = rsqrtf(block_sum<LN_THREADS>(sq, red) / p.D + p.eps);
+    const size_t goff = p.rows_per_group > 0 ? static_cast<size_t>(row / p.rows_per_group) * p.D : 0;
+    float4 v[LN_MAXV];
+    float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int idx = threadIdx.x + i * LN_THREADS;
-    if (idx < nvec) {
-      float y[4] = {(v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd, (v[i].w - mean) * rstd};
-      const int c = idx * 4;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (p.weight) y[u] = y[u] * p.weight[c + u] + p.bias[c + u];
-        if (p.round_norm_bf16) y[u] = bf16_round(y[u]);
-        if (p.scale) y[u] = __fadd_rn(__fmul_rn(y[u], __fadd_rn(1.0f, p.scale[goff + c + u])), p.shift[goff + c + u]);
-      }
-      if (p.out_is_bf16) {
-        uint2 o = make_uint2(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]));
-        *reinterpret_cast<uint2*>(static_cast<bf16*>(p.out) + static_cast<size_t>(row) * p.ldo + c) = o;
-      } else {
-        *reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + c) = make_float4(y[0], y[1], y[2], y[3]);
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int idx = threadIdx.x + i * LN_THREADS;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < nvec) {
+        if (p.x_is_bf16) {
+          const uint2 raw = *reinterpret_cast<const uint2*>(src + static_cast<size_t>(idx) * 8);
+          float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+          float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+          v[i] = make_float4(a.x, a.y, b.x, b.y);
+        } else {
+          v[i] = *reinterpret_cast<const float4*>(src + static_cast<size_t>(idx) * 16);
+        }
+        sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
       }
     }
+    const float mean = block_sum<LN_THREADS>(sum, red) / p.D;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int idx = threadIdx.x + i * LN_THREADS;
+      if (idx < nvec) {
+        float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        sq += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    const float rstd = rsqrtf(block_sum<LN_THREADS>(sq, red) / p.D + p.eps);
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int idx = threadIdx.x + i * LN_THREADS;
+      if (idx < nvec) {
+        float y[4] = {(v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd, (v[i].w - mean) * rstd};
+        const int c = idx * 4;
+        float4 wv, bv, scv, shv;
+        if (p.weight) { wv = *reinterpret_cast<const float4*>(p.weight + c); bv = *reinterpret_cast<const float4*>(p.bias + c); }
+        if (p.scale) { scv = *reinterpret_cast<const float4*>(p.scale + goff + c); shv = *reinterpret_cast<const float4*>(p.shift + goff + c); }
+        const float w4[4] = {wv.x, wv.y, wv.z, wv.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+        const float sc4[4] = {scv.x, scv.y, scv.z, scv.w}, sh4[4] = {shv.x, shv.y, shv.z, shv.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (p.weight) y[u] = y[u] * w4[u] + b4[u];
+          if (p.round_norm_bf16) y[u] = bf16_round(y[u]);
+          if (p.scale) y[u] = __fadd_rn(__fmul_rn(y[u], __fadd_rn(1.0f, sc4[u])), sh4[u]);
+        }
+        if (p.out_is_bf16) {
+          uint2 o = make_uint2(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]));
+          *reinterpret_cast<uint2*>(static_cast<bf16*>(p.out) + static_cast<size_t>(row) * p.ldo + c) = o;
+        } else {
+          *reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + c) = make_float4(y[0], y[1], y[2], y[3]);
+        }
+      }
+    }
+    if (!RING) break;
   }
 }
 
@@ -121,54 +173,88 @@ struct RmsArgs {
   int D; float eps;
 };
 
-__global__ void __launch_bounds__(RMS_THREADS) rms_norm_rope_kernel(RmsArgs p) {
+// RING: persistent CTAs with the shared-memory row ring of layer_norm_kernel (see there); results are bit-identical.
+template <bool RING>
+__global__ void __launch_bounds__(RMS_THREADS) rms_norm_rope_kernel(RmsArgs p, int rows) {
+  extern __shared__ __align__(128) uint8_t norm_ring[];
   __shared__ float red[32];
-  const int row = blockIdx.x;
+  __shared__ uint64_t full[NORM_RING];
   const int nvec = p.D >> 3;
-  bf16* xr = p.x + static_cast<size_t>(row) * p.ldx;
-  uint4 raw[RMS_MAXV];
-  float sq = 0.f;
-#pragma unroll
-  for (int i = 0; i < RMS_MAXV; ++i) {
-    const int idx = threadIdx.x + i * RMS_THREADS;
-    if (idx < nvec) {
-      raw[i] = *reinterpret_cast<const uint4*>(xr + idx * 8);
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float2 f = __bfloat1622float2(h[u]);
-        sq += f.x * f.x + f.y * f.y;
-      }
+  const uint32_t row_bytes = static_cast<uint32_t>(p.D) * 2;
+  const uint32_t slot_bytes = (row_bytes + 127u) & ~127u;
+  auto issue = [&](int i) {
+    const long long r = blockIdx.x + static_cast<long long>(i) * gridDim.x;
+    if (r < rows) {
+      const int sl = i % NORM_RING;
+      mbar_arrive_expect_tx(&full[sl], row_bytes);
+      bulk_g2s(norm_ring + sl * slot_bytes, p.x + r * p.ldx, row_bytes, &full[sl]);
     }
+  };
+  if (RING) {
+    if (threadIdx.x == 0) {
+      for (int sl = 0; sl < NORM_RING; ++sl) mbar_init(&full[sl], 1);
+      fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) for (int i = 0; i < NORM_RING - 1; ++i) issue(i);
   }
-  const float rstd = rsqrtf(block_sum<RMS_THREADS>(sq, red) / p.D + p.eps);
-#pragma unroll
-  for (int i = 0; i < RMS_MAXV; ++i) {
-    const int idx = threadIdx.x + i * RMS_THREADS;
-    if (idx < nvec) {
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
-      const int c = idx * 8;
-      uint32_t o[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float2 f = __bfloat1622float2(h[u]);
-        // (x.float() * rstd).type_as(x) * weight
-        float a = __fmul_rn(bf16_round(__fmul_rn(f.x, rstd)), p.weight[c + 2 * u]);
-        float b = __fmul_rn(bf16_round(__fmul_rn(f.y, rstd)), p.weight[c + 2 * u + 1]);
-        if (p.rope) {
-          const int pair = ((c + 2 * u) & 127) >> 1;                 // complex pair index inside the head
-          const double2 cs = *reinterpret_cast<const double2*>(p.rope + (static_cast<size_t>(row) * 64 + pair) * 2);
-          const double da = a, db = b;
-          const float re = static_cast<float>(da * cs.x - db * cs.y);
-          const float im = static_cast<float>(da * cs.y + db * cs.x);
-          a = re; b = im;
-        }
-        o[u] = pack_bf16x2(a, b);
-      }
-      *reinterpret_cast<uint4*>(xr + c) = make_uint4(o[0], o[1], o[2], o[3]);
+  for (int it = 0;; ++it) {
+    const long long row_ll = blockIdx.x + static_cast<long long>(it) * gridDim.x;
+    if (row_ll >= rows) break;
+    const int row = static_cast<int>(row_ll);
+    bf16* xr = p.x + static_cast<size_t>(row) * p.ldx;
+    const bf16* src = xr;
+    if (RING) {
+      if (threadIdx.x == 0) issue(it + NORM_RING - 1);
+      mbar_wait(&full[it % NORM_RING], (it / NORM_RING) & 1);
+      src = reinterpret_cast<const bf16*>(norm_ring + (it % NORM_RING) * slot_bytes);
     }
+    uint4 raw[RMS_MAXV];
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < RMS_MAXV; ++i) {
+      const int idx = threadIdx.x + i * RMS_THREADS;
+      if (idx < nvec) {
+        raw[i] = *reinterpret_cast<const uint4*>(src + idx * 8);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float2 f = __bfloat1622float2(h[u]);
+          sq += f.x * f.x + f.y * f.y;
+        }
+      }
+    }
+    const float rstd = rsqrtf(block_sum<RMS_THREADS>(sq, red) / p.D + p.eps);
+#pragma unroll
+    for (int i = 0; i < RMS_MAXV; ++i) {
+      const int idx = threadIdx.x + i * RMS_THREADS;
+      if (idx < nvec) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
+        const int c = idx * 8;
+        uint32_t o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float2 f = __bfloat1622float2(h[u]);
+          // (x.float() * rstd).type_as(x) * weight
+          float a = __fmul_rn(bf16_round(__fmul_rn(f.x, rstd)), p.weight[c + 2 * u]);
+          float b = __fmul_rn(bf16_round(__fmul_rn(f.y, rstd)), p.weight[c + 2 * u + 1]);
+          if (p.rope) {
+            const int pair = ((c + 2 * u) & 127) >> 1;                 // complex pair index inside the head
+            const double2 cs = *reinterpret_cast<const double2*>(p.rope + (static_cast<size_t>(row) * 64 + pair) * 2);
+            const double da = a, db = b;
+            const float re = static_cast<float>(da * cs.x - db * cs.y);
+            const float im = static_cast<float>(da * cs.y + db * cs.x);
+            a = re; b = im;
+          }
+          o[u] = pack_bf16x2(a, b);
+        }
+        *reinterpret_cast<uint4*>(xr + c) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    if (!RING) break;
   }
 }
+
 
 // ---------------------------------------------------------- q|k|v: RMSNorm + RoPE + scatter to the peers (Ulysses)
 // Same per-element arithmetic as rms_norm_rope_kernel (the results are bit-identical); instead of writing in place the
@@ -504,7 +590,22 @@ extern "C" int wf_layer_norm(const void* x, int ldx, int x_is_bf16, void* out, i
              "wf_layer_norm: scale/shift and weight/bias come in pairs");
   WF_REQUIRE(rows_per_group >= 0, "wf_layer_norm: rows_per_group must be >= 0");
   LnArgs a{x, ldx, x_is_bf16, out, ldo, out_is_bf16, scale, shift, weight, bias, D, eps, round_norm_bf16, rows_per_group};
-  layer_norm_kernel<<<rows, LN_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  const auto al16 = [](const void* q) { return q == nullptr || reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+  WF_REQUIRE(al16(scale) && al16(shift) && al16(weight) && al16(bias), "wf_layer_norm: scale / shift / weight / bias must be 16-byte aligned");
+  const int esize = x_is_bf16 ? 2 : 4;
+  const int slot = (D * esize + 127) & ~127;
+  // many rows: persistent CTAs with a shared-memory row ring (cp.async.bulk needs 16-byte aligned rows)
+  if (rows >= 4 * sm_count() && al16(x) && (static_cast<long long>(ldx) * esize) % 16 == 0 && (D * esize) % 16 == 0) {
+    static bool configured = false;
+    if (!configured) {
+      WF_CUDA_OK(cudaFuncSetAttribute(layer_norm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NORM_RING * 32768));
+      configured = true;
+    }
+    const int grid = std::min(rows, 3 * sm_count());
+    layer_norm_kernel<true><<<grid, LN_THREADS, NORM_RING * slot, static_cast<cudaStream_t>(stream)>>>(a, rows);
+  } else {
+    layer_norm_kernel<false><<<rows, LN_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a, rows);
+  }
   WF_LAUNCH_OK();
   return WF_OK;
 }
@@ -515,7 +616,18 @@ extern "C" int wf_rms_norm_rope(void* x, int ldx, const float* weight, const dou
   WF_REQUIRE(D % 8 == 0 && D <= 8 * RMS_THREADS * RMS_MAXV && ldx % 8 == 0, "wf_rms_norm_rope: dim must be a multiple of 8 and <= 8192");
   WF_REQUIRE(rope == nullptr || D % 128 == 0, "wf_rms_norm_rope: RoPE needs head_dim 128");
   RmsArgs a{static_cast<bf16*>(x), ldx, weight, rope, D, eps};
-  rms_norm_rope_kernel<<<rows, RMS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  if (rows >= 4 * sm_count() && reinterpret_cast<uintptr_t>(x) % 16 == 0 && D % 8 == 0) {
+    static bool configured = false;
+    if (!configured) {
+      WF_CUDA_OK(cudaFuncSetAttribute(rms_norm_rope_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NORM_RING * 16384));
+      configured = true;
+    }
+    const int slot = (D * 2 + 127) & ~127;
+    const int grid = std::min(rows, 4 * sm_count());
+    rms_norm_rope_kernel<true><<<grid, RMS_THREADS, NORM_RING * slot, static_cast<cudaStream_t>(stream)>>>(a, rows);
+  } else {
+    rms_norm_rope_kernel<false><<<rows, RMS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a, rows);
+  }
   WF_LAUNCH_OK();
   return WF_OK;
 }
