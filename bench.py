@@ -42,7 +42,12 @@ def emit(line: dict):
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 
-METRIC = "denoising_steps_per_sec_wan2.1_i2v_14b_480p_81f_irr_flf_dsg"
+METRIC = "denoising_steps_per_sec_wan2.1_i2v_14b_480p_81f_irr_flf_dsg"     # the default configuration (BASELINE.json configs[1])
+
+
+def metric_name(args):
+    res = {(480, 832): "480p", (720, 1280): "720p"}.get((args.height, args.width), f"{args.height}x{args.width}")
+    return f"denoising_steps_per_sec_wan2.1_i2v_14b_{res}_{args.frames}f_irr_flf_dsg"
 UNIT = "steps/s"
 
 
@@ -166,7 +171,7 @@ def run_reference(args):
     base["value"] = v
     f, h, w = (args.frames - 1) // 4 + 1, args.height // 8, args.width // 8
     emit({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric_name(args), "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"Wan2.1-I2V-14B {args.height}x{args.width} {args.frames}f, IRR+FLF+DSG, guided:plain 3:7 "
@@ -289,7 +294,7 @@ def run_ours(args):
         ach = flops / (mean_ms / 1000.0) / 1e12
         traffic = None
         pj = os.path.join(ROOT, "profiles", "ncu_summary.json")
-        if os.path.exists(pj):
+        if os.path.exists(pj) and (args.height, args.width, args.frames, world) == (480, 832, 81, 1):   # the captured shape
             traffic = json.load(open(pj)).get("attention_dram_bytes_per_launch")
         roof = {"kernel": "attention_tcgen05 (self-attention)", "bound": "tensor", "achieved": ach, "peak": pk["bf16"],
                 "unit": "TFLOP/s", "frac": ach / pk["bf16"], "traffic": traffic, "peak_source": pk["src"] + " sustained cuBLAS bf16",
@@ -297,7 +302,7 @@ def run_ours(args):
                 "share_of_step": sum(attn_ms) / ms}
     value = K / (ms / 1000.0)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+        "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"Wan2.1-I2V-14B {args.height}x{args.width} {args.frames}f guided sampling (IRR+FLF+DSG), "
                                f"{k_guided} guided + {K - k_guided} plain timed steps (the 15:35 mix of the 50-step run)",
