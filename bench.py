@@ -110,7 +110,7 @@ class ClockSampler:
 # CPU baseline: the oracle (port of the reference's algorithm) on the host cores, bounded sample, extrapolated
 # ----------------------------------------------------------------------------------------------------------------
 
-def cpu_baseline(args, budget_s: float = 20.0):
+def cpu_baseline(args, budget_s: float = float(os.environ.get("WF_CPU_BUDGET_S", "20"))):
     """Times one full-width Wan-14B DiT block and one small VAE round trip with the oracle on all host cores and
     extrapolates to steps/s of the benchmark configuration (attention scales with L^2, the rest with L; the VAE with
     pixels x frames).  Baseline only."""

@@ -1,0 +1,29 @@
+"""bench.py's driver contract, checked without a GPU through the reference arm: stdout carries exactly ONE line, it is
+JSON, and it has the keys the driver reads (library banners - NCCL prints one to stdout - must not leak onto it)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_json_line():
+    env = dict(os.environ, WF_CPU_BUDGET_S="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "steps/s" and d["higher_is_better"] is True
+    assert d["metric"] == "denoising_steps_per_sec_wan2.1_i2v_14b_480p_81f_irr_flf_dsg"
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_non_zero_ranks_of_the_reference_arm_stay_silent():
+    env = dict(os.environ, WF_CPU_BUDGET_S="1", RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip() == ""
