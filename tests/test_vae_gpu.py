@@ -101,24 +101,31 @@ def test_vae_rejects_cpu(cuda):
         m.decode(torch.zeros(1, 16, 1, 4, 4))
 
 
-@pytest.mark.parametrize("world,F_,H,W", [(2, 5, 64, 48), (4, 9, 96, 32), (8, 5, 128, 32), (3, 1, 48, 32)])
+@pytest.mark.parametrize("world,F_,H,W", [(2, 5, 64, 48), (4, 9, 96, 32), (8, 5, 128, 32), (3, 1, 48, 32), (8, 33, 64, 32)])
 def test_row_sharded_vae_is_bit_identical(cuda, world, F_, H, W):
-    """enable_row_sharding: every rank's slab (rows + recomputed halo), stitched in rank order, equals the single-GPU
-    evaluation bit for bit - simulated here by running the ranks one after the other on one GPU."""
+    """enable_row_sharding: the stages of the sharded evaluation (row slabs with recomputed halo; the mid-block attention
+    by frames), every rank's share stitched in rank order between stages, equal the single-GPU evaluation bit for bit -
+    simulated here by running the ranks one after the other on one GPU (tools/ulysses_check.py does it with real ranks)."""
     from worldforge_b200 import vae as wvae
     m = wvae.WfWanVAE.random_init(cuda, dim=8, seed=3)
     video = (torch.rand(1, 3, F_, H, W, generator=g(21)) * 2 - 1).to(cuda)
     z = torch.randn(1, 16, (F_ - 1) // 4 + 1, H // 8, W // 8, generator=g(22)).to(cuda)
     want_mu = m.encode(video).latent_dist.mode()
     want_dec = m.decode(z)[0]
-    (enc_seg, enc_tail), (dec_head, dec_seg) = m._split_plans()
-    b = m.row_bounds(H // 8, world)
-    assert b[0] == 0 and b[-1] == H // 8 and all(b[r + 1] > b[r] for r in range(world))
-    parts = [m.encode_rows(video[0], b[r], b[r + 1]) for r in range(world)]
-    h = m._run(enc_tail, wvae.assemble_rows(parts, 1))
-    mu = wvae.lib.cl_to_planar(m._conv(h, "conv1", wvae.TAPS_1, 2 * m.z_dim), m.z_dim).unsqueeze(0)
+
+    def run(which, full):
+        stages = m.sharded_stages(which, full, world)
+        assert len(stages) == 3                                     # rows | frames (attention) | rows
+        for stage in stages:
+            parts, dim = [], None
+            for r in range(world):
+                part, dim, bounds = stage(r, full)
+                assert part.shape[dim] == bounds[r + 1] - bounds[r]
+                parts.append(part)
+            full = wvae.assemble_rows(parts, dim)
+        return full
+
+    mu = wvae.lib.cl_to_planar(run("enc", video[0]).contiguous(), m.z_dim).unsqueeze(0)
     assert torch.equal(mu, want_mu)
     x = m._conv(wvae.lib.planar_to_cl(z[0].contiguous(), m.z_dim), "conv2", wvae.TAPS_1, m.z_dim)
-    x = m._run(dec_head, x)
-    parts = [m.decode_rows(x, 8 * b[r], 8 * b[r + 1]) for r in range(world)]
-    assert torch.equal(wvae.assemble_rows(parts, 2).unsqueeze(0), want_dec)
+    assert torch.equal(run("dec", x).unsqueeze(0), want_dec)

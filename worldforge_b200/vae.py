@@ -363,29 +363,75 @@ class WfWanVAE:
         lo, hi = need[-1]
         return x[:, lo - a:hi - a], lo
 
-    def _split_plans(self):
-        """encoder: (row-sharded layers up to the last downsample, replicated tail); decoder: (replicated layers up to
-        the first upsample, row-sharded rest)."""
-        e = max(i for i, p in enumerate(self.enc_plan) if p[0] in self.DOWNS) + 1
-        d = min(i for i, p in enumerate(self.dec_plan) if p[0] in self.UPS)
-        return (self.enc_plan[:e], self.enc_plan[e:]), (self.dec_plan[:d], self.dec_plan[d:])
+    def _segments(self, plan):
+        """Cut a layer plan at its attention blocks: [("rows", layers), ("frames", [attn]), ("rows", layers), ...].
+        Everything but the mid-block attention is local in space (row-shardable with a halo); the attention is one
+        full-frame softmax per frame and shards by frames instead."""
+        segs, cur = [], []
+        for layer in plan:
+            if layer[0] == "attn":
+                if cur:
+                    segs.append(("rows", cur))
+                segs.append(("frames", [layer]))
+                cur = []
+            else:
+                cur.append(layer)
+        if cur:
+            segs.append(("rows", cur))
+        return segs
 
-    def encode_rows(self, x_planar: torch.Tensor, lo: int, hi: int) -> torch.Tensor:
-        """x_planar [3,F,H,W] -> features [T', hi-lo, W/8, C] of latent rows [lo, hi) after the last downsample."""
-        (seg, _), _ = self._split_plans()
-        need, _ = self._needed_rows(seg, (lo, hi), x_planar.shape[2])
-        a, b = need[0]
-        cl = lib.planar_to_cl(x_planar[:, :, a:b].to(F32).contiguous(), 4)
-        y, _ = self._run_rows(seg, cl, a, need)
-        return y
+    def sharded_stages(self, which: str, x: torch.Tensor, world: int):
+        """The sharded evaluation of encode (``which='enc'``, x = [3,F,H,W] planar video) or decode (``'dec'``, x =
+        [T,h,w,z] channels-last output of conv2) as a list of stages.  A stage is ``fn(rank, full) -> (local, dim, bounds)``:
+        rank's share of the stage output computed from the stage's full (replicated) input, to be gathered along ``dim``
+        with ``bounds`` before the next stage.  The last stage's gathered output is the result (encode: channels-last
+        [T',h,w,2z] after conv1; decode: planar [3,F,H,W]).  ``encode`` / ``decode`` run the stages with an all-gather
+        between them; the parity test runs every rank's share on one GPU and stitches."""
+        sc = self.spatial_scale
+        segs = self._segments(self.enc_plan if which == "enc" else self.dec_plan)
+        stages = []
+        if which == "enc":
+            h_lat = x.shape[2] // sc
+        else:
+            h_lat = x.shape[1]
+        rb = self.row_bounds(h_lat, world)
+        for si, (kind, layers) in enumerate(segs):
+            first, last = si == 0, si == len(segs) - 1
+            if kind == "frames":
+                def attn_stage(rank, full, layers=layers):
+                    fb = self.row_bounds(full.shape[0], world)          # frames split like rows: as evenly as possible
+                    kind_, name, cin, _ = layers[0]
+                    part = self._attn(full[fb[rank]:fb[rank + 1]].contiguous(), name, cin) if fb[rank + 1] > fb[rank] \
+                        else full[:0]
+                    return part, 0, fb
+                stages.append(attn_stage)
+                continue
+            # a row segment: its output resolution relative to the latent grid decides the row bounds
+            n_up = sum(1 for l in layers if l[0] in self.UPS)
+            n_down = sum(1 for l in layers if l[0] in self.DOWNS)
 
-    def decode_rows(self, x_mid: torch.Tensor, lo: int, hi: int) -> torch.Tensor:
-        """x_mid [T, h, w, C] (output of the replicated decoder head part) -> planar [3, F, hi-lo, W] of the decoded
-        rows [lo, hi) (full resolution)."""
-        _, (_, seg) = self._split_plans()
-        need, _ = self._needed_rows(seg, (lo, hi), x_mid.shape[1])
-        y, _ = self._run_rows(seg, x_mid, 0, need, final_planar_rows=(lo, hi))
-        return y
+            def row_stage(rank, full, layers=layers, first=first, last=last, n_up=n_up, n_down=n_down):
+                planar_in = which == "enc" and first                   # the video arrives planar [3,F,H,W]
+                h_in = full.shape[2] if planar_in else full.shape[1]
+                h_out = (h_in << n_up) >> n_down
+                f = h_out // h_lat                                     # output rows per latent row (1 or spatial_scale)
+                bounds = [f * v for v in rb]
+                lo, hi = bounds[rank], bounds[rank + 1]
+                need, _ = self._needed_rows(layers, (lo, hi), h_in)
+                a, b = need[0]
+                if planar_in:
+                    slab = lib.planar_to_cl(full[:, :, a:b].to(F32).contiguous(), 4)
+                else:
+                    slab = full[:, a:b].contiguous()
+                if which == "dec" and last:                            # the head writes the clamped planar clip
+                    y, _ = self._run_rows(layers, slab, a, need, final_planar_rows=(lo, hi))
+                    return y, 2, bounds
+                y, _ = self._run_rows(layers, slab, a, need)
+                if which == "enc" and last:                            # conv1 (1x1) on the rank's rows
+                    y = self._conv(y.contiguous(), "conv1", TAPS_1, 2 * self.z_dim)
+                return y, 1, bounds
+            stages.append(row_stage)
+        return stages
 
     def _all_gather_rows(self, local: torch.Tensor, dim: int, bounds: List[int]) -> torch.Tensor:
         """``local`` holds rows [bounds[r], bounds[r+1]) along ``dim``; returns the tensor with all rows, same on every rank."""
@@ -407,13 +453,14 @@ class WfWanVAE:
             raise lib.WfError("WfWanVAE runs on CUDA tensors only (no CPU fallback)")
         assert x.shape[0] == 1 and x.shape[1] == 3
         if self.shard is not None and self.shard.world > 1:
-            b = self.row_bounds(x.shape[3] // self.spatial_scale, self.shard.world)
-            part = self.encode_rows(x[0], b[self.shard.rank], b[self.shard.rank + 1])
-            h = self._run(self._split_plans()[0][1], self._all_gather_rows(part, 1, b))
+            h = x[0]
+            for stage in self.sharded_stages("enc", h, self.shard.world):
+                part, dim, bounds = stage(self.shard.rank, h)
+                h = self._all_gather_rows(part, dim, bounds)
         else:
             cl = lib.planar_to_cl(x[0].to(F32).contiguous(), 4)
             h = self._run(self.enc_plan, cl)
-        h = self._conv(h, "conv1", TAPS_1, 2 * self.z_dim)
+            h = self._conv(h, "conv1", TAPS_1, 2 * self.z_dim)
         mu = lib.cl_to_planar(h, self.z_dim)
         return SimpleNamespace(latent_dist=_Dist(mu.unsqueeze(0)))
 
@@ -431,11 +478,10 @@ class WfWanVAE:
             nt += 1 if up else 0
         F_out = (f - 1) * (2 ** nt) + 1
         if self.shard is not None and self.shard.world > 1:
-            sc = self.spatial_scale
-            b = [sc * v for v in self.row_bounds(h, self.shard.world)]
-            x = self._run(self._split_plans()[1][0], x)
-            part = self.decode_rows(x, b[self.shard.rank], b[self.shard.rank + 1])
-            return (self._all_gather_rows(part, 2, b).unsqueeze(0),)
+            for stage in self.sharded_stages("dec", x, self.shard.world):
+                part, dim, bounds = stage(self.shard.rank, x)
+                x = self._all_gather_rows(part, dim, bounds)
+            return (x.unsqueeze(0),)
         out = torch.empty(3, F_out, 8 * h, 8 * w, dtype=F32, device=z.device)
         self._run(self.dec_plan, x, final_planar=out)
         return (out.unsqueeze(0),)
