@@ -73,3 +73,36 @@ def test_layout_helpers_roundtrip():
             assert torch.equal(send[d, :, j], qkv[:, j * H * 128 + d * hp: j * H * 128 + (d + 1) * hp])
     back = ulysses.tokens_to_heads_layout(torch.stack([qkv[:, :H * 128].view(Ll, world, hp)[:, r] for r in range(world)]))
     assert torch.equal(back, qkv[:, :H * 128])
+
+
+def _peer_setup_worker(rank, world, port, ret):
+    """PeerSequenceParallel's set-up must end the same way on every rank: here rank 1's allocation fails (there is no GPU
+    at all in this test), and BOTH ranks must raise PeerSetupError instead of one of them waiting for the other."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from worldforge_b200 import lib, ulysses
+
+        class FakeBuffer:
+            def __init__(self, nbytes):
+                if rank == 1:
+                    raise lib.WfError("no device memory")
+                self.ptr, self.handle, self.nbytes = 4096, b"h" * 64, nbytes
+            open = staticmethod(lambda handle: 8192)
+
+        lib.PeerBuffer = FakeBuffer
+        try:
+            ulysses.PeerSequenceParallel(None, 64, 32, 4, torch.device("cpu"))
+            ret[rank] = "built"
+        except ulysses.PeerSetupError as ex:
+            ret[rank] = "agreed:" + str(ex)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_setup_failure_is_agreed_by_all_ranks():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_peer_setup_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    assert ret[0].startswith("agreed:") and ret[1].startswith("agreed:")
+    assert "no device memory" in ret[1] and "a peer could not" in ret[0]

@@ -310,8 +310,13 @@ class WfWanTransformer:
         if sp is not None and getattr(sp, "peer", False):
             if (L, Ll) not in self._psp:
                 from . import ulysses
-                self._psp[(L, Ll)] = ulysses.PeerSequenceParallel(sp.group, L, Ll, nh, self.device)
-            psp = self._psp[(L, Ll)]
+                try:
+                    self._psp[(L, Ll)] = ulysses.PeerSequenceParallel(sp.group, L, Ll, nh, self.device)
+                except ulysses.PeerSetupError as ex:   # raised on every rank alike: all of them keep the NCCL all-to-all form
+                    import sys
+                    print(f"[worldforge_b200] {ex}; using the NCCL all-to-all exchange", file=sys.stderr, flush=True)
+                    sp.peer = False
+            psp = self._psp.get((L, Ll))
 
         # patch embedding (bf16 token stream, held in fp32 storage)
         lib.patchify(hs, B.cols)

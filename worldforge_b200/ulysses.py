@@ -72,6 +72,10 @@ class SequenceParallel:
         return tokens_to_heads_layout(back)
 
 
+class PeerSetupError(RuntimeError):
+    """Raised on EVERY rank when any rank could not build the peer-memory exchange."""
+
+
 class PeerSequenceParallel(SequenceParallel):
     """The same exchange without collectives on the data path: the kernels that produce q|k|v and the attention output
     store straight into the consuming rank's memory over NVLink (CUDA IPC peer mappings of ``wf_peer_alloc`` buffers).
@@ -94,10 +98,29 @@ class PeerSequenceParallel(SequenceParallel):
         P, hl = self.world, heads // self.world
         self.L, self.Ll, self.heads, self.hl, self.device = L, Ll, heads, hl, device
         self.ld_full, self.ld_att = 3 * hl * 128, heads * 128
-        self._bufs = [lib.PeerBuffer(L * self.ld_full * 2), lib.PeerBuffer(Ll * self.ld_att * 2), lib.PeerBuffer(Ll * self.ld_att * 2)]
+        # Set-up is collective and every step may fail on its own rank (allocation, IPC export, mapping a peer): the ranks
+        # exchange what they have, try, and then AGREE on the outcome - either all of them use peer memory or all of them
+        # raise PeerSetupError (the caller then keeps the NCCL all-to-all form; nothing hangs on a half-built exchange).
+        err = None
+        try:
+            self._bufs = [lib.PeerBuffer(L * self.ld_full * 2), lib.PeerBuffer(Ll * self.ld_att * 2), lib.PeerBuffer(Ll * self.ld_att * 2)]
+            mine = [b.handle for b in self._bufs]
+        except Exception as ex:                       # noqa: BLE001 - reported to every rank below
+            err, mine = ex, None
         handles = [None] * P
-        dist.all_gather_object(handles, [b.handle for b in self._bufs], group=self.group)
-        self._ptrs = [[self._bufs[i].ptr if r == self.rank else lib.PeerBuffer.open(handles[r][i]) for r in range(P)] for i in range(3)]
+        dist.all_gather_object(handles, mine, group=self.group)
+        if err is None and all(h is not None for h in handles):
+            try:
+                self._ptrs = [[self._bufs[i].ptr if r == self.rank else lib.PeerBuffer.open(handles[r][i]) for r in range(P)]
+                              for i in range(3)]
+            except Exception as ex:                   # noqa: BLE001
+                err = ex
+        elif err is None:
+            err = RuntimeError("a peer could not allocate or export its buffers")
+        oks = [None] * P
+        dist.all_gather_object(oks, err is None, group=self.group)
+        if not all(oks):
+            raise PeerSetupError(f"peer-memory exchange unavailable on rank(s) {[r for r, ok in enumerate(oks) if not ok]}: {err}")
         self.full = self._bufs[0].tensor((L, self.ld_full), torch.bfloat16, device)
         self.att = [self._bufs[1 + i].tensor((Ll, self.ld_att), torch.bfloat16, device) for i in range(2)]
         self._flag = torch.zeros(1, device=device)
