@@ -108,3 +108,46 @@ def test_gather_of_uneven_row_slabs_gloo():
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
+
+
+class _StagedStandIn(_StandIn):
+    """Stand-ins for the pieces sharded_stages drives besides the row slabs: a full-frame 'attention' (every output pixel
+    depends on the whole frame - it is only right if the rows were gathered before and the frames split after) and the
+    final 1x1 convolution."""
+    z_dim, spatial_scale = 1, 8
+
+    def __init__(self, w):
+        super().__init__(w)
+        self.enc_plan = ENC + [("res", "r", 0, 0), ("attn", "a", 0, 0), ("res", "r", 0, 0), ("head", "h", 0, 0)]
+        self.dec_plan = []
+
+    def _attn(self, x, name, c):
+        return x + x.mean(dim=(1, 2), keepdim=True) * torch.arange(1, x.shape[1] + 1, dtype=x.dtype).view(1, -1, 1, 1)
+
+    def _conv(self, x, wname, taps, cout, **kw):
+        return 2.0 * x
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_encode_stages_rows_frames_rows(world, monkeypatch):
+    """sharded_stages('enc'): [rows | frames | rows] with a gather between stages reproduces the unsharded evaluation."""
+    monkeypatch.setattr(wvae.lib, "planar_to_cl", lambda src, Cp: src.permute(1, 2, 3, 0).contiguous())
+    torch.manual_seed(1)
+    m = _StagedStandIn(torch.randn(1, 1, 3, 3) * 0.3)               # fp32: the first stage casts the video like the engine does
+    video = torch.randn(1, 5, 96, 16)                               # planar [C=1, F, H, W]
+    # the reference evaluation, layer by layer (attention in its place)
+    x = video.permute(1, 2, 3, 0)
+    for layer in m.enc_plan:
+        x = m._attn(x, "a", 0) if layer[0] == "attn" else m._run([layer], x)
+    want = m._conv(x, "conv1", None, 2)
+    stages = m.sharded_stages("enc", video, world)
+    assert len(stages) == 3
+    full = video
+    for stage in stages:
+        parts, dim = [], None
+        for r in range(world):
+            part, dim, bounds = stage(r, full)
+            assert part.shape[dim] == bounds[r + 1] - bounds[r]
+            parts.append(part)
+        full = wvae.assemble_rows(parts, dim)
+    torch.testing.assert_close(full, want, rtol=1e-5, atol=1e-5)    # torch's CPU convolution may block a cropped input differently
