@@ -205,6 +205,16 @@ int wf_latent_norm_replace(const float* enc, const void* x0, int is_bf16, void* 
  *          ((n+1)*127.5).clip(0,255), truncated. */
 long long wf_quantise_workspace_bytes(void);
 int wf_quantise_u8(const void* x, int is_bf16, unsigned char* out, long long n, int mode, void* workspace, void* stream);
+/* FLF channel scoring on the device (reference: cv2.calcOpticalFlowFarneback(prev, next, None, 0.5, 3, 15, 3, 5, 1.2, 0) per
+ * consecutive frame pair, scheduling_unipc_multistep_clean.py:220-224, and the flow metrics :541-604).  clips_u8: uint8
+ * [clips][T][H][W]; flow: fp32 [clips][T-1][H][W][2] (dx, dy).  Only frames whose Farneback pyramid has ONE level
+ * (min(H, W) < 64: the 60 x 104 latent frames of the 480p configuration); restated in oracle/farneback.py, pinned to OpenCV. */
+long long wf_farneback_workspace_bytes(int clips, int T, int H, int W);
+int wf_farneback_u8(const unsigned char* clips_u8, int clips, int T, int H, int W, int winsize, int iterations, float* flow,
+                    void* workspace, void* stream);
+/* per channel: mean end-point error, mean outlier indicator (epe > 3 and epe > 0.05 |ref|), mean angular error in degrees
+ * between two flow fields [channels][per_channel][2]; out3: fp32 [channels][3]. */
+int wf_flow_metrics(const float* flow_ref, const float* flow_cand, float* out3, int channels, long long per_channel, void* stream);
 /* LongCat CFG-zero + sign flip (pipeline_longcat_video.py:374-383, 875-888), fp32:
  * st = <cond,uncond>/(|uncond|^2 + 1e-8); out = -(uncond*st + scale*(cond - uncond*st)).  workspace: wf_dsg_workspace_bytes().
  * stats (device float[1] or NULL) receives st. */

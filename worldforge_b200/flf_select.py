@@ -7,10 +7,12 @@ latents with that of the model's prediction, after quantising each channel to ui
 
 * the min-max quantisation of both 16-channel tensors runs on the GPU (``wf_quantise_u8``,
   two passes over 2 MB) so 4 MB of uint8 cross PCIe instead of 16 MB of fp32 in 32 copies;
-* Farneback itself stays OpenCV on the host - it is the reference's own third-party dependency
-  for this step and its discrete outcome (an argsort over 16 scores) must not drift
-  (SURVEY.md §7 "hard parts", §8f item 1) - but the 640 independent frame pairs are spread over
-  a thread pool (OpenCV releases the GIL);
+* Farneback is OpenCV on the host by default - the reference's own third-party dependency for this
+  step, whose discrete outcome (an argsort over 16 scores) must not drift - with the 640 independent
+  frame pairs spread over a thread pool (OpenCV releases the GIL).  ``device_flow`` / WF_FLF_GPU=1
+  runs it on the GPU instead (``wf_farneback_u8`` + ``wf_flow_metrics``: 2.3 ms against 81 ms for a
+  16-channel x 21-frame call; flows equal to OpenCV's to ~3e-6 px, identical selections in
+  tests/test_flow_gpu.py; SURVEY.md §8f item 1);
 * the flow metrics (M-EPE / Fl-all / M-AE, :541-604) are evaluated where the flows already are,
   on the host, in the same fp32 torch expressions;
 * steps whose policy cannot select anything (step <= 5, :412-417) skip the flow computation.
@@ -37,6 +39,15 @@ def _flow_pair(args):
     return cv2.calcOpticalFlowFarneback(a, b, None, **_FARNEBACK)
 
 
+def similarity_from_means(mean_epe: torch.Tensor, mean_outlier: torch.Tensor, mean_angle: torch.Tensor) -> float:
+    """(:590-604) the three normalised error terms and their weighted sum, fp32 like the reference."""
+    n_epe = torch.clamp(mean_epe / 10.0, 0.0, 1.0)
+    n_fl = torch.clamp(mean_outlier / 0.5, 0.0, 1.0)
+    n_ae = torch.clamp(mean_angle / 30.0, 0.0, 1.0)
+    err = 0.45 * n_epe + 0.45 * n_fl + 0.1 * n_ae
+    return torch.clamp(1.0 - err, 0.0, 1.0).item()
+
+
 def flow_similarity(ref_flow: torch.Tensor, chan_flow: torch.Tensor) -> float:
     """[T-1, 2, H, W] fp32 flows -> similarity in [0,1] (:541-604)."""
     d = ref_flow - chan_flow
@@ -47,11 +58,7 @@ def flow_similarity(ref_flow: torch.Tensor, chan_flow: torch.Tensor) -> float:
     cos = torch.clamp(dot / (rn * cn + 1e-8), -1.0, 1.0)
     ang = torch.acos(cos) * 180.0 / torch.pi
     outlier = (epe > 3.0) & (epe > rn * 0.05)
-    n_epe = torch.clamp(epe.mean() / 10.0, 0.0, 1.0)
-    n_fl = torch.clamp(outlier.float().mean() / 0.5, 0.0, 1.0)
-    n_ae = torch.clamp(ang.mean() / 30.0, 0.0, 1.0)
-    err = 0.45 * n_epe + 0.45 * n_fl + 0.1 * n_ae
-    return torch.clamp(1.0 - err, 0.0, 1.0).item()
+    return similarity_from_means(epe.mean(), outlier.float().mean(), ang.mean())
 
 
 def selection_policy(scores, step: int) -> List[int]:
@@ -76,8 +83,13 @@ class FlowChannelSelector:
     cores are shared by all ranks of the box) and the scores are summed into every rank - each rank then takes the
     same decision from the same 16 numbers."""
 
-    def __init__(self, threads: int = 0, group=None, world: int = 1, rank: int = 0):
+    def __init__(self, threads: int = 0, group=None, world: int = 1, rank: int = 0, device_flow=None):
         self.group, self.world, self.rank = group, world, rank
+        # device_flow: Farneback + the flow metrics on the GPU (wf_farneback_u8 / wf_flow_metrics; frames whose pyramid has a
+        # single level only, i.e. the 60 x 104 latent frames of 480p) instead of OpenCV on host threads.  Opt-in this round
+        # (WF_FLF_GPU=1): the kernels agree with OpenCV to ~3e-6 px, the selections are equal on the test clips, but the
+        # full guided loop has only been measured with the OpenCV path.
+        self.device_flow = (os.environ.get("WF_FLF_GPU", "0") == "1") if device_flow is None else bool(device_flow)
         self.threads = threads or max(1, min(32, (os.cpu_count() or 8) // max(world, 1)))
         self._pool = None
         self.last_scores = None
@@ -101,14 +113,24 @@ class FlowChannelSelector:
         pred_u8 = lib.quantise_u8(pred_x0.contiguous())
         nc = ref_u8.shape[1]
         c0, c1 = (self.rank * nc) // self.world, ((self.rank + 1) * nc) // self.world
+        if self.device_flow and 10 <= min(ref_u8.shape[-2:]) < 64 and c1 > c0:      # single-level pyramid, frames >= 10 x 10
+            T, H, W = ref_u8.shape[2:]
+            clips = torch.cat([ref_u8[0, c0:c1], pred_u8[0, c0:c1]]).contiguous()       # [2C', T, H, W] uint8, on the device
+            flows = lib.farneback_u8(clips)                                              # [2C', T-1, H, W, 2]
+            means = lib.flow_metrics(flows[:c1 - c0].contiguous(), flows[c1 - c0:].contiguous()).cpu()   # [C', 3]: one small D2H
+            mine = [similarity_from_means(means[c, 0], means[c, 1], means[c, 2]) for c in range(c1 - c0)]
+            return self._share(mine, nc, c0, c1, pred_x0.device)
         both = torch.stack([ref_u8[0, c0:c1], pred_u8[0, c0:c1]]).cpu().numpy()       # one D2H copy, [2,C',T,H,W]
         ref_fl, pred_fl = self._flows(both[0]), self._flows(both[1])
         mine = [flow_similarity(ref_fl[c], pred_fl[c]) for c in range(ref_fl.shape[0])]
+        return self._share(mine, nc, c0, c1, pred_x0.device)
+
+    def _share(self, mine, nc: int, c0: int, c1: int, device) -> List[float]:
         if self.world > 1:
             import torch.distributed as dist
             t = torch.zeros(nc, dtype=torch.float64)
             t[c0:c1] = torch.tensor(mine, dtype=torch.float64)
-            t = t.to(pred_x0.device)
+            t = t.to(device)
             dist.all_reduce(t, group=self.group)                 # x + 0 is exact: every rank holds the same 16 scores
             mine = t.cpu().tolist()
         self.last_scores = mine

@@ -38,6 +38,8 @@ _SIGNATURES = {
     "wf_rms_norm_rope": [_vp, _i, _vp, _vp, _i, _i, _f, _vp],
     "wf_qkv_norm_rope_scatter": [_vp, _i, _vp, _vp, _vp, _i, _i, _f, _vp, _i, _i, _i, _vp],
     "wf_attention_bf16_peers": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _f, _vp],
+    "wf_farneback_u8": [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "wf_flow_metrics": [_vp, _vp, _vp, _i, _ll, _vp],
     "wf_peer_alloc": [_ll, _vp, _vp],
     "wf_peer_open": [_vp, _vp],
     "wf_peer_close": [_vp],
@@ -73,7 +75,8 @@ _SIGNATURES = {
     "wf_transpose_f32": [_vp, _vp, _i, _i, _i, _i, _vp],
 }
 _PLAIN = {"wf_last_error": (C.c_char_p, []), "wf_abi_version": (_i, []), "wf_sm_count": (_i, []),
-          "wf_dsg_workspace_bytes": (_ll, []), "wf_quantise_workspace_bytes": (_ll, [])}
+          "wf_dsg_workspace_bytes": (_ll, []), "wf_quantise_workspace_bytes": (_ll, []),
+          "wf_farneback_workspace_bytes": (_ll, [_i, _i, _i, _i])}
 
 
 def exported_symbols():
@@ -470,6 +473,26 @@ def quantise_u8(x, mode: int = 0, out=None):
     out = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if out is None else out
     ws = _workspace("quant", load().wf_quantise_workspace_bytes(), x.device)
     _call("wf_quantise_u8", _p(x), _is_bf16(x), _p(out), x.numel(), mode, _p(ws), _stream())
+    return out
+
+
+def farneback_u8(clips_u8, winsize: int = 15, iterations: int = 3):
+    """uint8 [clips, T, H, W] -> fp32 flows [clips, T-1, H, W, 2] (dx, dy) between consecutive frames (single-level Farneback)."""
+    assert clips_u8.dtype == torch.uint8 and clips_u8.is_contiguous() and clips_u8.dim() == 4
+    n, T, H, W = clips_u8.shape
+    flow = torch.empty(n, T - 1, H, W, 2, dtype=torch.float32, device=clips_u8.device)
+    ws = _workspace("farneback", load().wf_farneback_workspace_bytes(n, T, H, W), clips_u8.device)
+    _call("wf_farneback_u8", _p(clips_u8), n, T, H, W, winsize, iterations, _p(flow), _p(ws), _stream())
+    return flow
+
+
+def flow_metrics(flow_ref, flow_cand):
+    """[C, ..., 2] fp32 flow fields -> fp32 [C, 3]: mean EPE, mean outlier fraction, mean angular error (degrees) per channel."""
+    assert flow_ref.shape == flow_cand.shape and flow_ref.dtype == flow_cand.dtype == torch.float32
+    assert flow_ref.is_contiguous() and flow_cand.is_contiguous()
+    C_ = flow_ref.shape[0]
+    out = torch.empty(C_, 3, dtype=torch.float32, device=flow_ref.device)
+    _call("wf_flow_metrics", _p(flow_ref), _p(flow_cand), _p(out), C_, flow_ref.numel() // (2 * C_), _stream())
     return out
 
 
