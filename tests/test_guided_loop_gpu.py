@@ -56,3 +56,31 @@ def test_guided_loop_matches_oracle(cuda):
     # the DiT and VAE are identical in both runs; the only freedom the kernels have is the fp32 summation order of
     # the three DSG reductions (rounded to bf16 scalars), so the trajectories agree to bf16 resolution
     assert worst < 2e-3, worst
+
+
+def test_guided_loop_with_device_flow_scoring(cuda, monkeypatch):
+    """The same 14-step guided run with the FLF channel scoring on the device (Farneback + metrics kernels) and with OpenCV
+    on the host: the selections of every step and the latent trajectory must be IDENTICAL (latent frames 12 x 16: large
+    enough for the device path, single-level pyramid)."""
+    from worldforge_b200 import pipeline as wpipe, scheduler as wsched, synth
+    dcfg, vcfg, PD, PV, _ = _setup()
+    inp = synth.make_inputs(9, 96, 128, text_len=8, text_dim=32, img_len=3, img_dim=16)
+    to = lambda t: t.to(cuda)
+
+    def run(flag):
+        monkeypatch.setenv("WF_FLF_GPU", flag)
+        sched = wsched.WfUniPCScheduler(flow_shift=3.0)
+        hist = []
+        wpipe.denoise_loop(adapters.OracleTransformer(PD, dcfg, amp=True), adapters.OracleVAE(PV, vcfg), sched,
+                           to(inp.latents.clone()), to(inp.condition), to(inp.prompt_embeds), to(inp.negative_prompt_embeds),
+                           to(inp.image_embeds), 14, 4.0, video_ref=to(inp.video_ref), mask=to(inp.mask),
+                           generator=torch.Generator().manual_seed(42), on_step=lambda i, l: hist.append(l.detach().clone().cpu()),
+                           **KNOBS)
+        assert sched._selector is not None and sched._selector.device_flow == (flag == "1")
+        return sched.flf_log, hist
+
+    log_cv, hist_cv = run("0")
+    log_dev, hist_dev = run("1")
+    assert log_cv == log_dev, (log_cv, log_dev)
+    assert any(len(c) >= 1 for _, c in log_dev)
+    assert all(torch.equal(a, b) for a, b in zip(hist_cv, hist_dev))

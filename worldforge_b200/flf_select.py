@@ -7,12 +7,13 @@ latents with that of the model's prediction, after quantising each channel to ui
 
 * the min-max quantisation of both 16-channel tensors runs on the GPU (``wf_quantise_u8``,
   two passes over 2 MB) so 4 MB of uint8 cross PCIe instead of 16 MB of fp32 in 32 copies;
-* Farneback is OpenCV on the host by default - the reference's own third-party dependency for this
-  step, whose discrete outcome (an argsort over 16 scores) must not drift - with the 640 independent
-  frame pairs spread over a thread pool (OpenCV releases the GIL).  ``device_flow`` / WF_FLF_GPU=1
-  runs it on the GPU instead (``wf_farneback_u8`` + ``wf_flow_metrics``: 2.3 ms against 81 ms for a
-  16-channel x 21-frame call; flows equal to OpenCV's to ~3e-6 px, identical selections in
-  tests/test_flow_gpu.py; SURVEY.md §8f item 1);
+* Farneback - OpenCV in the reference, its own third-party dependency for this step, whose discrete
+  outcome (an argsort over 16 scores) must not drift - runs on the GPU for frames whose pyramid has a
+  single level (the 480p latent frames): ``wf_farneback_u8`` + ``wf_flow_metrics``, 2.3 ms against
+  81 ms for a 16-channel x 21-frame call, flows equal to OpenCV's to ~3e-6 px, identical scores and
+  selections (tests/test_flow_gpu.py).  Other frame sizes (720p: two pyramid
+  levels) and WF_FLF_GPU=0 keep OpenCV on the host, the 640 independent frame pairs spread over a
+  thread pool (OpenCV releases the GIL);
 * the flow metrics (M-EPE / Fl-all / M-AE, :541-604) are evaluated where the flows already are,
   on the host, in the same fp32 torch expressions;
 * steps whose policy cannot select anything (step <= 5, :412-417) skip the flow computation.
@@ -85,11 +86,11 @@ class FlowChannelSelector:
 
     def __init__(self, threads: int = 0, group=None, world: int = 1, rank: int = 0, device_flow=None):
         self.group, self.world, self.rank = group, world, rank
-        # device_flow: Farneback + the flow metrics on the GPU (wf_farneback_u8 / wf_flow_metrics; frames whose pyramid has a
-        # single level only, i.e. the 60 x 104 latent frames of 480p) instead of OpenCV on host threads.  Opt-in this round
-        # (WF_FLF_GPU=1): the kernels agree with OpenCV to ~3e-6 px, the selections are equal on the test clips, but the
-        # full guided loop has only been measured with the OpenCV path.
-        self.device_flow = (os.environ.get("WF_FLF_GPU", "0") == "1") if device_flow is None else bool(device_flow)
+        # device_flow: Farneback + the flow metrics on the GPU (wf_farneback_u8 / wf_flow_metrics) for frames whose pyramid has
+        # a single level (10 <= min side < 64: the 60 x 104 latent frames of 480p); other sizes, and WF_FLF_GPU=0, use OpenCV
+        # on host threads.  The kernels agree with OpenCV to ~3e-6 px; scores, selections and a 14-step guided trajectory are
+        # identical through either path (tests/test_flow_gpu.py, tests/test_guided_loop_gpu.py).
+        self.device_flow = (os.environ.get("WF_FLF_GPU", "1") == "1") if device_flow is None else bool(device_flow)
         self.threads = threads or max(1, min(32, (os.cpu_count() or 8) // max(world, 1)))
         self._pool = None
         self.last_scores = None
