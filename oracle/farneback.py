@@ -11,7 +11,8 @@ itself in tests/test_farneback_oracle.py.
 
 Facts of the call that matter (they fall out of the driver loop):
 * latent frames are 60 x 104 (480p) or 90 x 160 (720p): the pyramid loop stops at the first level whose smaller side would
-  drop under 32 pixels, so 60 x 104 runs ONE level (full resolution) and 90 x 160 two (45 x 80 then 90 x 160);
+  drop under 32 pixels, so 60 x 104 runs ONE level (full resolution) and 90 x 160 two (45 x 80 then 90 x 160; sigma of the
+  half-resolution level = (1/0.5 - 1)/2 = 0.5, kernel size cvRound(2.5)|1 = 3);
 * at scale 1 the pre-smoothing is GaussianBlur(3 x 3, sigma 0) = the fixed [1/4, 1/2, 1/4] kernel, reflect-101 border;
 * flags = 0: the flow update uses a 15 x 15 BOX window (replicated border), three iterations per level, matrices refreshed
   after the first two.
@@ -129,13 +130,6 @@ def update_matrices(R0: np.ndarray, R1: np.ndarray, flow: np.ndarray) -> np.ndar
     r3 = (r3 + ((r6 * dy).astype(f32) + (r5 * dx).astype(f32)).astype(f32)).astype(f32)
     B = len(_BORDER)
 
-    def edge(idx, size):
-        s = np.ones(size, dtype=f32)
-        for i in range(min(B, size)):
-            s[i] = (s[i] * _BORDER[i]).astype(f32)
-            s[size - 1 - i] = (s[size - 1 - i] * _BORDER[i]).astype(f32)
-        return s[idx]
-
     # (x < B ? border[x] : 1) * (x >= W-B ? border[W-x-1] : 1) * (y < B ? ...) * (y >= H-B ? ...), evaluated left to right
     sx_lo = np.where(xs < B, _BORDER[np.minimum(xs, B - 1)], one)
     sx_hi = np.where(xs >= W - B, _BORDER[np.clip(W - xs - 1, 0, B - 1)], one)
@@ -185,11 +179,53 @@ def _gauss3_reflect101(img: np.ndarray) -> np.ndarray:
     return (c + p[2:] * f32(0.25)).astype(f32)
 
 
+def _blur3(img: np.ndarray, k) -> np.ndarray:
+    """Separable 3-tap blur, BORDER_REFLECT_101, rows then columns, float32 (GaussianBlur with a 3 x 3 kernel)."""
+    f32 = np.float32
+    p = np.pad(img.astype(f32), ((0, 0), (1, 1)), mode="reflect")
+    r = (p[:, :-2] * f32(k[0]) + p[:, 1:-1] * f32(k[1])).astype(f32)
+    r = (r + p[:, 2:] * f32(k[2])).astype(f32)
+    p = np.pad(r, ((1, 1), (0, 0)), mode="reflect")
+    c = (p[:-2] * f32(k[0]) + p[1:-1] * f32(k[1])).astype(f32)
+    return (c + p[2:] * f32(k[2])).astype(f32)
+
+
+def _gauss_kernel3(sigma: float):
+    """cv::getGaussianKernel(3, sigma > 0, CV_32F)."""
+    e = np.exp(-1.0 / (2.0 * sigma * sigma))
+    s = 1.0 / (1.0 + 2.0 * e)
+    return np.array([e * s, s, e * s], dtype=np.float32)
+
+
+def _half(img: np.ndarray) -> np.ndarray:
+    """cv::resize(INTER_LINEAR) to exactly half the size (even sides): the mean of each 2 x 2 cell."""
+    return ((img[0::2, 0::2] + img[0::2, 1::2] + img[1::2, 0::2] + img[1::2, 1::2]) * np.float32(0.25)).astype(np.float32)
+
+
+def _double(x: np.ndarray) -> np.ndarray:
+    """cv::resize(INTER_LINEAR) to exactly twice the size: source coordinate (dst + 0.5) / 2 - 0.5, clamped taps."""
+    H, W = x.shape[:2]
+
+    def axis(n):
+        src = (np.arange(2 * n) + 0.5) / 2 - 0.5
+        i0 = np.floor(src).astype(np.int64)
+        w = (src - i0).astype(np.float32)
+        return np.clip(i0, 0, n - 1), np.clip(i0 + 1, 0, n - 1), w
+
+    y0, y1, wy = axis(H)
+    x0, x1, wx = axis(W)
+    wx, wy = wx[None, :, None], wy[:, None, None]
+    top = x[y0][:, x0] * (1 - wx) + x[y0][:, x1] * wx
+    bot = x[y1][:, x0] * (1 - wx) + x[y1][:, x1] * wx
+    return (top * (1 - wy) + bot * wy).astype(np.float32)
+
+
 def farneback(prev: np.ndarray, nxt: np.ndarray, pyr_scale: float = 0.5, levels: int = 3, winsize: int = 15,
               iterations: int = 3, poly_n: int = 5, poly_sigma: float = 1.2) -> np.ndarray:
-    """uint8 [H, W] x 2 -> float32 flow [H, W, 2] (dx, dy); flags = 0.  Only images whose pyramid has a single level are
-    restated (min(H, W) * pyr_scale < 32: the 60 x 104 latent frames of the 480p configuration); deeper pyramids need
-    OpenCV's GaussianBlur / resize at fractional scales and raise."""
+    """uint8 [H, W] x 2 -> float32 flow [H, W, 2] (dx, dy); flags = 0.  Pyramids of one level (min side * 0.5 < 32: the
+    60 x 104 latent frames of 480p - reproduced to a few 1e-6 px) and of two levels with even sides (90 x 160, 720p: the
+    half-resolution level is GaussianBlur(3 x 3, sigma 0.5) + a 2 x 2 mean, its flow comes back through a bilinear doubling
+    times 2 - reproduced to ~1e-4 px because OpenCV's filter engine rounds the blur differently).  Deeper pyramids raise."""
     H, W = prev.shape
     scale, k = 1.0, 0
     while k < levels:
@@ -197,13 +233,20 @@ def farneback(prev: np.ndarray, nxt: np.ndarray, pyr_scale: float = 0.5, levels:
         if W * scale < 32 or H * scale < 32:
             break
         k += 1
-    if k != 0:
-        raise NotImplementedError(f"{H}x{W}: the pyramid has {k + 1} levels; only the single-level case is restated")
-    R = [poly_exp(_gauss3_reflect101(img.astype(np.float32)), poly_n, poly_sigma) for img in (prev, nxt)]
-    flow = np.zeros((H, W, 2), dtype=np.float32)
-    M = update_matrices(R[0], R[1], flow)
-    for i in range(iterations):
-        flow = box_flow(M, winsize)
-        if i < iterations - 1:
-            M = update_matrices(R[0], R[1], flow)
+    if k > 1 or (k == 1 and (pyr_scale != 0.5 or H % 2 or W % 2)):
+        raise NotImplementedError(f"{H}x{W}: the pyramid has {k + 1} levels; one level, or two with even sides at scale 0.5, are restated")
+    flow = None
+    for lvl in range(k, -1, -1):
+        if lvl == 0:
+            imgs = [_gauss3_reflect101(img.astype(np.float32)) for img in (prev, nxt)]
+        else:
+            imgs = [_half(_blur3(img.astype(np.float32), _gauss_kernel3(0.5))) for img in (prev, nxt)]
+        R = [poly_exp(im, poly_n, poly_sigma) for im in imgs]
+        h, w = imgs[0].shape
+        flow = np.zeros((h, w, 2), dtype=np.float32) if flow is None else (_double(flow) * np.float32(1.0 / pyr_scale)).astype(np.float32)
+        M = update_matrices(R[0], R[1], flow)
+        for i in range(iterations):
+            flow = box_flow(M, winsize)
+            if i < iterations - 1:
+                M = update_matrices(R[0], R[1], flow)
     return flow

@@ -27,6 +27,10 @@ CASES = {
     "constant": lambda: (np.full((60, 104), 37, np.uint8), np.full((60, 104), 37, np.uint8)),
     "unrelated_smooth": lambda: (_smooth(4, sigma=2.0).astype(np.uint8), _smooth(5, sigma=2.0).astype(np.uint8)),
     "other_size": lambda: (_smooth(6, (40, 56)).astype(np.uint8), np.roll(_smooth(6, (40, 56)), 1, axis=0).astype(np.uint8)),
+    # 720p latent frames: two pyramid levels (45 x 80, then 90 x 160)
+    "720p_shift": lambda: (_smooth(7, (90, 160)).astype(np.uint8), np.roll(np.roll(_smooth(7, (90, 160)), 2, axis=0), -3, axis=1).astype(np.uint8)),
+    "720p_noise": lambda: ((np.random.default_rng(8).random((90, 160)) * 255).astype(np.uint8),
+                           (np.random.default_rng(9).random((90, 160)) * 255).astype(np.uint8)),
 }
 
 
@@ -50,7 +54,9 @@ def test_pieces_against_a_one_iteration_call():
 
 def test_deeper_pyramids_are_refused():
     with pytest.raises(NotImplementedError):
-        fb.farneback(np.zeros((90, 160), np.uint8), np.zeros((90, 160), np.uint8))
+        fb.farneback(np.zeros((180, 320), np.uint8), np.zeros((180, 320), np.uint8))       # three levels
+    with pytest.raises(NotImplementedError):
+        fb.farneback(np.zeros((91, 160), np.uint8), np.zeros((91, 160), np.uint8))         # two levels, odd side
 
 
 def test_channel_selection_is_the_same_from_either_flow():
