@@ -10,8 +10,11 @@ head<->sequence exchange of the reference's LongCat path (longcat_video/context_
 ONE collective for q, k and v instead of three and no second staging copy on the way in.  The 64-channel head output is
 scattered by each rank into a zero canvas and summed (8 MB).  Weights are replicated (33 GB of 180 GB).
 
-The scheduler, FLF and the VAE round trip operate on the replicated 8 MB latents and run identically on every rank (the
-causal VAE does not shard along frames: "replicas only").
+The scheduler and the per-pixel blend act on the replicated 8 MB latents and run identically on every rank; the VAE round
+trip is split by image rows (frames for its mid-block attention) and the FLF channel scoring by channels.
+
+``PeerSequenceParallel`` does the same exchange without collectives on the data path (NVLink peer stores from the producing
+kernels); ``SequenceParallel`` is the NCCL all-to-all form it falls back to when peer mapping is unavailable.
 """
 from __future__ import annotations
 
