@@ -230,16 +230,24 @@ int wf_cfg_zero(const float* cond, const float* uncond, float* out, float scale,
  * pixels per frame and ldc floats per pixel (planar_clamp = 1: planar [c][frame][out_H][out_W] with channel stride
  * planar_cstride, values clamped to [-1,1]).  resid (same addressing as out) is added when not NULL.
  * Replaces CausalConv3d.forward (vae.py:28-36), the Resample convs (:76-96,:128-140,:156-157), the 1x1 convs of
- * AttentionBlock (:246,:260) and, as a plain GEMM, its q.k^T and p.v products (:252-256). */
+ * AttentionBlock (:246,:260) and, as a plain GEMM, its q.k^T and p.v products (:252-256).
+ * Operand precision: kind::tf32 reads fp32 operands with the 13 low mantissa bits IGNORED (truncation) where cuDNN - the
+ * reference's fp32 VAE on a GPU - rounds to nearest; callers therefore hand this function operands already rounded to
+ * tf32 (weights at load; activations by their producer: round_tf32 of wf_rms_norm_cl / wf_planar_to_cl / wf_round_tf32,
+ * or round_out_tf32 = 1 here when every consumer of `out` is a convolution). */
 int wf_conv_tf32(const float* in, int in_T, int in_H, int in_W, int Cin, const float* weights, const float* bias,
                  int Cout, int ntaps, const signed char* taps, int T, int H, int W, int t_stride, int t_off, float* out,
                  int ldc, int out_H, int out_W, int t_mul, int c_split, int sy, int sx, int oy, int ox,
-                 const float* resid, int planar_clamp, long long planar_cstride, int tile_w, void* stream);
-/* RMS_norm (vae.py:51-54) over the channels of every pixel, optionally followed by SiLU (:195-197) */
+                 const float* resid, int planar_clamp, long long planar_cstride, int tile_w, int round_out_tf32,
+                 void* stream);
+/* RMS_norm (vae.py:51-54) over the channels of every pixel, optionally followed by SiLU (:195-197); round_tf32 = 1 stores
+   the result rounded to tf32 (it feeds a convolution) */
 int wf_rms_norm_cl(const float* x, int ldx, float* out, int ldo, const float* gamma, long long pixels, int C, int silu,
-                   void* stream);
-/* planar [C][n] -> channels-last [n][Cp] (channels C..Cp-1 zero) and back (first C of ld channels) */
-int wf_planar_to_cl(const float* src, float* dst, long long n, int C, int Cp, void* stream);
+                   int round_tf32, void* stream);
+/* planar [C][n] -> channels-last [n][Cp] (channels C..Cp-1 zero; optionally rounded to tf32) and back (first C of ld channels) */
+int wf_planar_to_cl(const float* src, float* dst, long long n, int C, int Cp, int round_tf32, void* stream);
+/* dst = src rounded to the nearest tf32 (ties away from zero), n a multiple of 4 */
+int wf_round_tf32(const float* src, float* dst, long long n, void* stream);
 int wf_cl_to_planar(const float* src, float* dst, long long n, int C, int ld, void* stream);
 /* [T][H][W][C] -> [T][H/2][W/2][4C]: turns ZeroPad2d((0,1,0,1)) + Conv2d(3, stride 2) (vae.py:87-96) into a 2x2-tap conv */
 int wf_space_to_depth(const float* src, float* dst, int T, int H, int W, int C, void* stream);
@@ -247,6 +255,10 @@ int wf_space_to_depth(const float* src, float* dst, int T, int H, int W, int C, 
 int wf_softmax_rows(float* x, int rows, int cols, int ld, float scale, void* stream);
 /* dst[c][r] = src[r][c] */
 int wf_transpose_f32(const float* src, float* dst, int R, int C, int lds, int ldd, void* stream);
+/* hi = x truncated to tf32 (13 low mantissa bits cleared), lo = x - hi: operands of the three-product fp32-accurate form of
+   the VAE mid-block attention matmuls (vae.py:252-256 - F.scaled_dot_product_attention on fp32 tensors; matmul TF32 is off
+   by default in torch, unlike cuDNN convolutions) */
+int wf_split_tf32(const float* x, float* hi, float* lo, long long n, void* stream);
 
 #ifdef __cplusplus
 }

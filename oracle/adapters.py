@@ -42,8 +42,13 @@ class _Dist:
 
 
 class OracleVAE:
-    def __init__(self, params, cfg: wan_vae.VaeConfig = wan_vae.WAN_VAE):
-        self.P, self.cfg = params, cfg
+    """``device=None``: evaluated on the CPU in fp32.  ``device='cuda'``: the same oracle functions evaluated on that
+    device - with ``torch.backends.cudnn.allow_tf32`` at its default (True) this is the arithmetic the reference's fp32
+    VAE has on a GPU (cuDNN tf32 convolutions), with it False it is exact fp32."""
+
+    def __init__(self, params, cfg: wan_vae.VaeConfig = wan_vae.WAN_VAE, device=None):
+        self.dev = torch.device("cpu") if device is None else torch.device(device)
+        self.P, self.cfg = {k: v.to(self.dev) for k, v in params.items()}, cfg
         self.dtype = torch.float32
         self.config = SimpleNamespace(z_dim=cfg.z_dim, latents_mean=list(wan_vae.LATENTS_MEAN[:cfg.z_dim]),
                                       latents_std=list(wan_vae.LATENTS_STD[:cfg.z_dim]))
@@ -51,11 +56,12 @@ class OracleVAE:
 
     def encode(self, x):
         assert x.shape[0] == 1
-        return SimpleNamespace(latent_dist=_Dist(wan_vae.encode_mode(self.P, self.cfg, x[0].cpu()).unsqueeze(0).to(x.device)))
+        mu = wan_vae.encode_mode(self.P, self.cfg, x[0].to(self.dev))
+        return SimpleNamespace(latent_dist=_Dist(mu.unsqueeze(0).to(x.device)))
 
     def decode(self, z, return_dict=False):
         assert z.shape[0] == 1
-        return (wan_vae.decode(self.P, self.cfg, z[0].cpu()).unsqueeze(0).to(z.device),)
+        return (wan_vae.decode(self.P, self.cfg, z[0].to(self.dev)).unsqueeze(0).to(z.device),)
 
 
 class OracleLongCatDit:

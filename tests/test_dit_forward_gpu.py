@@ -34,18 +34,46 @@ def test_forward_matches_oracle(cuda, grid, t):
     cfg = tiny_cfg()
     P = wan_dit.init_params(cfg, 7)
     x, ctx, clip = inputs(cfg, grid)
-    want = wan_dit.dit_forward(P, cfg, x[0], torch.tensor([t]), ctx[0], clip[0], amp=True)
+    want = wan_dit.dit_forward(P, cfg, x[0], torch.tensor([t]), ctx[0], clip[0], amp=True).to(torch.bfloat16).float()
+    truth = wan_dit.dit_forward(P, cfg, x[0], torch.tensor([t]), ctx[0], clip[0], amp=False)
     m = WfWanTransformer.from_state_dict(P, product_cfg(cfg), cuda)
     got = m(x.to(cuda), torch.tensor([t], device=cuda), ctx.to(cuda), clip.to(cuda), return_dict=False)[0]
     assert got.dtype == torch.bfloat16 and got.shape == (1, 16) + tuple(x.shape[2:])
     got = got[0].float().cpu()
-    rel = ((got - want).norm() / want.norm()).item()
-    # oracle-vs-reference spread under bf16 autocast is ~1e-3 (see tests/test_oracle_pinning.py); the
-    # output itself is rounded to bf16 (2^-9 relative per element, ~1.1e-3 rms)
-    assert rel < 4e-3, rel
+    rel = lambda a, b: ((a - b).norm() / b.norm()).item()
+    # measured floor instead of a constant: the engine may not be further from the exact (fp32) forward than the
+    # reference's own bf16 rounding points (oracle amp=True, output in the model dtype) put it
+    e_model, e_engine = rel(want, truth), rel(got, truth)
+    print(f"\n[floor] tiny DiT forward grid={grid}: model-vs-fp32 {e_model:.3e}  engine-vs-fp32 {e_engine:.3e}  "
+          f"engine-vs-model {rel(got, want):.3e}")
+    assert e_engine <= 1.1 * e_model, (e_engine, e_model)
+    assert rel(got, want) <= e_model
     # second call with the same embeddings hits the context K/V cache and must give the same answer
     got2 = m(x.to(cuda), torch.tensor([t], device=cuda), ctx.to(cuda), clip.to(cuda), return_dict=False)[0]
     assert torch.equal(got2[0].float().cpu(), got)
+    assert m._ctx_cache.hits_content == 1 and m._ctx_cache.misses == 1
+
+
+def test_second_prompt_of_equal_shape_is_not_served_from_the_cache(cuda):
+    """the first prompt's embeddings are freed, the second prompt's land on the recycled address with
+    _version 0 - the forward must still use the second prompt's K|V."""
+    from worldforge_b200.transformer import WfWanTransformer
+    cfg = tiny_cfg(layers=1)
+    P = wan_dit.init_params(cfg, 3)
+    grid = (2, 8, 8)
+    x, ctx_a, clip_a = inputs(cfg, grid, seed=1)
+    _, ctx_b, clip_b = inputs(cfg, grid, seed=2)
+    t = torch.tensor([400], device=cuda)
+    m = WfWanTransformer.from_state_dict(P, product_cfg(cfg), cuda)
+    def run(model, ctx, clip):
+        c, i = ctx.to(cuda), clip.to(cuda)               # temporaries: freed on return, their blocks are recycled
+        return model(x.to(cuda), t, c, i, return_dict=False)[0].float().cpu()
+    out_a = run(m, ctx_a, clip_a)
+    out_b = run(m, ctx_b, clip_b)
+    fresh = WfWanTransformer.from_state_dict(P, product_cfg(cfg), cuda)
+    assert torch.equal(out_b, run(fresh, ctx_b, clip_b))
+    assert not torch.equal(out_a, out_b)
+    assert torch.equal(run(m, ctx_a, clip_a), out_a)      # both prompts stay cached
 
 
 def test_diffusers_key_names(cuda):

@@ -23,11 +23,22 @@ def test_two_guided_steps_config1_shape(cuda):
     args = lambda: (to(inp.latents.clone()), to(inp.condition), to(inp.prompt_embeds), to(inp.negative_prompt_embeds),
                     to(inp.image_embeds), 2, 4.0)
 
-    want = []
-    o_sched = unipc.OracleUniPC(flow_shift=3.0)
-    opipe.denoise_loop(adapters.OracleTransformer(PD, dcfg, amp=True), adapters.OracleVAE(PV, vcfg), o_sched, *args(),
-                       video_ref=to(inp.video_ref), mask=to(inp.mask), generator=torch.Generator().manual_seed(42),
-                       on_step=lambda i, l: want.append(l.float().cpu()), **knobs)
+    def oracle_run(amp, vae_device, tf32):
+        """The oracle loop with (amp, tf32) = (True, True): the reference's GPU arithmetic (bf16 autocast DiT, cuDNN tf32
+        VAE convolutions); (False, False): exact fp32 inside both networks, same pipeline dtype flow."""
+        old = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        try:
+            out, sched = [], unipc.OracleUniPC(flow_shift=3.0)
+            opipe.denoise_loop(adapters.OracleTransformer(PD, dcfg, amp=amp), adapters.OracleVAE(PV, vcfg, device=vae_device),
+                               sched, *args(), video_ref=to(inp.video_ref), mask=to(inp.mask),
+                               generator=torch.Generator().manual_seed(42), on_step=lambda i, l: out.append(l.float().cpu()), **knobs)
+            return out, sched
+        finally:
+            torch.backends.cudnn.allow_tf32 = old
+
+    truth, _ = oracle_run(False, None, False)
+    want, o_sched = oracle_run(True, cuda, True)
 
     pcfg = wtr.WanDitConfig(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=64, text_len=16, img_dim=64,
                             img_len=5, freq_dim=32)
@@ -38,11 +49,13 @@ def test_two_guided_steps_config1_shape(cuda):
     wpipe.denoise_loop(tr, vae, w_sched, *args(), video_ref=to(inp.video_ref), mask=to(inp.mask),
                        generator=torch.Generator().manual_seed(42), on_step=lambda i, l: got.append(l.float().cpu()), **knobs)
     assert w_sched.fuse_calls == o_sched.fuse_calls == 4 and tr.calls == 8
-    for i, (a, b) in enumerate(zip(want, got)):
-        rel = ((a - b).norm() / a.norm()).item()
-        # north-star bar: 1e-3 relative per denoised latent for the DiT; the VAE round trip inside FLF runs in
-        # tf32 (cuDNN's default for the reference on a GPU) against the oracle's exact fp32, which adds ~2e-3
-        assert rel < 6e-3, (i, rel)
+    rel = lambda a, b: ((a - b).norm() / b.norm()).item()
+    for i, (t, a, b) in enumerate(zip(truth, want, got)):
+        # measured floor: per denoised latent the engine is no further from the exact-arithmetic trajectory than the
+        # reference's own GPU arithmetic (bf16 DiT, tf32 VAE) is
+        e_model, e_engine = rel(a, t), rel(b, t)
+        print(f"\n[floor] guided step {i}: model-vs-fp32 {e_model:.3e}  engine-vs-fp32 {e_engine:.3e}  engine-vs-model {rel(b, a):.3e}")
+        assert e_engine <= 1.1 * e_model, (i, e_engine, e_model)
 
 
 def test_pipeline_object_surface(cuda):

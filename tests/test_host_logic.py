@@ -189,3 +189,28 @@ def test_longcat_host_logic_matches_oracle():
     tab = longcat.rope_table((2, 3, 4))
     assert torch.equal(tab[..., 0], fr.cos()[:, 0::2]) and torch.equal(tab[..., 1], fr.sin()[:, 0::2])
     assert longcat.LongCatConfig().ffn_dim == old.LongCatConfig().ffn_dim == 11008
+
+
+def test_context_cache_is_keyed_by_content_not_by_address():
+    """a cache keyed by (data_ptr, _version) alone returns the previous prompt's K|V when the
+    allocator recycles the address.  Entries hold their sources; a fresh tensor hits only if its bytes are equal."""
+    from worldforge_b200.ctx_cache import ContextCache
+    c = ContextCache(2)
+    a, img = torch.randn(4, 8), torch.randn(3, 8)
+    assert c.get((a, img)) is None
+    c.put((a, img), "A")
+    assert c.get((a, img)) == "A" and c.hits_identity == 1
+    assert c.get((a[:], img)) == "A" and c.hits_identity == 2          # a view of the same storage
+    assert c.get((a.clone(), img.clone())) == "A" and c.hits_content == 1
+    b = torch.randn(4, 8)
+    assert c.get((b, img)) is None                                     # same shape, other prompt
+    ptr = a.data_ptr()
+    held_alive = c._entries[0][0][0]
+    del a
+    assert held_alive.data_ptr() == ptr                                # the entry keeps the storage from being recycled
+    held_alive.add_(1.0)                                               # in-place write after caching: entry is stale
+    assert c.get((held_alive, img)) is None
+    c.put((held_alive, img), "A2")
+    assert len(c) == 1 and c.get((held_alive, img)) == "A2"            # the stale entry was dropped
+    c.put((b, img), "B"); c.put((torch.randn(4, 8), img), "C")
+    assert len(c) == 2 and c.get((b, img)) == "B"                      # capacity 2: oldest evicted

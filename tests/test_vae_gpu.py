@@ -127,5 +127,5 @@ def test_row_sharded_vae_is_bit_identical(cuda, world, F_, H, W):
 
     mu = wvae.lib.cl_to_planar(run("enc", video[0]).contiguous(), m.z_dim).unsqueeze(0)
     assert torch.equal(mu, want_mu)
-    x = m._conv(wvae.lib.planar_to_cl(z[0].contiguous(), m.z_dim), "conv2", wvae.TAPS_1, m.z_dim)
+    x = m._conv(wvae.lib.planar_to_cl(z[0].contiguous(), m.z_dim, round_tf32=True), "conv2", wvae.TAPS_1, m.z_dim, round_out=True)
     assert torch.equal(run("dec", x).unsqueeze(0), want_dec)

@@ -225,6 +225,14 @@ __host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt, uint32_t m, uint
 
 // ------------------------------------------------------------------- numerics
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// fp32 -> nearest tf32 (ties away from zero), held in fp32.  tcgen05.mma kind::tf32 ignores the 13 low mantissa bits of its
+// operands (truncation); cuDNN - the reference's fp32 VAE on a GPU - converts with round-to-nearest.  Activations and weights
+// that feed a convolution are therefore rounded where they are PRODUCED, and the tensor core's truncation becomes a no-op.
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

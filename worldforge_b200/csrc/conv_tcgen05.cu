@@ -65,6 +65,7 @@ struct ConvArgs {
   const float* resid;       // same addressing as out, or null
   int planar_clamp;         // 1: out is planar [c_split][frames][out_H][out_W], values clamped to [-1,1]
   long long planar_cstride; // elements between channels in planar mode
+  int round_out;            // 1: the stored value is rounded to tf32 (its only consumers are convolutions: see tf32_round)
 };
 
 // Epilogue of one 128-pixel x BN tile for epilogue warp q (rows 32q..32q+31 of the tile): TMEM -> registers -> shared-memory
@@ -127,6 +128,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvArgs& p, float* til
         float v = tile_s[rr * CV_EPI_LD + lane] + b0;
         if (p.resid) v += rv[rr];
         if (p.planar_clamp) v = fminf(fmaxf(v, -1.0f), 1.0f);
+        if (p.round_out) v = tf32_round(v);
         p.out[base + static_cast<size_t>(row_part[rr]) * pitch] = v;
       }
     }
@@ -475,7 +477,7 @@ extern "C" int wf_conv_tf32(const float* in, int in_T, int in_H, int in_W, int C
                             int Cout, int ntaps, const signed char* taps, int T, int H, int W, int t_stride, int t_off,
                             float* out, int ldc, int out_H, int out_W, int t_mul, int c_split, int sy, int sx, int oy,
                             int ox, const float* resid, int planar_clamp, long long planar_cstride, int tile_w,
-                            void* stream) {
+                            int round_out_tf32, void* stream) {
   WF_REQUIRE(in && weights && out && taps, "wf_conv_tf32: null pointer");
   WF_REQUIRE(Cin > 0 && Cin % 4 == 0, "wf_conv_tf32: Cin must be a positive multiple of 4 (16-byte pixel rows)");
   WF_REQUIRE(Cout > 0 && ntaps > 0 && ntaps <= CV_MAX_TAPS, "wf_conv_tf32: bad Cout / tap count");
@@ -497,6 +499,7 @@ extern "C" int wf_conv_tf32(const float* in, int in_T, int in_H, int in_W, int C
   a.out = out; a.ldc = ldc; a.out_H = out_H; a.out_W = out_W; a.t_mul = t_mul; a.c_split = c_split;
   a.sy = sy; a.sx = sx; a.oy = oy; a.ox = ox; a.bias = bias; a.resid = resid;
   a.planar_clamp = planar_clamp; a.planar_cstride = planar_cstride;
+  a.round_out = round_out_tf32 != 0;
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(in_W), static_cast<uint64_t>(in_H), static_cast<uint64_t>(in_T)};

@@ -27,7 +27,7 @@ __device__ __forceinline__ float wmax(float v) {
 constexpr int VR_MAXK = 24;   // up to 768 channels
 __global__ void __launch_bounds__(256) rms_silu_cl_kernel(const float* __restrict__ x, float* __restrict__ out,
                                                           const float* __restrict__ gamma, size_t pixels, int C, int ldx,
-                                                          int ldo, int silu) {
+                                                          int ldo, int silu, int round_tf32) {
   const int lane = threadIdx.x & 31;
   const size_t warp0 = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
   const size_t nwarps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
@@ -51,20 +51,29 @@ __global__ void __launch_bounds__(256) rms_silu_cl_kernel(const float* __restric
       if (c < C) {
         float y = v[k] / denom * scale * gamma[c];
         if (silu) y = y / (1.0f + expf(-y));
-        orow[c] = y;
+        orow[c] = round_tf32 ? tf32_round(y) : y;
       }
     }
   }
 }
 
 // planar [C][N] -> channels-last [N][Cp] with channels C..Cp-1 zero
-__global__ void planar_to_cl_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t N, int C, int Cp) {
+__global__ void planar_to_cl_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t N, int C, int Cp, int round_tf32) {
   const size_t total = N * Cp;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % Cp);
     const size_t n = i / Cp;
-    dst[i] = (c < C) ? src[static_cast<size_t>(c) * N + n] : 0.f;
+    const float v = (c < C) ? src[static_cast<size_t>(c) * N + n] : 0.f;
+    dst[i] = round_tf32 ? tf32_round(v) : v;
+  }
+}
+// dst = src rounded to tf32 (the raw residual stream read by a 1x1 shortcut convolution, vae.py:192-193)
+__global__ void round_tf32_kernel(const float4* __restrict__ src, float4* __restrict__ dst, size_t n4) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float4 v = src[i];
+    v.x = tf32_round(v.x); v.y = tf32_round(v.y); v.z = tf32_round(v.z); v.w = tf32_round(v.w);
+    dst[i] = v;
   }
 }
 // channels-last [N][ld] (first C channels) -> planar [C][N]
@@ -135,6 +144,22 @@ __global__ void transpose_f32_kernel(const float* __restrict__ src, float* __res
   }
 }
 
+// hi = x with the 13 low mantissa bits cleared (exactly what a kind::tf32 tcgen05.mma reads of x), lo = x - hi (exact in
+// fp32).  A . B = A_hi.B_hi + A_hi.B_lo + A_lo.B_hi + O(2^-22): three tf32 products accumulate to fp32 accuracy - used for
+// the mid-block attention of the VAE, whose matmuls the reference computes in fp32 (vae.py:252-256; torch keeps
+// allow_tf32 OFF for matmuls, unlike cuDNN convolutions).
+__global__ void split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo, size_t n4) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 v = x[i];
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+    hi[i] = h; lo[i] = l;
+  }
+}
+
 static int grid_for_n(size_t n, int waves = 8) {
   return static_cast<int>(std::max<size_t>(1, std::min<size_t>((n + 255) / 256, static_cast<size_t>(sm_count()) * waves)));
 }
@@ -145,19 +170,19 @@ using namespace wf;
 #define WF_STREAM static_cast<cudaStream_t>(stream)
 
 extern "C" int wf_rms_norm_cl(const float* x, int ldx, float* out, int ldo, const float* gamma, long long pixels, int C,
-                              int silu, void* stream) {
+                              int silu, int round_tf32, void* stream) {
   WF_REQUIRE(x && out && gamma && pixels > 0, "wf_rms_norm_cl: bad arguments");
   WF_REQUIRE(C > 0 && C <= 32 * VR_MAXK, "wf_rms_norm_cl: 1..768 channels");
   const size_t warps = static_cast<size_t>(pixels);
   const int blocks = static_cast<int>(std::min<size_t>((warps + 7) / 8, static_cast<size_t>(sm_count()) * 16));
-  rms_silu_cl_kernel<<<blocks, 256, 0, WF_STREAM>>>(x, out, gamma, static_cast<size_t>(pixels), C, ldx, ldo, silu);
+  rms_silu_cl_kernel<<<blocks, 256, 0, WF_STREAM>>>(x, out, gamma, static_cast<size_t>(pixels), C, ldx, ldo, silu, round_tf32);
   WF_LAUNCH_OK();
   return WF_OK;
 }
 
-extern "C" int wf_planar_to_cl(const float* src, float* dst, long long n, int C, int Cp, void* stream) {
+extern "C" int wf_planar_to_cl(const float* src, float* dst, long long n, int C, int Cp, int round_tf32, void* stream) {
   WF_REQUIRE(src && dst && n > 0 && C > 0 && Cp >= C, "wf_planar_to_cl: bad arguments");
-  planar_to_cl_kernel<<<grid_for_n(static_cast<size_t>(n) * Cp), 256, 0, WF_STREAM>>>(src, dst, static_cast<size_t>(n), C, Cp);
+  planar_to_cl_kernel<<<grid_for_n(static_cast<size_t>(n) * Cp), 256, 0, WF_STREAM>>>(src, dst, static_cast<size_t>(n), C, Cp, round_tf32);
   WF_LAUNCH_OK();
   return WF_OK;
 }
@@ -189,6 +214,25 @@ extern "C" int wf_transpose_f32(const float* src, float* dst, int R, int C, int 
   WF_REQUIRE(src && dst && R > 0 && C > 0, "wf_transpose_f32: bad arguments");
   dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
   transpose_f32_kernel<<<grid, block, 0, WF_STREAM>>>(src, dst, R, C, lds, ldd);
+  WF_LAUNCH_OK();
+  return WF_OK;
+}
+
+extern "C" int wf_split_tf32(const float* x, float* hi, float* lo, long long n, void* stream) {
+  WF_REQUIRE(x && hi && lo && n > 0 && n % 4 == 0, "wf_split_tf32: bad arguments (n must be a multiple of 4)");
+  WF_REQUIRE((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) % 16 == 0,
+             "wf_split_tf32: pointers must be 16-byte aligned");
+  split_tf32_kernel<<<grid_for_n(static_cast<size_t>(n) / 4), 256, 0, WF_STREAM>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(hi), reinterpret_cast<float4*>(lo), static_cast<size_t>(n) / 4);
+  WF_LAUNCH_OK();
+  return WF_OK;
+}
+
+extern "C" int wf_round_tf32(const float* src, float* dst, long long n, void* stream) {
+  WF_REQUIRE(src && dst && n > 0 && n % 4 == 0, "wf_round_tf32: bad arguments (n must be a multiple of 4)");
+  WF_REQUIRE((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) % 16 == 0, "wf_round_tf32: pointers must be 16-byte aligned");
+  round_tf32_kernel<<<grid_for_n(static_cast<size_t>(n) / 4), 256, 0, WF_STREAM>>>(reinterpret_cast<const float4*>(src),
+                                                                                    reinterpret_cast<float4*>(dst), static_cast<size_t>(n) / 4);
   WF_LAUNCH_OK();
   return WF_OK;
 }

@@ -66,13 +66,15 @@ _SIGNATURES = {
     "wf_refine_upsample": [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp],
     "wf_cfg_zero": [_vp, _vp, _vp, _f, _ll, _vp, _vp, _vp],
     "wf_conv_tf32": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i,
-                     _vp, _i, _ll, _i, _vp],
-    "wf_rms_norm_cl": [_vp, _i, _vp, _i, _vp, _ll, _i, _i, _vp],
-    "wf_planar_to_cl": [_vp, _vp, _ll, _i, _i, _vp],
+                     _vp, _i, _ll, _i, _i, _vp],
+    "wf_rms_norm_cl": [_vp, _i, _vp, _i, _vp, _ll, _i, _i, _i, _vp],
+    "wf_planar_to_cl": [_vp, _vp, _ll, _i, _i, _i, _vp],
+    "wf_round_tf32": [_vp, _vp, _ll, _vp],
     "wf_cl_to_planar": [_vp, _vp, _ll, _i, _i, _vp],
     "wf_space_to_depth": [_vp, _vp, _i, _i, _i, _i, _vp],
     "wf_softmax_rows": [_vp, _i, _i, _i, _f, _vp],
     "wf_transpose_f32": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "wf_split_tf32": [_vp, _vp, _vp, _ll, _vp],
 }
 _PLAIN = {"wf_last_error": (C.c_char_p, []), "wf_abi_version": (_i, []), "wf_sm_count": (_i, []),
           "wf_dsg_workspace_bytes": (_ll, []), "wf_quantise_workspace_bytes": (_ll, []),
@@ -517,9 +519,11 @@ def refine_upsample(video_u8, F2: int, H: int, W: int, pad_front: int = 0, pad_b
 # ------------------------------------------------------------------------------ VAE kernels
 
 def conv_tf32(inp, weights, bias, taps, out, *, T, H, W, Cout, t_stride=1, t_off=0, t_mul=1, c_split=None, sy=1, sx=1,
-              oy=0, ox=0, resid=None, planar_clamp=False, tile_w=16, out_hw=None, ldc=None):
+              oy=0, ox=0, resid=None, planar_clamp=False, tile_w=16, out_hw=None, ldc=None, round_out=False):
     """inp: channels-last fp32 [in_T, in_H, in_W, Cin]; weights fp32 [ntaps*Cout, Cin]; taps: list of (dt,dy,dx).
-    out: channels-last fp32 [frames, out_H, out_W, ldc] (or planar [c, frames, out_H, out_W] with planar_clamp)."""
+    out: channels-last fp32 [frames, out_H, out_W, ldc] (or planar [c, frames, out_H, out_W] with planar_clamp).
+    The tensor core truncates its fp32 operands to tf32: pass operands already ROUNDED to tf32 (round_tf32 / round_out of
+    the producers) to get cuDNN's round-to-nearest arithmetic.  round_out: store ``out`` rounded to tf32."""
     assert inp.dtype == torch.float32 and inp.is_contiguous() and inp.dim() == 4
     in_T, in_H, in_W, Cin = inp.shape
     ntaps = len(taps)
@@ -538,25 +542,35 @@ def conv_tf32(inp, weights, bias, taps, out, *, T, H, W, Cout, t_stride=1, t_off
         cstride = 0
     _call("wf_conv_tf32", _p(inp), in_T, in_H, in_W, Cin, _p(weights), _p(bias), Cout, ntaps, C.cast(tb, _vp), T, H, W,
           t_stride, t_off, _p(out), ld, oH, oW, t_mul, cs, sy, sx, oy, ox, _p(resid), int(planar_clamp), cstride, tile_w,
-          _stream())
+          int(round_out), _stream())
     return out
 
 
-def rms_norm_cl(x, gamma, out=None, silu=True):
+def rms_norm_cl(x, gamma, out=None, silu=True, round_tf32=True):
+    """RMS-norm (+SiLU) over the channels of every pixel.  Its result always feeds a convolution in the VAE, so by default
+    it is stored rounded to tf32 (cuDNN's operand conversion; see conv_tf32)."""
     C_ = x.shape[-1]
     assert x.dtype == torch.float32 and x.is_contiguous() and gamma.numel() == C_
     out = torch.empty_like(x) if out is None else out
-    _call("wf_rms_norm_cl", _p(x), C_, _p(out), C_, _p(gamma), x.numel() // C_, C_, int(silu), _stream())
+    _call("wf_rms_norm_cl", _p(x), C_, _p(out), C_, _p(gamma), x.numel() // C_, C_, int(silu), int(round_tf32), _stream())
     return out
 
 
-def planar_to_cl(src, Cp):
-    """[C, ...] planar fp32 -> [..., Cp] channels-last with zero-padded channels."""
+def planar_to_cl(src, Cp, round_tf32=False):
+    """[C, ...] planar fp32 -> [..., Cp] channels-last with zero-padded channels (optionally rounded to tf32)."""
     assert src.dtype == torch.float32 and src.is_contiguous()
     C_ = src.shape[0]
     n = src.numel() // C_
     dst = torch.empty(*src.shape[1:], Cp, dtype=torch.float32, device=src.device)
-    _call("wf_planar_to_cl", _p(src), _p(dst), n, C_, Cp, _stream())
+    _call("wf_planar_to_cl", _p(src), _p(dst), n, C_, Cp, int(round_tf32), _stream())
+    return dst
+
+
+def round_tf32(src, dst=None):
+    """src rounded to the nearest tf32 (what cuDNN feeds the tensor cores), as a new tensor or into ``dst``."""
+    assert src.dtype == torch.float32 and src.is_contiguous() and src.numel() % 4 == 0
+    dst = torch.empty_like(src) if dst is None else dst
+    _call("wf_round_tf32", _p(src), _p(dst), src.numel(), _stream())
     return dst
 
 
@@ -589,3 +603,12 @@ def transpose_f32(src, dst):
     assert dst.shape == (C_, R)
     _call("wf_transpose_f32", _p(src), _p(dst), R, C_, src.stride(0), dst.stride(0), _stream())
     return dst
+
+
+def split_tf32(x, hi=None, lo=None):
+    """x = hi + lo with hi exactly representable in tf32 (what the tensor core reads of x) and lo the exact remainder."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.numel() % 4 == 0
+    hi = torch.empty_like(x) if hi is None else hi
+    lo = torch.empty_like(x) if lo is None else lo
+    _call("wf_split_tf32", _p(x), _p(hi), _p(lo), x.numel(), _stream())
+    return hi, lo

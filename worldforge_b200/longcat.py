@@ -25,6 +25,7 @@ from typing import Dict, Tuple
 import torch
 
 from . import lib
+from .ctx_cache import ContextCache
 
 BF, F32 = torch.bfloat16, torch.float32
 
@@ -102,7 +103,7 @@ class WfLongCatTransformer:
         self.config = SimpleNamespace(in_channels=cfg.in_channels, out_channels=cfg.out_channels, patch_size=cfg.patch)
         self.cp_split_hw = [1, 1]
         self.blocks = []
-        self._buf, self._rope, self._ctx_cache = {}, {}, {}
+        self._buf, self._rope, self._ctx_cache = {}, {}, ContextCache(4)
         self.calls = 0
         self.bsa_params = None          # the checkpoint's bsa_params (longcat_video_dit.py:32,56)
         self._bsa_on = False
@@ -186,9 +187,9 @@ class WfLongCatTransformer:
 
     def _context(self, ctx):
         """Caption embedding and every block's cross-attention K|V: functions of the prompt only, computed once."""
-        key = (ctx.data_ptr(), ctx._version, ctx.shape[0])
-        if key in self._ctx_cache:
-            return self._ctx_cache[key]
+        hit = self._ctx_cache.get((ctx,))                     # entries hold their source tensor: see ctx_cache.py
+        if hit is not None:
+            return hit
         c, dev = self.cfg, self.device
         M, C = ctx.shape[0], c.hidden_size
         e = lambda *s: torch.empty(*s, dtype=BF, device=dev)
@@ -200,9 +201,7 @@ class WfLongCatTransformer:
             # kv_linear output is [M, 2, H, 128] (attention.py:215): k = first C columns, v = last C
             lib.rms_norm_head_rope_(kv[:, :C], b.ckn, 1e-6, None)
             kvs.append(kv)
-        if len(self._ctx_cache) >= 4:
-            self._ctx_cache.pop(next(iter(self._ctx_cache)))
-        self._ctx_cache[key] = kvs
+        self._ctx_cache.put((ctx,), kvs)
         return kvs
 
     @torch.no_grad()

@@ -33,6 +33,7 @@ from typing import Dict, Optional, Tuple
 import torch
 
 from . import lib
+from .ctx_cache import ContextCache
 
 BF, F32 = torch.bfloat16, torch.float32
 
@@ -140,7 +141,7 @@ class WfWanTransformer:
         self.blocks = []
         self._buf = {}
         self._rope = {}
-        self._ctx_cache = {}
+        self._ctx_cache = ContextCache(4)
         self.cache_context = True
         self.calls = 0
         self.sp = None
@@ -252,10 +253,11 @@ class WfWanTransformer:
     def _context_kv(self, ctx_txt_in: torch.Tensor, ctx_img_in: torch.Tensor):
         """Per-block cross-attention K|V of the text and image context.  They depend only on the
         prompt / image embeddings and the weights, not on the latents or the timestep, so they are
-        computed once per distinct embedding tensor and reused by every forward of the run."""
-        key = (ctx_txt_in.data_ptr(), ctx_txt_in._version, ctx_img_in.data_ptr(), ctx_img_in._version)
-        if self.cache_context and key in self._ctx_cache:
-            return self._ctx_cache[key]
+        computed once per distinct embedding content and reused by every forward of the run."""
+        if self.cache_context:
+            kv = self._ctx_cache.get((ctx_txt_in, ctx_img_in))     # entries hold their source tensors: see ctx_cache.py
+            if kv is not None:
+                return kv
         c, dev = self.cfg, self.device
         e = lambda *s, dt=BF: torch.empty(*s, dtype=dt, device=dev)
         txt = ctx_txt_in.to(BF)
@@ -277,9 +279,7 @@ class WfWanTransformer:
             lib.rms_norm_rope_(ki[:, :c.dim], b.cnorm_ki, c.eps, None)
             kv.append((kt, ki))
         if self.cache_context:
-            if len(self._ctx_cache) >= 4:
-                self._ctx_cache.pop(next(iter(self._ctx_cache)))
-            self._ctx_cache[key] = kv
+            self._ctx_cache.put((ctx_txt_in, ctx_img_in), kv)
         return kv
 
     # ------------------------------------------------------------------------------ forward

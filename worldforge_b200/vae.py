@@ -12,7 +12,11 @@ few dozen full-grid launches:
 
 * activations are channels-last fp32 ``[T][H][W][C]`` so that a convolution tap is a shifted 4-D TMA box;
 * every convolution is ``wf_conv_tf32`` (tcgen05, tf32 operands = cuDNN's default precision for the reference's
-  fp32 VAE, fp32 accumulation); bias, the residual add of ResidualBlock / AttentionBlock, upsample3d's
+  fp32 VAE, fp32 accumulation).  The tensor core TRUNCATES fp32 operands to tf32 where cuDNN rounds to nearest
+  (measured: 7.7e-4 against 2.9e-4 relative error per convolution), so every convolution operand is rounded to tf32
+  where it is produced - weights at load, activations by the RMS-norm kernel, the layout converter, a producing
+  convolution's epilogue when all its consumers are convolutions (``_round_out``), or ``wf_round_tf32`` for the raw
+  residual stream read by the three 1x1 shortcut convolutions - and the truncation is then exact; bias, the residual add of ResidualBlock / AttentionBlock, upsample3d's
   channel->frame de-interleave and the final clamp + planar store are fused into its epilogue;
 * nearest-exact 2x upsampling is never materialised: upsample + 3x3 conv = four 2x2-tap convolutions on the
   low-resolution tensor (one per output parity) with pre-summed weights;
@@ -48,6 +52,11 @@ TAPS_1 = [(0, 0, 0)]
 TAPS_T_CAUSAL = [(-2, 0, 0), (-1, 0, 0), (0, 0, 0)]
 TAPS_T_STRIDE2 = [(0, 0, 0), (1, 0, 0), (2, 0, 0)]
 TAPS_S2D = [(0, a, b) for a in range(2) for b in range(2)]
+
+
+def _round_tf32_host(w: torch.Tensor) -> torch.Tensor:
+    """fp32 -> nearest tf32 (ties away from zero, like cvt.rna.tf32.f32), any device."""
+    return ((w.contiguous().view(torch.int32) + 0x1000) & -0x2000).view(torch.float32)
 
 
 def _pad_cin(w2: torch.Tensor) -> torch.Tensor:
@@ -206,27 +215,40 @@ class WfWanVAE:
                 elif kind == "head":
                     gamma(name + ".0.gamma"); conv3(name + ".2")
         conv3("conv1"); conv3("conv2")
+        for k in list(W):                      # convolution weights are tensor-core operands: rounded to tf32 once, here
+            if k.endswith(".w"):
+                W[k] = _round_tf32_host(W[k])
+        # a layer's output may be STORED rounded to tf32 when every consumer is a convolution: the residual block in
+        # front of a resampling layer (Resample reads it through convolutions only, vae.py:98-160)
+        self._round_out = set()
+        for plan in (self.enc_plan, self.dec_plan):
+            for (kind, name, _, _), nxt in zip(plan[:-1], plan[1:]):
+                if kind == "res" and nxt[0] in ("up2d", "up3d", "down2d", "down3d"):
+                    self._round_out.add(name)
 
     # ------------------------------------------------------------------------------ layers
     @staticmethod
     def _tile_w(w: int) -> int:
         return 16 if w % 16 == 0 else 8
 
-    def _conv(self, x, wname, taps, cout, *, resid=None, t_out=None, t_stride=1, t_off=0, out=None, t_mul=1, c_split=None):
+    def _conv(self, x, wname, taps, cout, *, resid=None, t_out=None, t_stride=1, t_off=0, out=None, t_mul=1, c_split=None,
+              round_out=False):
         T, H, Wd, _ = x.shape
         t_out = T if t_out is None else t_out
         if out is None:
             out = torch.empty(t_out * t_mul, H, Wd, cout if c_split is None else c_split, dtype=F32, device=x.device)
         lib.conv_tf32(x, self.w[wname + ".w"], self.w[wname + ".b"], taps, out, T=t_out, H=H, W=Wd, Cout=cout,
-                      t_stride=t_stride, t_off=t_off, t_mul=t_mul, c_split=c_split, resid=resid, tile_w=self._tile_w(Wd))
+                      t_stride=t_stride, t_off=t_off, t_mul=t_mul, c_split=c_split, resid=resid, tile_w=self._tile_w(Wd),
+                      round_out=round_out)
         return out
 
     def _res(self, x, name, cin, cout):
-        h = self._conv(x, name + ".shortcut", TAPS_1, cout) if cin != cout else x
+        # the 1x1 shortcut reads the raw residual stream: a tf32-rounded copy is its operand (x itself stays exact)
+        h = self._conv(lib.round_tf32(x), name + ".shortcut", TAPS_1, cout) if cin != cout else x
         y = lib.rms_norm_cl(x, self.w[name + ".residual.0.gamma"])
         y = self._conv(y, name + ".residual.2", TAPS_333, cout)
         lib.rms_norm_cl(y, self.w[name + ".residual.3.gamma"], out=y)
-        return self._conv(y, name + ".residual.6", TAPS_333, cout, resid=h)
+        return self._conv(y, name + ".residual.6", TAPS_333, cout, resid=h, round_out=name in self._round_out)
 
     def _attn(self, x, name, c):
         T, H, Wd, _ = x.shape
@@ -237,26 +259,45 @@ class WfWanVAE:
         o = torch.empty(T, H, Wd, c, dtype=F32, device=x.device)
         s = torch.empty(hw, hw, dtype=F32, device=x.device)
         vt = torch.empty(c, hw, dtype=F32, device=x.device)
+        # The reference computes these two matmuls in fp32 (F.scaled_dot_product_attention on fp32 tensors, vae.py:252-256;
+        # torch keeps TF32 off for matmuls).  Three tf32 products of the (hi, lo) splits accumulate to fp32 accuracy:
+        # A.B = A_hi.B_hi + A_hi.B_lo + A_lo.B_hi + O(2^-22).  60 GFLOP x 3 per frame: ~1 % of a decode.
+        e2 = lambda *sh: (torch.empty(*sh, dtype=F32, device=x.device), torch.empty(*sh, dtype=F32, device=x.device))
+        q_hl, k_hl, s_hl, v_hl = e2(hw, c), e2(hw, c), e2(hw, hw), e2(c, hw)
+        def mm3(a_hl, b_hl, out, n, round_out=False):   # out[hw, n] = a[hw, K] . b[n, K]^T with both operands split
+            a_hi, a_lo = (t.view(1, 1, hw, -1) for t in a_hl)
+            ov = out.view(1, 1, hw, n)
+            lib.conv_tf32(a_lo, b_hl[0], None, TAPS_1, ov, T=1, H=1, W=hw, Cout=n, tile_w=128)          # small terms first
+            lib.conv_tf32(a_hi, b_hl[1], None, TAPS_1, ov, T=1, H=1, W=hw, Cout=n, tile_w=128, resid=ov)
+            lib.conv_tf32(a_hi, b_hl[0], None, TAPS_1, ov, T=1, H=1, W=hw, Cout=n, tile_w=128, resid=ov, round_out=round_out)
         for t in range(T):
-            qt, kt, vv = q[t].view(1, 1, hw, c), k[t].view(hw, c), v[t].view(hw, c)
-            lib.conv_tf32(qt, kt, None, TAPS_1, s.view(1, 1, hw, hw), T=1, H=1, W=hw, Cout=hw, tile_w=128)
+            lib.split_tf32(q[t].view(hw, c), *q_hl)
+            lib.split_tf32(k[t].view(hw, c), *k_hl)
+            mm3(q_hl, k_hl, s, hw)
             lib.softmax_rows_(s, c ** -0.5)
-            lib.transpose_f32(vv, vt)
-            lib.conv_tf32(s.view(1, 1, hw, hw), vt, None, TAPS_1, o[t].view(1, 1, hw, c), T=1, H=1, W=hw, Cout=c, tile_w=128)
+            lib.transpose_f32(v[t].view(hw, c), vt)
+            lib.split_tf32(s, *s_hl)
+            lib.split_tf32(vt, *v_hl)
+            mm3(s_hl, v_hl, o[t].view(hw, c), c, round_out=True)      # o feeds the proj convolution only
+        del q_hl, k_hl, s_hl, v_hl
         del q, k, v, s, vt
         return self._conv(o, name + ".proj", TAPS_1, c, resid=x)
 
     def _down(self, x, name, c, temporal):
         T, H, Wd, _ = x.shape
-        s = lib.space_to_depth(x)
+        s = lib.space_to_depth(x)                  # x was stored tf32-rounded by the residual block in front (_round_out)
+        temporal = temporal and T > 1
         y = torch.empty(T, H // 2, Wd // 2, c, dtype=F32, device=x.device)
+        # down3d: the strided 2-D conv's result feeds the temporal conv (rounded to tf32) - except frame 0, which is also
+        # passed through as the first output frame and must stay exact: it is computed a second time, unrounded
         lib.conv_tf32(s, self.w[name + ".s2d.w"], self.w[name + ".s2d.b"], TAPS_S2D, y, T=T, H=H // 2, W=Wd // 2, Cout=c,
-                      tile_w=self._tile_w(Wd // 2))
-        del s
-        if temporal and T > 1:
+                      tile_w=self._tile_w(Wd // 2), round_out=temporal)
+        if temporal:
             t2 = (T - 1) // 2
             out = torch.empty(1 + t2, H // 2, Wd // 2, c, dtype=F32, device=x.device)
-            out[0].copy_(y[0])
+            lib.conv_tf32(s[:1], self.w[name + ".s2d.w"], self.w[name + ".s2d.b"], TAPS_S2D, out[:1], T=1, H=H // 2, W=Wd // 2,
+                          Cout=c, tile_w=self._tile_w(Wd // 2))
+            del s
             self._conv(y, name + ".time_conv", TAPS_T_STRIDE2, c, t_out=t2, t_stride=2, out=out[1:])
             return out
         return y
@@ -267,7 +308,7 @@ class WfWanVAE:
             xt = torch.empty(1 + 2 * (T - 1), H, Wd, c, dtype=F32, device=x.device)
             xt[0].copy_(x[0])
             # frames 1.. through the temporal conv with an all-zero history; 2C output channels -> two frames of C
-            self._conv(x[1:], name + ".time_conv", TAPS_T_CAUSAL, 2 * c, out=xt[1:], t_mul=2, c_split=c)
+            self._conv(x[1:], name + ".time_conv", TAPS_T_CAUSAL, 2 * c, out=xt[1:], t_mul=2, c_split=c, round_out=True)
             x = xt
             T = x.shape[0]
         out = torch.empty(T, 2 * H, 2 * Wd, c // 2, dtype=F32, device=x.device)
@@ -297,7 +338,7 @@ class WfWanVAE:
                                   Cout=cout, planar_clamp=True, tile_w=self._tile_w(Wd))
                     x = final_planar
                 else:
-                    x = self._conv(y, name + ".2", TAPS_333, cout)
+                    x = self._conv(y, name + ".2", TAPS_333, cout, round_out=True)   # encoder head -> the 1x1 conv1 only
         return x
 
 
@@ -420,7 +461,7 @@ class WfWanVAE:
                 need, _ = self._needed_rows(layers, (lo, hi), h_in)
                 a, b = need[0]
                 if planar_in:
-                    slab = lib.planar_to_cl(full[:, :, a:b].to(F32).contiguous(), 4)
+                    slab = lib.planar_to_cl(full[:, :, a:b].to(F32).contiguous(), 4, round_tf32=True)
                 else:
                     slab = full[:, a:b].contiguous()
                 if which == "dec" and last:                            # the head writes the clamped planar clip
@@ -458,7 +499,7 @@ class WfWanVAE:
                 part, dim, bounds = stage(self.shard.rank, h)
                 h = self._all_gather_rows(part, dim, bounds)
         else:
-            cl = lib.planar_to_cl(x[0].to(F32).contiguous(), 4)
+            cl = lib.planar_to_cl(x[0].to(F32).contiguous(), 4, round_tf32=True)
             h = self._run(self.enc_plan, cl)
             h = self._conv(h, "conv1", TAPS_1, 2 * self.z_dim)
         mu = lib.cl_to_planar(h, self.z_dim)
@@ -471,8 +512,8 @@ class WfWanVAE:
             raise lib.WfError("WfWanVAE runs on CUDA tensors only (no CPU fallback)")
         assert z.shape[0] == 1 and z.shape[1] == self.z_dim
         f, h, w = z.shape[2:]
-        cl = lib.planar_to_cl(z[0].to(F32).contiguous(), self.z_dim)
-        x = self._conv(cl, "conv2", TAPS_1, self.z_dim)
+        cl = lib.planar_to_cl(z[0].to(F32).contiguous(), self.z_dim, round_tf32=True)
+        x = self._conv(cl, "conv2", TAPS_1, self.z_dim, round_out=True)        # conv2 -> decoder.conv1 only
         nt = 0
         for i, up in enumerate(self.temperal_downsample):
             nt += 1 if up else 0
