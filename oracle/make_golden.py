@@ -9,6 +9,8 @@ inputs and random-init weights that are reproducible from seeds (oracle.*.init_p
   vae_mu/dec  WanVAE_.encode / .decode, chunked with the feature cache   (wan/modules/vae.py:516-568)
   sched_*     14 guided steps (IRR + FLF + DSG) driven through the reference's UniPCMultistepScheduler
               (utils/scheduling_unipc_multistep_clean.py), per-step latents and the FLF channel choices
+  wan_pipeline_call   WanImageToVideoPipeline.__call__ itself (utils/pipeline_wan_i2v_clean.py:390-753), unmodified, over
+              the oracle DiT / VAE and the reference scheduler: conditioning tensor and per-step latents
 
 Run:  python -m oracle.make_golden     (the GPU box never runs this; it only reads the committed file)
 """
@@ -118,6 +120,62 @@ def ref_sched():
     s50.set_timesteps(50)
     return hist, log, dict(timesteps=s50.timesteps.clone(), sigmas=s50.sigmas.clone(),
                            resample_timesteps=s50.resample_timesteps.clone())
+
+
+PIPE_STEPS = 14
+# steps 0-11 guided (FLF selects 0 / 1 / 2-6 channels as the step index passes 5 and 10); omega != omega_resample and
+# resample_round > guide_steps: step 12 runs IRR + DSG without FLF and switches omega for good (:678-679); step 13 is plain
+PIPE_KNOBS = dict(guided=True, resample_steps=2, guide_steps=12, omega=4.0, omega_resample=2.0, resample_round=13,
+                  use_pca_channel_selection=True, static=True)
+
+
+def pipeline_inputs():
+    dcfg, vcfg, PD, PV, inp = sched_setup()
+    image = inp.video_ref[:, :, 0] * 2 - 1                      # [1,3,H,W] in [-1,1]: the first reference frame
+    return dcfg, vcfg, PD, PV, inp, image
+
+
+def run_pipeline_oracle(sched):
+    """oracle/pipeline.py (prepare_condition + denoise_loop) on the inputs of ref_pipeline_call."""
+    dcfg, vcfg, PD, PV, inp, image = pipeline_inputs()
+    vae = adapters.OracleVAE(PV, vcfg)
+    cond = pipeline.prepare_condition(vae, image, 9, 64, 96)
+    hist = []
+    pipeline.denoise_loop(adapters.OracleTransformer(PD, dcfg, amp=True), vae, sched, inp.latents.clone().float(), cond,
+                          inp.prompt_embeds.to(torch.bfloat16), inp.negative_prompt_embeds.to(torch.bfloat16),
+                          inp.image_embeds.to(torch.bfloat16), PIPE_STEPS, 4.0, video_ref=inp.video_ref, mask=inp.mask,
+                          generator=torch.Generator().manual_seed(42), on_step=lambda i, l: hist.append(l.clone()), **PIPE_KNOBS)
+    return cond, hist
+
+
+def ref_pipeline_call():
+    """WanImageToVideoPipeline.__call__ of the reference (utils/pipeline_wan_i2v_clean.py:390-753), UNMODIFIED, driving the
+    reference's own UniPCMultistepScheduler over the oracle DiT / VAE objects: prepare_latents, the IRR inner loop, CFG,
+    re-noise, DSG with its scheduler-state pokes and the bf16 cast.  Per-step latents through callback_on_step_end."""
+    pm, sm = ref_shim.load_wan_pipeline_module(), ref_shim.load_scheduler_module()
+    dcfg, vcfg, PD, PV, inp, image = pipeline_inputs()
+    enc = ref_shim.FixedImageEncoder(inp.image_embeds)
+    sched = sm.UniPCMultistepScheduler(num_train_timesteps=1000, solver_order=2, prediction_type="flow_prediction",
+                                       use_flow_sigmas=True, flow_shift=3.0)
+    pipe = pm.WanImageToVideoPipeline(tokenizer=None, text_encoder=None, image_encoder=enc.encoder, image_processor=enc.processor,
+                                      transformer=adapters.OracleTransformer(PD, dcfg, amp=True), vae=adapters.OracleVAE(PV, vcfg),
+                                      scheduler=sched)
+    hist, conds = [], []
+    orig_prepare = pipe.prepare_latents
+    def spy_prepare(*a, **k):                                   # record the conditioning tensor the reference builds
+        lat, cond = orig_prepare(*a, **k)
+        conds.append(cond.clone())
+        return lat, cond
+    pipe.prepare_latents = spy_prepare
+    def on_step(p, i, t, kw):
+        hist.append(kw["latents"].clone())
+        return {}
+    out = pipe(image=image, height=64, width=96, num_frames=9, num_inference_steps=PIPE_STEPS, guidance_scale=4.0,
+               generator=torch.Generator().manual_seed(42), latents=inp.latents.clone(), prompt_embeds=inp.prompt_embeds,
+               negative_prompt_embeds=inp.negative_prompt_embeds, output_type="latent", return_dict=False,
+               callback_on_step_end=on_step, video_ref=inp.video_ref, mask=inp.mask, **PIPE_KNOBS)[0]
+    assert torch.equal(out, hist[-1])
+    return dict(condition=conds[0], latents=[h.clone() for h in hist], dtypes=[str(h.dtype) for h in hist])
 
 
 LC_DIT = dict(hidden_size=256, depth=2, num_heads=2, caption_channels=64, adaln_tembed_dim=32, frequency_embedding_size=32)
@@ -271,6 +329,7 @@ def main():
         "sched_tables_50": tables,
         "longcat_dit_fp32": ref_longcat_dit().clone(), "longcat_sched": ref_longcat_sched(),
         "bsa": ref_bsa(), "longcat_dit_bsa_fp32": ref_longcat_dit_bsa().clone(), "longcat_refine": ref_refine(),
+        "wan_pipeline_call": ref_pipeline_call(),
         "meta": {"reference_commit": "3314da5", "torch": torch.__version__, "generator": "oracle/make_golden.py"},
     }
     os.makedirs(os.path.dirname(OUT), exist_ok=True)

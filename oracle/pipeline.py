@@ -26,6 +26,20 @@ def first_frame_mask(num_frames: int, lat_h: int, lat_w: int, t_scale: int = 4) 
     return m.view(1, -1, t_scale, lat_h, lat_w).transpose(1, 2)
 
 
+def prepare_condition(vae, image: torch.Tensor, num_frames: int, height: int, width: int, t_scale: int = 4,
+                      s_scale: int = 8) -> torch.Tensor:
+    """The [B, 4 + z, f, h, w] conditioning tensor of prepare_latents (:316-362): the first frame followed by zeros is
+    encoded (argmax = the mean), normalised with the VAE's latent statistics and preceded by the 4-channel frame mask.
+    ``image`` [B,3,H,W] fp32 in [-1,1]."""
+    video = torch.cat([image.unsqueeze(2), image.new_zeros(image.shape[0], image.shape[1], num_frames - 1, height, width)], dim=2)
+    video = video.to(dtype=torch.float32)
+    mean = torch.tensor(vae.config.latents_mean).view(1, vae.config.z_dim, 1, 1, 1).to(video.device, torch.float32)
+    inv_std = 1.0 / torch.tensor(vae.config.latents_std).view(1, vae.config.z_dim, 1, 1, 1).to(video.device, torch.float32)
+    cond = (vae.encode(video).latent_dist.mode() - mean) * inv_std
+    mask = first_frame_mask(num_frames, height // s_scale, width // s_scale, t_scale).to(cond.device)
+    return torch.cat([mask.expand(cond.shape[0], -1, -1, -1, -1), cond], dim=1)
+
+
 def denoise_loop(transformer, vae, scheduler, latents, condition, prompt_embeds, negative_prompt_embeds,
                  image_embeds, num_inference_steps: int, guidance_scale: float, video_ref=None, mask=None,
                  guided=False, resample_steps=1, guide_steps=20, omega=1.8, omega_resample=1.0,

@@ -289,3 +289,133 @@ def load_longcat_scheduler_module():
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
     return m
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The reference PIPELINES: WanImageToVideoPipeline.__call__ and LongCatVideoPipeline.generate_i2v run
+# UNMODIFIED over oracle objects, so that oracle/pipeline.py and oracle/longcat_sched.py - restatements of those two
+# loops - are pinned against the loops themselves and not only against the schedulers they drive.
+# ------------------------------------------------------------------------------------------------------------------
+
+class _Progress:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+    def update(self, *a, **k):
+        pass
+
+
+class _DiffusionPipeline:
+    """Stand-in for diffusers.DiffusionPipeline with the five members pipeline_wan_i2v_clean.py uses:
+    register_modules (:152), _execution_device (:484), progress_bar (:562), maybe_free_model_hooks (:748) and the
+    plain constructor."""
+    exec_device = torch.device("cpu")
+
+    def __init__(self, *a, **k):
+        pass
+
+    def register_modules(self, **kw):
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+    @property
+    def _execution_device(self):
+        return self.exec_device
+
+    def progress_bar(self, iterable=None, total=None):
+        return _Progress()
+
+    def maybe_free_model_hooks(self):
+        pass
+
+
+class _VideoProcessor:
+    """Stand-in for diffusers.video_processor.VideoProcessor.  ``preprocess`` is only defined here for what the pinning
+    runs feed it - a [B,3,H,W] float tensor already in [-1,1] at the target size, which diffusers' VaeImageProcessor
+    returns unchanged (it skips its [0,1]->[-1,1] normalisation when the tensor has negative values) - and raises for
+    anything else instead of guessing."""
+
+    def __init__(self, vae_scale_factor=8, **kw):
+        self.vae_scale_factor = vae_scale_factor
+
+    def preprocess(self, image, height=None, width=None):
+        if not (isinstance(image, torch.Tensor) and image.dim() == 4 and image.shape[-2:] == (height, width)
+                and float(image.min()) < 0 and float(image.abs().max()) <= 1):
+            raise NotImplementedError("shim VideoProcessor: pass a [B,3,H,W] tensor in [-1,1] of the target size")
+        return image
+
+    def postprocess_video(self, video, output_type="np"):
+        raise NotImplementedError("shim VideoProcessor: run the pinned pipelines with output_type='latent'")
+
+
+def _randn_tensor(shape, generator=None, device=None, dtype=None, layout=None):
+    """diffusers.utils.torch_utils.randn_tensor for a single CPU generator: drawn on the generator's device, then moved."""
+    return torch.randn(shape, generator=generator, dtype=dtype).to(device)
+
+
+def install_pipeline_shim() -> None:
+    """The remaining ``diffusers`` names the reference pipelines import (pipeline_wan_i2v_clean.py:22-31,
+    pipeline_longcat_video.py:11-12)."""
+    install_diffusers_shim()
+    d = sys.modules["diffusers"]
+    if not getattr(d, "_wf_shim", False):
+        return
+    def mod(name):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+        return sys.modules[name]
+    cb = mod("diffusers.callbacks")
+    cb.PipelineCallback = type("PipelineCallback", (), {})
+    cb.MultiPipelineCallbacks = type("MultiPipelineCallbacks", (), {})
+    mod("diffusers.image_processor").PipelineImageInput = object
+    mod("diffusers.loaders").WanLoraLoaderMixin = type("WanLoraLoaderMixin", (), {})
+    mm = sys.modules["diffusers.models"]
+    mm.AutoencoderKLWan = type("AutoencoderKLWan", (), {})
+    mm.WanTransformer3DModel = type("WanTransformer3DModel", (), {})
+    sys.modules["diffusers.schedulers"].FlowMatchEulerDiscreteScheduler = type("FlowMatchEulerDiscreteScheduler", (), {})
+    ut = sys.modules["diffusers.utils"]
+    ut.is_ftfy_available = lambda: False
+    ut.is_torch_xla_available = lambda: False
+    ut.replace_example_docstring = lambda doc: (lambda fn: fn)
+    tu = mod("diffusers.utils.torch_utils"); tu.randn_tensor = _randn_tensor
+    ut.torch_utils = tu
+    mod("diffusers.video_processor").VideoProcessor = _VideoProcessor
+    pp = mod("diffusers.pipelines"); pu = mod("diffusers.pipelines.pipeline_utils")
+    pu.DiffusionPipeline = _DiffusionPipeline
+    pw = mod("diffusers.pipelines.wan"); po = mod("diffusers.pipelines.wan.pipeline_output")
+    po.WanPipelineOutput = lambda frames: types.SimpleNamespace(frames=frames)
+    pp.pipeline_utils, pp.wan, pw.pipeline_output = pu, pw, po
+    for name in ("callbacks", "image_processor", "loaders", "video_processor", "pipelines"):
+        setattr(d, name, sys.modules["diffusers." + name])
+
+
+def load_wan_pipeline_module():
+    """utils/pipeline_wan_i2v_clean.py, unmodified (its ``transformers`` imports resolve to the installed package)."""
+    assert available()
+    install_pipeline_shim()
+    spec = importlib.util.spec_from_file_location(
+        "wf_ref_pipeline_wan_i2v", os.path.join(REF_WAN, "utils", "pipeline_wan_i2v_clean.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+class FixedImageEncoder:
+    """``image_processor`` + ``image_encoder`` stand-ins for encode_image (pipeline_wan_i2v_clean.py:205-209): the
+    reference refuses ``image`` together with ``image_embeds`` (:362-363) but needs ``image`` for prepare_latents, so the
+    CLIP embedding enters through these two objects; the second-to-last hidden state is the tensor given here."""
+
+    def __init__(self, image_embeds):
+        self.embeds = image_embeds
+
+    def processor(self, images=None, return_tensors="pt"):
+        class _Batch(dict):
+            def to(self, device):
+                return self
+        return _Batch(pixel_values=images)
+
+    def encoder(self, pixel_values=None, output_hidden_states=True):
+        return types.SimpleNamespace(hidden_states=[None, self.embeds, None])

@@ -84,3 +84,32 @@ def test_guided_loop_with_device_flow_scoring(cuda, monkeypatch):
     assert log_cv == log_dev, (log_cv, log_dev)
     assert any(len(c) >= 1 for _, c in log_dev)
     assert all(torch.equal(a, b) for a, b in zip(hist_cv, hist_dev))
+
+
+def test_pipeline_call_tracks_the_reference_call_fixture(cuda):
+    """The engine's public ``WfWanI2VPipeline.__call__`` (image in, prepare_condition, 14 steps) against the fixture the
+    UNMODIFIED reference ``WanImageToVideoPipeline.__call__`` produced on the CPU (tests/golden, oracle/make_golden.py:
+    ref_pipeline_call) - the oracle DiT / VAE plugged into the engine's pipeline so that only the pipeline / scheduler /
+    sampler kernels differ.  The reference ran with CPU scalar semantics, the engine with CUDA's, so the
+    trajectories agree to bf16 resolution rather than bit for bit; the FLF branch structure must be the same."""
+    import os
+    from oracle import make_golden as mg
+    from worldforge_b200 import pipeline as wpipe, scheduler as wsched
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "wan_golden.pt"), weights_only=False)["wan_pipeline_call"]
+    dcfg, vcfg, PD, PV, inp, image = mg.pipeline_inputs()
+    sched = wsched.WfUniPCScheduler(flow_shift=3.0)
+    pipe = wpipe.WfWanI2VPipeline(adapters.OracleTransformer(PD, dcfg, amp=True), adapters.OracleVAE(PV, vcfg), sched)
+    cond = wpipe.prepare_condition(pipe.vae, image.to(cuda), 9, 64, 96)
+    torch.testing.assert_close(cond.cpu(), gold["condition"], rtol=1e-5, atol=1e-5)
+    hist = []
+    pipe(image=image, height=64, width=96, num_frames=9, num_inference_steps=mg.PIPE_STEPS, guidance_scale=4.0,
+         generator=torch.Generator().manual_seed(42), latents=inp.latents.clone(), prompt_embeds=inp.prompt_embeds,
+         negative_prompt_embeds=inp.negative_prompt_embeds, image_embeds=inp.image_embeds, video_ref=inp.video_ref,
+         mask=inp.mask, on_step=lambda i, l: hist.append(l.detach().clone().cpu()), device=cuda, **mg.PIPE_KNOBS)
+    assert len(hist) == len(gold["latents"]) == mg.PIPE_STEPS
+    for i, (a, b) in enumerate(zip(hist, gold["latents"])):
+        assert str(a.dtype) == gold["dtypes"][i], (i, a.dtype)
+        rel = ((a.float() - b.float()).norm() / b.float().norm()).item()
+        assert rel < 2e-3, (i, rel)
+    picked = [len(c) for _, c in sched.flf_log]
+    assert 0 in picked and 1 in picked and max(picked) >= 2

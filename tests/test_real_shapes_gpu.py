@@ -62,7 +62,7 @@ def bf16_close_gpu(got, want, ulps=1, max_frac=0.2, atol=1e-6):
 
 def accumulation_atol(a, w, K):
     """Bound on the difference of two fp32 summation orders of sum_k a_k w_k: a few units of 2^-24 of sum_k |a_k w_k|."""
-    return 8.0 * 2.0 ** -24 * K * a.float().abs().mean().item() * w.float().abs().mean().item()
+    return 16.0 * 2.0 ** -24 * K * a.float().abs().mean().item() * w.float().abs().mean().item()
 
 
 # ----------------------------------------------------------------------------------------------------------------
