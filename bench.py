@@ -63,6 +63,7 @@ def parse():
     ap.add_argument("--layers", type=int, default=40, help="DiT depth (40 = Wan2.1-14B; smaller only for dry runs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the PyTorch + flash-attn comparator leg (N=1 only)")
     return ap.parse_args()
 
 
@@ -110,10 +111,18 @@ class ClockSampler:
 # CPU baseline: the oracle (port of the reference's algorithm) on the host cores, bounded sample, extrapolated
 # ----------------------------------------------------------------------------------------------------------------
 
-def cpu_baseline(args, budget_s: float = float(os.environ.get("WF_CPU_BUDGET_S", "20"))):
-    """Times one full-width Wan-14B DiT block and one small VAE round trip with the oracle on all host cores and
-    extrapolates to steps/s of the benchmark configuration (attention scales with L^2, the rest with L; the VAE with
-    pixels x frames).  Baseline only."""
+def _median_spread(ts):
+    med = statistics.median(ts)
+    return med, (max(ts) - min(ts)) / med
+
+
+def cpu_baseline(args, reps: int = int(os.environ.get("WF_CPU_REPS", "2"))):
+    """The oracle (CPU port of the reference's algorithm) on all host cores, on a bounded sample of the benchmark
+    workload, extrapolated to steps/s.  Sample (fixed seeds): ONE full-width Wan-14B DiT block at L = 4680 tokens - the
+    token count of BASELINE config 1 (480p, 9 frames), i.e. the benchmark's 60 x 104 latent frames with 3 instead of 21
+    of them - its self-attention alone at the same L, and one VAE decode + encode of a 9 x 128 x 192 clip; each timed
+    ``reps`` times after one warm-up, MEDIAN taken, spread (max-min)/median reported.  Extrapolation: attention with
+    (L/4680)^2 = 49, the rest of the block with L/4680 = 7, x 40 blocks; the VAE with pixels x frames.  Baseline only."""
     import torch
     from oracle import wan_dit, wan_vae
     cores = os.cpu_count() or 1
@@ -122,53 +131,55 @@ def cpu_baseline(args, budget_s: float = float(os.environ.get("WF_CPU_BUDGET_S",
     P = wan_dit.init_params(cfg, 3)
     f, h, w = (args.frames - 1) // 4 + 1, args.height // 8, args.width // 8
     L = f * (h // 2) * (w // 2)
-    grid_s = (1, 30, 26)                      # 780 tokens of the same width
+    grid_s = (3, 30, 52)
     Ls = grid_s[0] * grid_s[1] * grid_s[2]
-    x = torch.randn(Ls, cfg.dim)
-    e0 = torch.randn(1, 6, cfg.dim) * 0.1
-    ctx = torch.randn(cfg.img_len + cfg.text_len, cfg.dim)
-    def timed(fn, budget):
-        """mean wall time of fn() over as many repetitions as fit in ``budget`` seconds (at least 2, the first discarded)"""
-        fn()
-        n, t0 = 0, time.time()
-        while n < 1 or time.time() - t0 < budget:
-            fn(); n += 1
-        return (time.time() - t0) / n, n
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(Ls, cfg.dim, generator=g)
+    e0 = torch.randn(1, 6, cfg.dim, generator=g) * 0.1
+    ctx = torch.randn(cfg.img_len + cfg.text_len, cfg.dim, generator=g)
+    q = torch.randn(Ls, cfg.num_heads, 128, generator=g)
+
+    def timed(fn, n=reps):
+        fn()                                       # warm-up (thread pool, allocator)
+        ts = []
+        for _ in range(max(n, 1)):
+            t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+        return ts
 
     with torch.no_grad():
-        t_blk, n_blk = timed(lambda: wan_dit.block_forward(P, cfg, 0, x, e0, grid_s, ctx, amp=True), 0.4 * budget_s)
-        q = torch.randn(Ls, cfg.num_heads, 128)
-        t_att, _ = timed(lambda: wan_dit.attention(q, q, q, amp=True), 0.1 * budget_s)
+        ts_blk = timed(lambda: wan_dit.block_forward(P, cfg, 0, x, e0, grid_s, ctx, amp=True))
+        ts_att = timed(lambda: wan_dit.attention(q, q, q, amp=True), 2 * reps + 1)    # x49 in the extrapolation: more samples
+    (t_blk, sp_blk), (t_att, sp_att) = _median_spread(ts_blk), _median_spread(ts_att)
     t_lin = max(t_blk - t_att, 1e-6)
     t_fwd = 40 * (t_lin * L / Ls + t_att * (L / Ls) ** 2)
     vcfg = wan_vae.VaeConfig()
     PV = wan_vae.init_params(vcfg, 4)
-    Fs, Hs, Ws = 5, 64, 96
+    Fs, Hs, Ws = 9, 128, 192
     with torch.no_grad():
-        z = torch.randn(16, 2, Hs // 8, Ws // 8)
-        t_vs, n_vs = timed(lambda: wan_vae.encode_mode(PV, vcfg, wan_vae.decode(PV, vcfg, z)), 0.5 * budget_s)
+        z = torch.randn(16, (Fs - 1) // 4 + 1, Hs // 8, Ws // 8, generator=g)
+        ts_vae = timed(lambda: wan_vae.encode_mode(PV, vcfg, wan_vae.decode(PV, vcfg, z)))
+    t_vs, sp_vae = _median_spread(ts_vae)
     t_vae = t_vs * (args.frames * args.height * args.width) / (Fs * Hs * Ws)
     # 50-step mix: 15 guided steps (4 forwards + 2 VAE round trips) and 35 plain steps (2 forwards)
     t_step = (15 * (4 * t_fwd + 2 * t_vae) + 35 * 2 * t_fwd) / 50
     return {"value": 1.0 / t_step, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"oracle (CPU port of the reference), ~{budget_s:.0f} s of CPU work: one Wan-14B-width DiT block at {Ls} tokens "
-                      f"({t_blk:.2f}s mean of {n_blk}, attention {t_att:.2f}s) and one VAE decode+encode of {Fs}x{Hs}x{Ws} "
-                      f"({t_vs:.2f}s mean of {n_vs}), extrapolated to "
-                      f"L={L} tokens / {args.frames}x{args.height}x{args.width} and the 15:35 guided:plain step mix"}
+            "reps": reps, "spread": {"block": round(sp_blk, 4), "attention": round(sp_att, 4), "vae": round(sp_vae, 4)},
+            "block_s": t_blk, "attention_s": t_att, "vae_round_trip_s": t_vs,
+            "sample": f"oracle (CPU port of the reference) on {cores} threads, fixed seeds, median of {reps} after a warm-up: one "
+                      f"Wan-14B-width DiT block at L={Ls} tokens ({t_blk:.2f}s, spread {sp_blk:.1%}; its self-attention "
+                      f"{t_att:.2f}s, spread {sp_att:.1%}) and one VAE decode+encode of {Fs}x{Hs}x{Ws} ({t_vs:.2f}s, spread "
+                      f"{sp_vae:.1%}), extrapolated to L={L} tokens x 40 blocks / {args.frames}x{args.height}x{args.width} and "
+                      f"the 15:35 guided:plain step mix"}
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU path = the oracle port on all host cores (the Python reference itself cannot
-    travel to the GPU box and has no compiled component); each 'step' re-times the bounded sample."""
+    travel to the GPU box and has no compiled component).  One bounded sample, every piece timed >= 5 times, medians."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
-    for _ in range(max(1, min(args.steps, 3))):
-        vals.append(cpu_baseline(args))
-    v = statistics.mean(x["value"] for x in vals)
-    base = vals[-1]
-    base["value"] = v
+    base = cpu_baseline(args, reps=max(5, min(args.steps, 7)))
+    v = base["value"]
     f, h, w = (args.frames - 1) // 4 + 1, args.height // 8, args.width // 8
     emit({
         "impl": "reference", "metric": metric_name(args), "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -178,6 +189,42 @@ def run_reference(args):
                                "(CPU port of the reference, bounded sample extrapolated)", "tokens": f * (h // 2) * (w // 2)},
         "cpu_baseline": base,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+
+
+def gpu_reference(args, tr, dev, devt, n_guided: int = 2, n_plain: int = 2):
+    """The comparator BASELINE.json's metric names - "the reference's PyTorch+flash-attn path on the same box" (BASELINE.md
+    §3, kind port-gpu): oracle/gpu_path.py = the vendored WanModel op sequence on cuBLAS bf16 GEMMs + eager fp32 torch ops +
+    flash_attn_varlen_func (flash-attn 2.8.3), the chunked / cached WanVAE_ schedule on cuDNN (tf32), the reference loop
+    and scheduler, OpenCV FLF scoring on the host - on the SAME weights, inputs, GPU.  One guided warm-up step, then
+    ``n_guided`` guided + ``n_plain`` plain steps timed with CUDA events; steps/s for the 15:35 mix of the 50-step run."""
+    import torch
+    from oracle import gpu_path, pipeline as opipe, unipc, wan_vae
+    torch.cuda.empty_cache()
+    ref_tr = gpu_path.RefGpuTransformer(tr)
+    vcfg = wan_vae.VaeConfig()
+    ref_vae = gpu_path.RefGpuVAE(wan_vae.init_params(vcfg, 4321), vcfg, dev)
+    warm = 1
+    guide, total = warm + n_guided, warm + n_guided + n_plain
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(total + 1)]
+    ev[0].record()
+    opipe.denoise_loop(ref_tr, ref_vae, unipc.OracleUniPC(flow_shift=3.0), devt["latents"].clone(), devt["condition"],
+                       devt["prompt_embeds"], devt["negative_prompt_embeds"], devt["image_embeds"], 50, 4.0,
+                       video_ref=devt["video_ref"], mask=devt["mask"], guided=True, resample_steps=2, guide_steps=guide,
+                       omega=4.0, omega_resample=4.0, resample_round=guide, use_pca_channel_selection=True, static=True,
+                       generator=torch.Generator().manual_seed(42), on_step=lambda i, lat: ev[i + 1].record(), max_steps=total)
+    torch.cuda.synchronize()
+    ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(total)]
+    g_ms, p_ms = statistics.mean(ms[warm:guide]), statistics.mean(ms[guide:])
+    t_step = (15 * g_ms + 35 * p_ms) / 50
+    del ref_tr, ref_vae
+    torch.cuda.empty_cache()
+    import flash_attn
+    return {"value": 1000.0 / t_step, "unit": UNIT, "kind": "port-gpu", "guided_step_ms": g_ms, "plain_step_ms": p_ms,
+            "dit_forward_ms": p_ms / 2, "step_ms": ms,
+            "sample": f"oracle/gpu_path.py on the same GPU, weights and inputs: {warm} guided warm-up step, then {n_guided} guided + "
+                      f"{n_plain} plain steps (CUDA events), weighted 15:35; cuBLAS bf16 Linears, eager fp32 norms / complex128 "
+                      f"RoPE, flash-attn {flash_attn.__version__} varlen, chunked cuDNN tf32 VAE, OpenCV FLF scoring on the host "
+                      "(the timed guided steps have step index < 6, where the reference's selector returns without scoring)"}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -312,6 +359,13 @@ def run_ours(args):
         "clocks": clk, "gpu_launches": launches, "e2e": e2e, "roofline": roof,
         "dit_forwards_per_sec": (fwd - 4 * W) / (ms / 1000.0),
     }
+    if world == 1 and not args.no_gpu_reference:
+        try:
+            ref = gpu_reference(args, tr, dev, devt)
+            ref["ours_over_reference"] = {"device_resident": value / ref["value"], "e2e": (e2e["value"] / ref["value"]) if e2e else None}
+            line["gpu_reference"] = ref
+        except Exception as ex:  # comparator only - never fail the bench for it
+            line["gpu_reference"] = {"error": f"{type(ex).__name__}: {ex}"}
     if world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline(args)
