@@ -131,7 +131,7 @@ def cpu_baseline(args, reps: int = int(os.environ.get("WF_CPU_REPS", "2"))):
     P = wan_dit.init_params(cfg, 3)
     f, h, w = (args.frames - 1) // 4 + 1, args.height // 8, args.width // 8
     L = f * (h // 2) * (w // 2)
-    grid_s = (3, 30, 52)
+    grid_s = tuple(int(v) for v in os.environ.get("WF_CPU_GRID", "3x30x52").split("x"))   # tests shrink the sample
     Ls = grid_s[0] * grid_s[1] * grid_s[2]
     g = torch.Generator().manual_seed(0)
     x = torch.randn(Ls, cfg.dim, generator=g)
@@ -154,7 +154,7 @@ def cpu_baseline(args, reps: int = int(os.environ.get("WF_CPU_REPS", "2"))):
     t_fwd = 40 * (t_lin * L / Ls + t_att * (L / Ls) ** 2)
     vcfg = wan_vae.VaeConfig()
     PV = wan_vae.init_params(vcfg, 4)
-    Fs, Hs, Ws = 9, 128, 192
+    Fs, Hs, Ws = (9, 128, 192) if "WF_CPU_GRID" not in os.environ else (5, 32, 48)
     with torch.no_grad():
         z = torch.randn(16, (Fs - 1) // 4 + 1, Hs // 8, Ws // 8, generator=g)
         ts_vae = timed(lambda: wan_vae.encode_mode(PV, vcfg, wan_vae.decode(PV, vcfg, z)))
@@ -178,7 +178,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base = cpu_baseline(args, reps=max(5, min(args.steps, 7)))
+    base = cpu_baseline(args, reps=int(os.environ.get("WF_CPU_REPS_REF", max(5, min(args.steps, 7)))))
     v = base["value"]
     f, h, w = (args.frames - 1) // 4 + 1, args.height // 8, args.width // 8
     emit({

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_one_json_line():
-    env = dict(os.environ, WF_CPU_BUDGET_S="1")
+    env = dict(os.environ, WF_CPU_GRID="1x10x13", WF_CPU_REPS_REF="1")   # a tiny sample: the contract, not the number
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
@@ -23,7 +23,7 @@ def test_reference_arm_prints_one_json_line():
 
 
 def test_non_zero_ranks_of_the_reference_arm_stay_silent():
-    env = dict(os.environ, WF_CPU_BUDGET_S="1", RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    env = dict(os.environ, WF_CPU_GRID="1x10x13", WF_CPU_REPS_REF="1", RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and r.stdout.strip() == ""
