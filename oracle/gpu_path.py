@@ -99,7 +99,7 @@ class RefGpuTransformer:
         self.calls += 1
         cols, grid = wan_dit.patchify(hidden_states[0].to(BF), c)
         tok = self.lin(cols, t.patch_w, t.patch_b)                                  # bf16 token stream (:534)
-        s = wan_dit.sinusoid(c.freq_dim, timestep.reshape(-1)[:1]).to(F32)
+        s = wan_dit.sinusoid(c.freq_dim, timestep.reshape(-1)[:1].cpu()).to(F32).to(tok.device)
         e = F.linear(F.silu(F.linear(s, t.t0_w, t.t0_b)), t.t2_w, t.t2_b)            # fp32 island (:546-550)
         e0 = F.linear(F.silu(e), t.tp_w, t.tp_b).unflatten(1, (6, c.dim))
         txt = encoder_hidden_states[0]
