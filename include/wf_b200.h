@@ -234,12 +234,16 @@ int wf_cfg_zero(const float* cond, const float* uncond, float* out, float scale,
  * Operand precision: kind::tf32 reads fp32 operands with the 13 low mantissa bits IGNORED (truncation) where cuDNN - the
  * reference's fp32 VAE on a GPU - rounds to nearest; callers therefore hand this function operands already rounded to
  * tf32 (weights at load; activations by their producer: round_tf32 of wf_rms_norm_cl / wf_planar_to_cl / wf_round_tf32,
- * or round_out_tf32 = 1 here when every consumer of `out` is a convolution). */
+ * or round_out_tf32 = 1 here when every consumer of `out` is a convolution).
+ * Fused RMS_norm (+SiLU) (vae.py:51-54, :195-197 - the norm that FOLLOWS this convolution in ResidualBlock): with
+ * norm_gamma != NULL (needs Cout <= 192 so that one accumulator tile holds all channels of a pixel, plain channels-last
+ * output) a = silu?(v / max(|v|_2, 1e-12) * sqrt(Cout) * gamma), rounded to tf32, is stored to norm_out, or replaces v in
+ * `out` when norm_out is NULL. */
 int wf_conv_tf32(const float* in, int in_T, int in_H, int in_W, int Cin, const float* weights, const float* bias,
                  int Cout, int ntaps, const signed char* taps, int T, int H, int W, int t_stride, int t_off, float* out,
                  int ldc, int out_H, int out_W, int t_mul, int c_split, int sy, int sx, int oy, int ox,
                  const float* resid, int planar_clamp, long long planar_cstride, int tile_w, int round_out_tf32,
-                 void* stream);
+                 const float* norm_gamma, float* norm_out, int norm_silu, void* stream);
 /* RMS_norm (vae.py:51-54) over the channels of every pixel, optionally followed by SiLU (:195-197); round_tf32 = 1 stores
    the result rounded to tf32 (it feeds a convolution) */
 int wf_rms_norm_cl(const float* x, int ldx, float* out, int ldo, const float* gamma, long long pixels, int C, int silu,

@@ -34,7 +34,7 @@ def _clips(n, T, shape=(60, 104)):
     return u8
 
 
-@pytest.mark.parametrize("shape", [(60, 104), (40, 56)])
+@pytest.mark.parametrize("shape", [(60, 104), (40, 56), (90, 160), (88, 160), (64, 72)])     # the last three: two-level pyramids
 def test_device_flow_matches_oracle_and_opencv(cuda, shape):
     from worldforge_b200 import lib
     u8 = _clips(6, 4, shape)
@@ -45,7 +45,8 @@ def test_device_flow_matches_oracle_and_opencv(cuda, shape):
             want = fb.farneback(u8[c, t], u8[c, t + 1])
             ref = cv2.calcOpticalFlowFarneback(u8[c, t], u8[c, t + 1], None, **ARGS)
             np.testing.assert_allclose(got[c, t], want, rtol=0, atol=1e-4)      # FMA contraction in the double sums only
-            np.testing.assert_allclose(got[c, t], ref, rtol=0, atol=1e-4)
+            # two levels: OpenCV's filter engine rounds the sigma-0.5 blur differently (oracle/farneback.py: ~1e-4 px)
+            np.testing.assert_allclose(got[c, t], ref, rtol=0, atol=1e-4 if min(shape) < 64 else 1e-3)
 
 
 def test_device_metrics_match_the_host_expressions(cuda):
@@ -61,10 +62,12 @@ def test_device_metrics_match_the_host_expressions(cuda):
         assert abs(got - want) < 2e-6, (c, got, want)
 
 
-def test_selector_scores_device_vs_opencv(cuda):
-    """The whole scoring call on 16 channels x 21 frames of 60 x 104: device path vs OpenCV path, and its timing."""
+@pytest.mark.parametrize("shape", [(60, 104), (90, 160)])
+def test_selector_scores_device_vs_opencv(cuda, shape):
+    """The whole scoring call on 16 channels x 21 latent frames (60 x 104 at 480p: one pyramid level; 90 x 160 at 720p: two):
+    device path vs OpenCV path, and its timing."""
     from worldforge_b200 import flf_select
-    u8 = _clips(32, 21)
+    u8 = _clips(32, 21, shape)
     # latents whose min-max quantisation reproduces the clips: x = u8 / 255 spans [0, 1] in both tensors
     ref = torch.from_numpy(u8[:16].astype(np.float32) / 255.0).unsqueeze(0).to(cuda)
     pred = torch.from_numpy(u8[16:].astype(np.float32) / 255.0).unsqueeze(0).to(cuda)
@@ -77,7 +80,8 @@ def test_selector_scores_device_vs_opencv(cuda):
     torch.cuda.synchronize()
     t0 = time.perf_counter(); dev.scores(pred, ref); torch.cuda.synchronize(); t_dev = time.perf_counter() - t0
     t0 = time.perf_counter(); host.scores(pred, ref); t_host = time.perf_counter() - t0
-    print(f"FLF scoring: device {t_dev * 1e3:.1f} ms, OpenCV on {host.threads} host threads {t_host * 1e3:.1f} ms")
+    print(f"\nFLF scoring {shape}: device {t_dev * 1e3:.1f} ms, OpenCV on {host.threads} host threads {t_host * 1e3:.1f} ms")
+    assert dev.device_path_covers(*shape)
     np.testing.assert_allclose(s_dev, s_host, rtol=0, atol=2e-5)
     for step in (7, 12, 30):
         assert flf_select.selection_policy(s_dev, step) == flf_select.selection_policy(s_host, step)

@@ -41,10 +41,26 @@ int main(int argc, char** argv) {
   std::vector<float> vert(frames * hw * 3), R(frames * hw * 5), M(pairs * hw * 5), flow(pairs * hw * 2);
   std::vector<double> V(pairs * hw * 5);
   FbConst c = fb_constants(1.2);
+  const int extra = fb_extra_levels(H, W);
+  if (extra > 1 || (extra == 1 && (H % 2 || W % 2))) return 3;
+  if (extra == 1) {      // the launch sequence of wf_farneback_u8 for a two-level pyramid
+    const int h2 = H / 2, w2 = W / 2;
+    std::vector<float> half_img(frames * h2 * w2), half_flow(pairs * h2 * w2 * 2);
+    float k3[3]; fb_gauss3(0.5, k3);
+    fb_blur_half_kernel(u8.data(), half_img.data(), (int)frames, H, W, k3[0], k3[1], k3[2]);
+    fb_vertical_f32_kernel(half_img.data(), vert.data(), (int)frames, h2, w2, c);
+    fb_horizontal_kernel(vert.data(), R.data(), (int)frames, h2, w2, c);
+    for (int it = 0; it < 3; ++it) {
+      fb_matrices_kernel(R.data(), half_flow.data(), M.data(), clips, T, h2, w2, it == 0);
+      fb_box_vertical_kernel(M.data(), V.data(), (int)pairs, h2, w2, 7);
+      fb_box_solve_kernel(V.data(), half_flow.data(), (int)pairs, h2, w2, 7, 1.0 / 225.0);
+    }
+    fb_double_flow_kernel(half_flow.data(), flow.data(), (int)pairs, H, W);
+  }
   fb_vertical_kernel(u8.data(), vert.data(), (int)frames, H, W, c);
   fb_horizontal_kernel(vert.data(), R.data(), (int)frames, H, W, c);
   for (int it = 0; it < 3; ++it) {
-    fb_matrices_kernel(R.data(), flow.data(), M.data(), clips, T, H, W, it == 0);
+    fb_matrices_kernel(R.data(), flow.data(), M.data(), clips, T, H, W, it == 0 && extra == 0);
     fb_box_vertical_kernel(M.data(), V.data(), (int)pairs, H, W, 7);
     fb_box_solve_kernel(V.data(), flow.data(), (int)pairs, H, W, 7, 1.0 / 225.0);
   }
@@ -55,7 +71,8 @@ int main(int argc, char** argv) {
 
 
 @pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
-def test_flow_kernel_source_reproduces_the_oracle_on_the_host(tmp_path):
+@pytest.mark.parametrize("H,W", [(60, 104), (90, 160)])           # 480p latent frames: one pyramid level; 720p: two
+def test_flow_kernel_source_reproduces_the_oracle_on_the_host(tmp_path, H, W):
     src = open(os.path.join(ROOT, "worldforge_b200", "csrc", "flow_ops.cu")).read()
     i = src.index("namespace wf {")
     j = src.index("// ---------------------------------------------------------------- 5. flow similarity metrics")
@@ -66,7 +83,7 @@ def test_flow_kernel_source_reproduces_the_oracle_on_the_host(tmp_path):
     exe = tmp_path / "emu"
     subprocess.run(["g++", "-O1", "-ffp-contract=off", "-std=c++17", str(cpp), "-o", str(exe)], check=True)
     rng = np.random.default_rng(5)
-    clips, T, H, W = 3, 3, 60, 104
+    clips, T = 3, 3
     yy, xx = np.mgrid[0:H, 0:W]
     u8 = np.zeros((clips, T, H, W), np.uint8)
     for t in range(T):

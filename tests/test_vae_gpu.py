@@ -71,7 +71,7 @@ def test_mid_attention_and_resblock(cuda):
     xc = x.permute(1, 2, 3, 0).contiguous().to(cuda)
     got = m._attn(xc, "decoder.middle.1", 32).permute(3, 0, 1, 2).cpu()
     assert rel(got, wan_vae.attn_block(P, "decoder.middle.1", x)) < 2e-3
-    got = m._res(xc, "decoder.middle.0", 32, 32).permute(3, 0, 1, 2).cpu()
+    got = m._res(xc, "decoder.middle.0", 32, 32)[0].permute(3, 0, 1, 2).cpu()
     assert rel(got, wan_vae.res_block(P, "decoder.middle.0", x)) < 2e-3
 
 

@@ -66,6 +66,12 @@ struct ConvArgs {
   int planar_clamp;         // 1: out is planar [c_split][frames][out_H][out_W], values clamped to [-1,1]
   long long planar_cstride; // elements between channels in planar mode
   int round_out;            // 1: the stored value is rounded to tf32 (its only consumers are convolutions: see tf32_round)
+  // fused RMS_norm (+SiLU) of the result (vae.py:51-54,195-197): with gamma != null (and one N tile covering all Cout
+  // channels) every output pixel v[0..Cout) also yields a = silu(v / max(|v|, 1e-12) * sqrt(Cout) * gamma), rounded to tf32,
+  // stored to norm_out - or INSTEAD of v when norm_out is null (the raw result has no other reader)
+  const float* norm_gamma;
+  float* norm_out;
+  int norm_silu;
 };
 
 // Epilogue of one 128-pixel x BN tile for epilogue warp q (rows 32q..32q+31 of the tile): TMEM -> registers -> shared-memory
@@ -85,6 +91,46 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvArgs& p, float* til
     row_ok |= (y < p.H && x < p.W) ? (1u << rr) : 0u;
   }
   const size_t frame_elems = static_cast<size_t>(p.out_H) * p.out_W;
+  // ---- fused RMS-norm statistics: TMEM hands each thread one pixel ROW, so the sum of squares over the channels is a
+  // per-thread loop (bias and residual included, exactly the value that is stored); the normalised values are produced in the
+  // store loop below, where a lane owns a channel, with the row's scale fetched from its owner lane by a shuffle
+  float inv = 0.f;
+  if (p.norm_gamma) {
+    const int r_in_tile = q * 32 + lane;
+    const int y = y0 + (r_in_tile >> p.tw_shift), x = x0 + (r_in_tile & (p.TW - 1));
+    const bool own_ok = y < p.H && x < p.W;
+    const size_t own = (static_cast<size_t>(t) * p.t_mul * frame_elems + static_cast<size_t>((y * p.sy + p.oy) * p.out_W + (x * p.sx + p.ox))) * p.ldc;
+    float ss = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < p.BN; c += 16) {
+      uint32_t r[16];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "r"(t_row + c) : "memory");
+      tmem_ld_wait();
+      float rs[16];
+      if (p.resid && own_ok) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 v4 = (c + j < p.Cout) ? *reinterpret_cast<const float4*>(p.resid + own + c + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          rs[j] = v4.x; rs[j + 1] = v4.y; rs[j + 2] = v4.z; rs[j + 3] = v4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) rs[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (c + j < p.Cout) {
+          const float v = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + c + j) : 0.f) + rs[j];
+          ss = fmaf(v, v, ss);
+        }
+      }
+    }
+    inv = sqrtf(static_cast<float>(p.Cout)) / fmaxf(sqrtf(ss), 1e-12f);
+  }
 #pragma unroll 1
   for (int c = 0; c < p.BN; c += 32) {
     const int n = n0 + c;
@@ -122,14 +168,32 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvArgs& p, float* til
       for (int rr = 0; rr < 32; ++rr)
         rv[rr] = ((okm >> rr) & 1u) ? p.resid[base + static_cast<size_t>(row_part[rr]) * pitch] : 0.f;
     }
+    if (p.norm_gamma) {
+      const float gm = col_ok ? p.norm_gamma[col] : 0.f;
+      float* nout = p.norm_out ? p.norm_out : p.out;
 #pragma unroll
-    for (int rr = 0; rr < 32; ++rr) {
-      if ((okm >> rr) & 1u) {
-        float v = tile_s[rr * CV_EPI_LD + lane] + b0;
-        if (p.resid) v += rv[rr];
-        if (p.planar_clamp) v = fminf(fmaxf(v, -1.0f), 1.0f);
-        if (p.round_out) v = tf32_round(v);
-        p.out[base + static_cast<size_t>(row_part[rr]) * pitch] = v;
+      for (int rr = 0; rr < 32; ++rr) {
+        const float inv_r = __shfl_sync(0xffffffffu, inv, rr);         // row rr's scale lives in lane rr
+        if ((okm >> rr) & 1u) {
+          float v = tile_s[rr * CV_EPI_LD + lane] + b0;
+          if (p.resid) v += rv[rr];
+          const size_t at = base + static_cast<size_t>(row_part[rr]) * pitch;
+          if (p.norm_out) p.out[at] = p.round_out ? tf32_round(v) : v;
+          float a = v * inv_r * gm;
+          if (p.norm_silu) a = a / (1.0f + expf(-a));
+          nout[at] = tf32_round(a);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr) {
+        if ((okm >> rr) & 1u) {
+          float v = tile_s[rr * CV_EPI_LD + lane] + b0;
+          if (p.resid) v += rv[rr];
+          if (p.planar_clamp) v = fminf(fmaxf(v, -1.0f), 1.0f);
+          if (p.round_out) v = tf32_round(v);
+          p.out[base + static_cast<size_t>(row_part[rr]) * pitch] = v;
+        }
       }
     }
     __syncwarp();
@@ -477,7 +541,7 @@ extern "C" int wf_conv_tf32(const float* in, int in_T, int in_H, int in_W, int C
                             int Cout, int ntaps, const signed char* taps, int T, int H, int W, int t_stride, int t_off,
                             float* out, int ldc, int out_H, int out_W, int t_mul, int c_split, int sy, int sx, int oy,
                             int ox, const float* resid, int planar_clamp, long long planar_cstride, int tile_w,
-                            int round_out_tf32, void* stream) {
+                            int round_out_tf32, const float* norm_gamma, float* norm_out, int norm_silu, void* stream) {
   WF_REQUIRE(in && weights && out && taps, "wf_conv_tf32: null pointer");
   WF_REQUIRE(Cin > 0 && Cin % 4 == 0, "wf_conv_tf32: Cin must be a positive multiple of 4 (16-byte pixel rows)");
   WF_REQUIRE(Cout > 0 && ntaps > 0 && ntaps <= CV_MAX_TAPS, "wf_conv_tf32: bad Cout / tap count");
@@ -500,6 +564,12 @@ extern "C" int wf_conv_tf32(const float* in, int in_T, int in_H, int in_W, int C
   a.sy = sy; a.sx = sx; a.oy = oy; a.ox = ox; a.bias = bias; a.resid = resid;
   a.planar_clamp = planar_clamp; a.planar_cstride = planar_cstride;
   a.round_out = round_out_tf32 != 0;
+  a.norm_gamma = norm_gamma; a.norm_out = norm_out; a.norm_silu = norm_silu;
+  if (norm_gamma) {
+    WF_REQUIRE(Cout <= CV_MAX_BN && Cout % 4 == 0, "wf_conv_tf32: the fused RMS-norm needs all channels of a pixel in one N tile (Cout <= 192)");
+    WF_REQUIRE(!planar_clamp && c_split == Cout && t_mul == 1 && ldc % 4 == 0, "wf_conv_tf32: the fused RMS-norm needs a plain channels-last output");
+    WF_REQUIRE(!resid || reinterpret_cast<uintptr_t>(resid) % 16 == 0, "wf_conv_tf32: fused RMS-norm: residual must be 16-byte aligned");
+  }
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(in_W), static_cast<uint64_t>(in_H), static_cast<uint64_t>(in_T)};

@@ -3,9 +3,11 @@
 // The reference scores every latent channel by comparing OpenCV Farneback flows of two uint8 clips
 // (scheduling_unipc_multistep_clean.py:156-248 -> cv2.calcOpticalFlowFarneback(prev, next, None, 0.5, 3, 15, 3, 5, 1.2, 0),
 // :497-607 for the metrics) on the CPU: 640 calls + 32 device-to-host copies per guided step, on the critical path.  These
-// kernels restate the algorithm of OpenCV's modules/video/src/optflowgf.cpp for the case the selector hits at 480p - frames
-// of 60 x 104 whose pyramid has ONE level (the driver loop stops when the smaller side would drop under 32 pixels) - as
-// oracle/farneback.py does in numpy (pinned to OpenCV to 4e-6 px, tests/test_farneback_oracle.py):
+// kernels restate the algorithm of OpenCV's modules/video/src/optflowgf.cpp for the two cases the selector hits - frames of
+// 60 x 104 (480p) whose pyramid has ONE level (the driver loop stops when the smaller side would drop under 32 pixels) and
+// frames of 90 x 160 (720p; 88 x 160 for LongCat's refine pass) with TWO: the half-resolution level is
+// GaussianBlur(3 x 3, sigma 0.5) + an exact 2 x 2 mean (cv::resize INTER_LINEAR by 1/2), its flow returns through a bilinear
+// doubling times 2 - as oracle/farneback.py does in numpy (pinned to OpenCV to 4e-6 px / 1e-4 px, tests/test_farneback_oracle.py):
 //
 //   poly_exp      GaussianBlur(3x3, sigma 0) = [1/4 1/2 1/4] reflect-101, then FarnebackPolyExp(n = 5, sigma = 1.2): per pixel
 //                 the 5 coefficients (y, x, yy, xx, xy) of the local quadratic; vertical pass in float, horizontal in double
@@ -31,6 +33,79 @@ struct FbConst {
   float g[2 * FB_N + 1], xg[2 * FB_N + 1], xxg[2 * FB_N + 1];
   double ig11, ig03, ig33, ig55;
 };
+
+// ---------------------------------------------------------------- 0. the half-resolution pyramid level (two-level pyramids)
+// frames: uint8 [nf][H][W] (H, W even) -> half: float [nf][H/2][W/2] = 2x2 mean of GaussianBlur(3x3, k) with reflect-101 borders
+__global__ void fb_blur_half_kernel(const unsigned char* __restrict__ frames, float* __restrict__ half, int nf, int H, int W, float k0,
+                                    float k1, float k2) {
+  const int H2 = H / 2, W2 = W / 2;
+  const size_t total = static_cast<size_t>(nf) * H2 * W2;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int x2 = static_cast<int>(i % W2);
+    const int y2 = static_cast<int>((i / W2) % H2);
+    const unsigned char* img = frames + (i / (static_cast<size_t>(H2) * W2)) * H * W;
+    auto refl = [](int p, int n) { return p < 0 ? -p : (p >= n ? 2 * n - 2 - p : p); };      // BORDER_REFLECT_101
+    auto blurred = [&](int y, int x) {       // rows, then columns, float
+      float col[3];
+#pragma unroll
+      for (int d = -1; d <= 1; ++d) {
+        const unsigned char* row = img + static_cast<size_t>(refl(y + d, H)) * W;
+        float r = __fadd_rn(__fmul_rn(static_cast<float>(row[refl(x - 1, W)]), k0), __fmul_rn(static_cast<float>(row[x]), k1));
+        col[d + 1] = __fadd_rn(r, __fmul_rn(static_cast<float>(row[refl(x + 1, W)]), k2));
+      }
+      return __fadd_rn(__fadd_rn(__fmul_rn(col[0], k0), __fmul_rn(col[1], k1)), __fmul_rn(col[2], k2));
+    };
+    const float a = blurred(2 * y2, 2 * x2), b = blurred(2 * y2, 2 * x2 + 1), c = blurred(2 * y2 + 1, 2 * x2), d = blurred(2 * y2 + 1, 2 * x2 + 1);
+    half[i] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(a, b), c), d), 0.25f);
+  }
+}
+
+// vertical pass of the polynomial expansion on a float image (the half-resolution level is not smoothed again)
+__global__ void fb_vertical_f32_kernel(const float* __restrict__ imgs, float* __restrict__ vert, int nf, int H, int W, FbConst c) {
+  const size_t total = static_cast<size_t>(nf) * H * W;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % W);
+    const int y = static_cast<int>((i / W) % H);
+    const float* img = imgs + (i / (static_cast<size_t>(H) * W)) * H * W;
+    auto at = [&](int yy) { return img[static_cast<size_t>(yy) * W + x]; };
+    float r0 = __fmul_rn(at(y), c.g[FB_N]), r1 = 0.f, r2 = 0.f;
+#pragma unroll
+    for (int k = 1; k <= FB_N; ++k) {
+      const float up = at(max(y - k, 0)), dn = at(min(y + k, H - 1));
+      const float p = __fadd_rn(up, dn);
+      r0 = __fadd_rn(r0, __fmul_rn(c.g[FB_N + k], p));
+      r1 = __fadd_rn(r1, __fmul_rn(c.xg[FB_N + k], __fsub_rn(dn, up)));
+      r2 = __fadd_rn(r2, __fmul_rn(c.xxg[FB_N + k], p));
+    }
+    float* o = vert + i * 3;
+    o[0] = r0; o[1] = r1; o[2] = r2;
+  }
+}
+
+// flow of the half-resolution level -> initial flow of the full level: cv::resize(INTER_LINEAR) by 2 (source coordinate
+// (dst + 0.5) / 2 - 0.5, taps clamped) times 1 / pyr_scale = 2.  half [pairs][H/2][W/2][2] -> flow [pairs][H][W][2]
+__global__ void fb_double_flow_kernel(const float* __restrict__ half, float* __restrict__ flow, int pairs, int H, int W) {
+  const int H2 = H / 2, W2 = W / 2;
+  const size_t total = static_cast<size_t>(pairs) * H * W;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % W);
+    const int y = static_cast<int>((i / W) % H);
+    const float* src = half + (i / (static_cast<size_t>(H) * W)) * H2 * W2 * 2;
+    // (d + 0.5) / 2 - 0.5 = d/2 - 0.25: floor and fraction are exact in integers (fraction 0.75 for even d, 0.25 for odd d)
+    const int ix = (x & 1) ? (x - 1) / 2 : x / 2 - 1, iy = (y & 1) ? (y - 1) / 2 : y / 2 - 1;
+    const float wx = (x & 1) ? 0.25f : 0.75f, wy = (y & 1) ? 0.25f : 0.75f;
+    const int x0 = min(max(ix, 0), W2 - 1), x1 = min(max(ix + 1, 0), W2 - 1);
+    const int y0 = min(max(iy, 0), H2 - 1), y1 = min(max(iy + 1, 0), H2 - 1);
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      const float p00 = src[(static_cast<size_t>(y0) * W2 + x0) * 2 + ch], p01 = src[(static_cast<size_t>(y0) * W2 + x1) * 2 + ch];
+      const float p10 = src[(static_cast<size_t>(y1) * W2 + x0) * 2 + ch], p11 = src[(static_cast<size_t>(y1) * W2 + x1) * 2 + ch];
+      const float top = __fadd_rn(__fmul_rn(p00, __fsub_rn(1.f, wx)), __fmul_rn(p01, wx));
+      const float bot = __fadd_rn(__fmul_rn(p10, __fsub_rn(1.f, wx)), __fmul_rn(p11, wx));
+      flow[i * 2 + ch] = __fmul_rn(__fadd_rn(__fmul_rn(top, __fsub_rn(1.f, wy)), __fmul_rn(bot, wy)), 2.0f);
+    }
+  }
+}
 
 // ---------------------------------------------------------------- 1. blur + vertical pass of the polynomial expansion
 // frames: uint8 [nf][H][W] -> vert: float [nf][H][W][3]
@@ -251,6 +326,24 @@ static FbConst fb_constants(double sigma) {
   return c;
 }
 
+// cv::getGaussianKernel(3, sigma > 0, CV_32F): [e s, s, e s] with e = exp(-1 / (2 sigma^2)), s = 1 / (1 + 2 e)
+static void fb_gauss3(double sigma, float k[3]) {
+  const double e = std::exp(-1.0 / (2.0 * sigma * sigma)), s = 1.0 / (1.0 + 2.0 * e);
+  k[0] = k[2] = static_cast<float>(e * s);
+  k[1] = static_cast<float>(s);
+}
+
+// number of pyramid levels BELOW full resolution the OpenCV driver runs for (pyr_scale 0.5, levels 3)
+static int fb_extra_levels(int H, int W) {
+  int k = 0;
+  double scale = 1.0;
+  for (; k < 3; ++k) {
+    scale *= 0.5;
+    if (W * scale < 32 || H * scale < 32) break;
+  }
+  return k;
+}
+
 }  // namespace wf
 
 using namespace wf;
@@ -262,35 +355,57 @@ static int flow_grid(size_t n) {
 extern "C" long long wf_farneback_workspace_bytes(int clips, int T, int H, int W) {
   const long long hw = static_cast<long long>(H) * W;
   const long long frames = static_cast<long long>(clips) * T, pairs = static_cast<long long>(clips) * (T - 1);
-  // vert (frames*hw*3 f32) | R (frames*hw*5 f32) | M (pairs*hw*5 f32) | V (pairs*hw*5 f64), each rounded to 256 B
+  // vert (frames*hw*3 f32) | R (frames*hw*5 f32) | M (pairs*hw*5 f32) | V (pairs*hw*5 f64) | half-resolution images
+  // (frames*hw/4 f32) | half-resolution flow (pairs*hw/4*2 f32), each rounded to 256 B; the first four serve both levels
   auto r = [](long long b) { return (b + 255) / 256 * 256; };
-  return r(frames * hw * 3 * 4) + r(frames * hw * 5 * 4) + r(pairs * hw * 5 * 4) + r(pairs * hw * 5 * 8);
+  return r(frames * hw * 3 * 4) + r(frames * hw * 5 * 4) + r(pairs * hw * 5 * 4) + r(pairs * hw * 5 * 8) + r(frames * (hw / 4) * 4) +
+         r(pairs * (hw / 4) * 2 * 4);
 }
 
 extern "C" int wf_farneback_u8(const unsigned char* clips_u8, int clips, int T, int H, int W, int winsize, int iterations,
                                float* flow, void* workspace, void* stream) {
   WF_REQUIRE(clips_u8 && flow && workspace, "wf_farneback_u8: null pointer");
   WF_REQUIRE(clips > 0 && T >= 2 && H >= 2 * FB_BORDER && W >= 2 * FB_BORDER, "wf_farneback_u8: empty clips or frames smaller than 10x10");
-  WF_REQUIRE(std::min(H, W) * 0.5 < 32, "wf_farneback_u8: only frames whose Farneback pyramid has one level (min side < 64)");
+  const int extra = fb_extra_levels(H, W);
+  WF_REQUIRE(extra == 0 || (extra == 1 && H % 2 == 0 && W % 2 == 0),
+             "wf_farneback_u8: frames whose Farneback pyramid has one level (min side < 64) or two with even sides (min side < 128)");
   WF_REQUIRE(winsize >= 3 && (winsize & 1) && iterations >= 1, "wf_farneback_u8: odd window >= 3, at least one iteration");
   const size_t hw = static_cast<size_t>(H) * W;
   const size_t frames = static_cast<size_t>(clips) * T, pairs = static_cast<size_t>(clips) * (T - 1);
   auto r = [](size_t b) { return (b + 255) / 256 * 256; };
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  float* vert = reinterpret_cast<float*>(ws);
-  float* R = reinterpret_cast<float*>(ws + r(frames * hw * 3 * 4));
-  float* M = reinterpret_cast<float*>(ws + r(frames * hw * 3 * 4) + r(frames * hw * 5 * 4));
-  double* V = reinterpret_cast<double*>(ws + r(frames * hw * 3 * 4) + r(frames * hw * 5 * 4) + r(pairs * hw * 5 * 4));
+  float* vert = reinterpret_cast<float*>(ws); ws += r(frames * hw * 3 * 4);
+  float* R = reinterpret_cast<float*>(ws); ws += r(frames * hw * 5 * 4);
+  float* M = reinterpret_cast<float*>(ws); ws += r(pairs * hw * 5 * 4);
+  double* V = reinterpret_cast<double*>(ws); ws += r(pairs * hw * 5 * 8);
+  float* half_img = reinterpret_cast<float*>(ws); ws += r(frames * (hw / 4) * 4);
+  float* half_flow = reinterpret_cast<float*>(ws);
   static const FbConst c = fb_constants(1.2);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int m = winsize / 2;
+  const double box_scale = 1.0 / (static_cast<double>(winsize) * winsize);
+  auto iterate = [&](float* fl, int h, int w, bool zero_start) {
+    const size_t n = pairs * static_cast<size_t>(h) * w;
+    for (int it = 0; it < iterations; ++it) {
+      fb_matrices_kernel<<<flow_grid(n), 256, 0, st>>>(R, fl, M, clips, T, h, w, (it == 0 && zero_start) ? 1 : 0);
+      fb_box_vertical_kernel<<<flow_grid(n * 5), 256, 0, st>>>(M, V, static_cast<int>(pairs), h, w, m);
+      fb_box_solve_kernel<<<flow_grid(n), 256, 0, st>>>(V, fl, static_cast<int>(pairs), h, w, m, box_scale);
+    }
+  };
+  if (extra == 1) {
+    // half-resolution level first: sigma = (1 / 0.5 - 1) * 0.5 = 0.5, 3 x 3 kernel, exact 2 x 2 mean; flow starts at zero
+    const int h2 = H / 2, w2 = W / 2;
+    float k3[3];
+    fb_gauss3(0.5, k3);
+    fb_blur_half_kernel<<<flow_grid(frames * h2 * w2), 256, 0, st>>>(clips_u8, half_img, static_cast<int>(frames), H, W, k3[0], k3[1], k3[2]);
+    fb_vertical_f32_kernel<<<flow_grid(frames * h2 * w2), 256, 0, st>>>(half_img, vert, static_cast<int>(frames), h2, w2, c);
+    fb_horizontal_kernel<<<flow_grid(frames * h2 * w2), 256, 0, st>>>(vert, R, static_cast<int>(frames), h2, w2, c);
+    iterate(half_flow, h2, w2, true);
+    fb_double_flow_kernel<<<flow_grid(pairs * hw), 256, 0, st>>>(half_flow, flow, static_cast<int>(pairs), H, W);
+  }
   fb_vertical_kernel<<<flow_grid(frames * hw), 256, 0, st>>>(clips_u8, vert, static_cast<int>(frames), H, W, c);
   fb_horizontal_kernel<<<flow_grid(frames * hw), 256, 0, st>>>(vert, R, static_cast<int>(frames), H, W, c);
-  const int m = winsize / 2;
-  for (int it = 0; it < iterations; ++it) {
-    fb_matrices_kernel<<<flow_grid(pairs * hw), 256, 0, st>>>(R, flow, M, clips, T, H, W, it == 0 ? 1 : 0);
-    fb_box_vertical_kernel<<<flow_grid(pairs * hw * 5), 256, 0, st>>>(M, V, static_cast<int>(pairs), H, W, m);
-    fb_box_solve_kernel<<<flow_grid(pairs * hw), 256, 0, st>>>(V, flow, static_cast<int>(pairs), H, W, m, 1.0 / (static_cast<double>(winsize) * winsize));
-  }
+  iterate(flow, H, W, extra == 0);
   WF_LAUNCH_OK();
   return WF_OK;
 }

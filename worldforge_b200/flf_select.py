@@ -8,12 +8,12 @@ latents with that of the model's prediction, after quantising each channel to ui
 * the min-max quantisation of both 16-channel tensors runs on the GPU (``wf_quantise_u8``,
   two passes over 2 MB) so 4 MB of uint8 cross PCIe instead of 16 MB of fp32 in 32 copies;
 * Farneback - OpenCV in the reference, its own third-party dependency for this step, whose discrete
-  outcome (an argsort over 16 scores) must not drift - runs on the GPU for frames whose pyramid has a
-  single level (the 480p latent frames): ``wf_farneback_u8`` + ``wf_flow_metrics``, 2.3 ms against
-  81 ms for a 16-channel x 21-frame call, flows equal to OpenCV's to ~3e-6 px, identical scores and
-  selections (tests/test_flow_gpu.py).  Other frame sizes (720p: two pyramid
-  levels) and WF_FLF_GPU=0 keep OpenCV on the host, the 640 independent frame pairs spread over a
-  thread pool (OpenCV releases the GIL);
+  outcome (an argsort over 16 scores) must not drift - runs on the GPU for frames whose pyramid has one
+  level (the 60 x 104 latent frames of 480p) or two (90 x 160 at 720p): ``wf_farneback_u8`` +
+  ``wf_flow_metrics``, 2.3 ms against 81 ms for a 16-channel x 21-frame call at 480p, flows equal to
+  OpenCV's to ~3e-6 px (one level) / ~1e-4 px (two levels), identical scores and selections
+  (tests/test_flow_gpu.py).  Other frame sizes and WF_FLF_GPU=0 keep OpenCV on
+  the host, the 640 independent frame pairs spread over a thread pool (OpenCV releases the GIL);
 * the flow metrics (M-EPE / Fl-all / M-AE, :541-604) are evaluated where the flows already are,
   on the host, in the same fp32 torch expressions;
 * steps whose policy cannot select anything (step <= 5, :412-417) skip the flow computation.
@@ -87,13 +87,19 @@ class FlowChannelSelector:
     def __init__(self, threads: int = 0, group=None, world: int = 1, rank: int = 0, device_flow=None):
         self.group, self.world, self.rank = group, world, rank
         # device_flow: Farneback + the flow metrics on the GPU (wf_farneback_u8 / wf_flow_metrics) for frames whose pyramid has
-        # a single level (10 <= min side < 64: the 60 x 104 latent frames of 480p); other sizes, and WF_FLF_GPU=0, use OpenCV
-        # on host threads.  The kernels agree with OpenCV to ~3e-6 px; scores, selections and a 14-step guided trajectory are
+        # one or two levels (device_path_covers); other sizes, and WF_FLF_GPU=0, use OpenCV on host threads.  The kernels agree with OpenCV to ~3e-6 px; scores, selections and a 14-step guided trajectory are
         # identical through either path (tests/test_flow_gpu.py, tests/test_guided_loop_gpu.py).
         self.device_flow = (os.environ.get("WF_FLF_GPU", "1") == "1") if device_flow is None else bool(device_flow)
         self.threads = threads or max(1, min(32, (os.cpu_count() or 8) // max(world, 1)))
         self._pool = None
         self.last_scores = None
+
+    @staticmethod
+    def device_path_covers(H: int, W: int) -> bool:
+        """wf_farneback_u8 restates the one-level pyramid (10 <= min side < 64: the 60 x 104 latent frames of 480p) and the
+        two-level one with even sides (64 <= min side < 128: 90 x 160 at 720p, 88 x 160 in LongCat's refine pass)."""
+        m = min(H, W)
+        return 10 <= m < 64 or (64 <= m < 128 and H % 2 == 0 and W % 2 == 0)
 
     def _flows(self, u8: np.ndarray) -> torch.Tensor:
         """uint8 [C,T,H,W] -> fp32 [C, T-1, 2, H, W]."""
@@ -114,7 +120,7 @@ class FlowChannelSelector:
         pred_u8 = lib.quantise_u8(pred_x0.contiguous())
         nc = ref_u8.shape[1]
         c0, c1 = (self.rank * nc) // self.world, ((self.rank + 1) * nc) // self.world
-        if self.device_flow and 10 <= min(ref_u8.shape[-2:]) < 64 and c1 > c0:      # single-level pyramid, frames >= 10 x 10
+        if self.device_flow and self.device_path_covers(*ref_u8.shape[-2:]) and c1 > c0:
             T, H, W = ref_u8.shape[2:]
             clips = torch.cat([ref_u8[0, c0:c1], pred_u8[0, c0:c1]]).contiguous()       # [2C', T, H, W] uint8, on the device
             flows = lib.farneback_u8(clips)                                              # [2C', T-1, H, W, 2]

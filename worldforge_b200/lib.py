@@ -66,7 +66,7 @@ _SIGNATURES = {
     "wf_refine_upsample": [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp],
     "wf_cfg_zero": [_vp, _vp, _vp, _f, _ll, _vp, _vp, _vp],
     "wf_conv_tf32": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i,
-                     _vp, _i, _ll, _i, _i, _vp],
+                     _vp, _i, _ll, _i, _i, _vp, _vp, _i, _vp],
     "wf_rms_norm_cl": [_vp, _i, _vp, _i, _vp, _ll, _i, _i, _i, _vp],
     "wf_planar_to_cl": [_vp, _vp, _ll, _i, _i, _i, _vp],
     "wf_round_tf32": [_vp, _vp, _ll, _vp],
@@ -519,11 +519,14 @@ def refine_upsample(video_u8, F2: int, H: int, W: int, pad_front: int = 0, pad_b
 # ------------------------------------------------------------------------------ VAE kernels
 
 def conv_tf32(inp, weights, bias, taps, out, *, T, H, W, Cout, t_stride=1, t_off=0, t_mul=1, c_split=None, sy=1, sx=1,
-              oy=0, ox=0, resid=None, planar_clamp=False, tile_w=16, out_hw=None, ldc=None, round_out=False):
+              oy=0, ox=0, resid=None, planar_clamp=False, tile_w=16, out_hw=None, ldc=None, round_out=False,
+              norm_gamma=None, norm_out=None, norm_silu=True):
     """inp: channels-last fp32 [in_T, in_H, in_W, Cin]; weights fp32 [ntaps*Cout, Cin]; taps: list of (dt,dy,dx).
     out: channels-last fp32 [frames, out_H, out_W, ldc] (or planar [c, frames, out_H, out_W] with planar_clamp).
     The tensor core truncates its fp32 operands to tf32: pass operands already ROUNDED to tf32 (round_tf32 / round_out of
-    the producers) to get cuDNN's round-to-nearest arithmetic.  round_out: store ``out`` rounded to tf32."""
+    the producers) to get cuDNN's round-to-nearest arithmetic.  round_out: store ``out`` rounded to tf32.
+    norm_gamma: fuse the RMS-norm (+SiLU) that follows this convolution into its epilogue (Cout <= 192): the normalised,
+    tf32-rounded activation goes to ``norm_out``, or replaces the raw result in ``out`` when ``norm_out`` is None."""
     assert inp.dtype == torch.float32 and inp.is_contiguous() and inp.dim() == 4
     in_T, in_H, in_W, Cin = inp.shape
     ntaps = len(taps)
@@ -542,7 +545,7 @@ def conv_tf32(inp, weights, bias, taps, out, *, T, H, W, Cout, t_stride=1, t_off
         cstride = 0
     _call("wf_conv_tf32", _p(inp), in_T, in_H, in_W, Cin, _p(weights), _p(bias), Cout, ntaps, C.cast(tb, _vp), T, H, W,
           t_stride, t_off, _p(out), ld, oH, oW, t_mul, cs, sy, sx, oy, ox, _p(resid), int(planar_clamp), cstride, tile_w,
-          int(round_out), _stream())
+          int(round_out), _p(norm_gamma), _p(norm_out), int(norm_silu), _stream())
     return out
 
 

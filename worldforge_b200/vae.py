@@ -21,7 +21,10 @@ few dozen full-grid launches:
 * nearest-exact 2x upsampling is never materialised: upsample + 3x3 conv = four 2x2-tap convolutions on the
   low-resolution tensor (one per output parity) with pre-summed weights;
 * pad(0,1,0,1) + stride-2 3x3 conv = a 2x2-tap convolution on the space-to-depth tensor;
-* RMS-norm + SiLU is one fused pass (``wf_rms_norm_cl``).
+* RMS-norm + SiLU rides in the epilogue of the convolution that PRODUCES its input wherever one accumulator tile holds
+  all channels of a pixel (<= 192 channels: every full- and half-resolution layer): the norm between a residual block's two
+  convolutions replaces the first one's raw result, and the norm that opens the next block (or the head) is stored next to
+  the second one's result; only the 384-channel layers and the layers behind a resampling step use ``wf_rms_norm_cl``.
 
 Multi-GPU (``enable_row_sharding``): the causal feature caches forbid a split along frames, but every layer outside
 the mid block is local in space, so the P ranks of one box split the image ROWS.  Each rank evaluates the sharded
@@ -232,23 +235,36 @@ class WfWanVAE:
         return 16 if w % 16 == 0 else 8
 
     def _conv(self, x, wname, taps, cout, *, resid=None, t_out=None, t_stride=1, t_off=0, out=None, t_mul=1, c_split=None,
-              round_out=False):
+              round_out=False, norm_gamma=None, norm_out=None, norm_silu=True):
         T, H, Wd, _ = x.shape
         t_out = T if t_out is None else t_out
         if out is None:
             out = torch.empty(t_out * t_mul, H, Wd, cout if c_split is None else c_split, dtype=F32, device=x.device)
         lib.conv_tf32(x, self.w[wname + ".w"], self.w[wname + ".b"], taps, out, T=t_out, H=H, W=Wd, Cout=cout,
                       t_stride=t_stride, t_off=t_off, t_mul=t_mul, c_split=c_split, resid=resid, tile_w=self._tile_w(Wd),
-                      round_out=round_out)
+                      round_out=round_out, norm_gamma=norm_gamma, norm_out=norm_out, norm_silu=norm_silu)
         return out
 
-    def _res(self, x, name, cin, cout):
+    FUSE_NORM_MAX_C = 192      # wf_conv_tf32 fuses the following RMS-norm when one accumulator tile holds a pixel's channels
+
+    def _res(self, x, name, cin, cout, pre=None, next_gamma=None):
+        """ResidualBlock (vae.py:186-220).  ``pre``: silu(norm0(x)) if the layer in front already produced it in its
+        epilogue.  ``next_gamma``: gamma of the NEXT layer's first norm - then this block's second convolution stores that
+        activation too and (out, activation) is returned.  The norm between the two convolutions is always fused into the
+        first one's epilogue (its raw result has no other reader) when the width allows."""
         # the 1x1 shortcut reads the raw residual stream: a tf32-rounded copy is its operand (x itself stays exact)
         h = self._conv(lib.round_tf32(x), name + ".shortcut", TAPS_1, cout) if cin != cout else x
-        y = lib.rms_norm_cl(x, self.w[name + ".residual.0.gamma"])
-        y = self._conv(y, name + ".residual.2", TAPS_333, cout)
-        lib.rms_norm_cl(y, self.w[name + ".residual.3.gamma"], out=y)
-        return self._conv(y, name + ".residual.6", TAPS_333, cout, resid=h, round_out=name in self._round_out)
+        y = pre if pre is not None else lib.rms_norm_cl(x, self.w[name + ".residual.0.gamma"])
+        if cout <= self.FUSE_NORM_MAX_C:
+            y = self._conv(y, name + ".residual.2", TAPS_333, cout, norm_gamma=self.w[name + ".residual.3.gamma"])
+        else:
+            y = self._conv(y, name + ".residual.2", TAPS_333, cout)
+            lib.rms_norm_cl(y, self.w[name + ".residual.3.gamma"], out=y)
+        if next_gamma is not None:
+            act = torch.empty(*y.shape[:3], cout, dtype=F32, device=x.device)
+            out = self._conv(y, name + ".residual.6", TAPS_333, cout, resid=h, norm_gamma=next_gamma, norm_out=act)
+            return out, act
+        return self._conv(y, name + ".residual.6", TAPS_333, cout, resid=h, round_out=name in self._round_out), None
 
     def _attn(self, x, name, c):
         T, H, Wd, _ = x.shape
@@ -319,21 +335,30 @@ class WfWanVAE:
         return out
 
     def _run(self, plan, x, final_planar=None):
-        for kind, name, cin, cout in plan:
+        """``final_planar``: the decoder head's output tensor (planar, clamped), or "alloc" to allocate it here."""
+        pre = None                 # silu(norm(x)) handed over by the previous residual block's epilogue
+        for i, (kind, name, cin, cout) in enumerate(plan):
             if kind == "conv":
-                x = self._conv(x, name, TAPS_333, cout)
+                x, pre = self._conv(x, name, TAPS_333, cout), None
             elif kind == "res":
-                x = self._res(x, name, cin, cout)
+                nxt = plan[i + 1] if i + 1 < len(plan) else None
+                ng = None
+                if nxt is not None and cout <= self.FUSE_NORM_MAX_C and nxt[0] in ("res", "head"):
+                    ng = self.w[nxt[1] + (".residual.0.gamma" if nxt[0] == "res" else ".0.gamma")]
+                x, pre = self._res(x, name, cin, cout, pre=pre, next_gamma=ng)
             elif kind == "attn":
-                x = self._attn(x, name, cin)
+                x, pre = self._attn(x, name, cin), None
             elif kind in ("down2d", "down3d"):
-                x = self._down(x, name, cin, kind == "down3d")
+                x, pre = self._down(x, name, cin, kind == "down3d"), None
             elif kind in ("up2d", "up3d"):
-                x = self._up(x, name, cin, kind == "up3d")
+                x, pre = self._up(x, name, cin, kind == "up3d"), None
             elif kind == "head":
-                y = lib.rms_norm_cl(x, self.w[name + ".0.gamma"])
+                y = pre if pre is not None else lib.rms_norm_cl(x, self.w[name + ".0.gamma"])
+                pre = None
                 if final_planar is not None:
                     T, H, Wd, _ = y.shape
+                    if isinstance(final_planar, str):
+                        final_planar = torch.empty(cout, T, H, Wd, dtype=F32, device=y.device)
                     lib.conv_tf32(y, self.w[name + ".2.w"], self.w[name + ".2.b"], TAPS_333, final_planar, T=T, H=H, W=Wd,
                                   Cout=cout, planar_clamp=True, tile_w=self._tile_w(Wd))
                     x = final_planar
@@ -384,23 +409,26 @@ class WfWanVAE:
 
     def _run_rows(self, seg, x, a: int, need, final_planar_rows=None):
         """Run ``seg`` on a row slab: ``x`` [T, rows, W, C] holds image rows a.. of the segment's input.  Before every
-        resampling layer the slab is cut down to the rows still needed.  Returns (output slab, its first image row)."""
-        for i, (kind, name, cin, cout) in enumerate(seg):
+        resampling layer the slab is cut down to the rows still needed; the layers between two cuts run as ONE ``_run`` call,
+        so the cross-layer epilogue fusions are the same as in the unsharded evaluation (bit-identical results).
+        Returns (output slab, its first image row)."""
+        i = 0
+        while i < len(seg):
+            j = i + 1
+            while j < len(seg) and seg[j][0] not in self.UPS and seg[j][0] not in self.DOWNS:
+                j += 1
             lo, hi = need[i]
-            if i == 0 or kind in self.UPS or kind in self.DOWNS:
-                if lo > a or hi < a + x.shape[1]:
-                    x = x[:, lo - a:hi - a].contiguous()
-                    a = lo
-            if kind == "head" and final_planar_rows is not None:
-                T, H, Wd, _ = x.shape
-                y = lib.rms_norm_cl(x, self.w[name + ".0.gamma"])
-                out = torch.empty(cout, T, H, Wd, dtype=F32, device=x.device)
-                lib.conv_tf32(y, self.w[name + ".2.w"], self.w[name + ".2.b"], TAPS_333, out, T=T, H=H, W=Wd, Cout=cout,
-                              planar_clamp=True, tile_w=self._tile_w(Wd))
-                lo, hi = final_planar_rows
-                return out[:, :, lo - a:hi - a], lo
-            x = self._run([(kind, name, cin, cout)], x)
+            if lo > a or hi < a + x.shape[1]:
+                x = x[:, lo - a:hi - a].contiguous()
+                a = lo
+            kind = seg[i][0]
+            last_is_planar_head = seg[j - 1][0] == "head" and final_planar_rows is not None
+            x = self._run(seg[i:j], x, final_planar="alloc" if last_is_planar_head else None)
             a = a * 2 if kind in self.UPS else a // 2 if kind in self.DOWNS else a
+            if last_is_planar_head:
+                lo, hi = final_planar_rows
+                return x[:, :, lo - a:hi - a], lo
+            i = j
         lo, hi = need[-1]
         return x[:, lo - a:hi - a], lo
 
