@@ -59,12 +59,18 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=832)
-    ap.add_argument("--frames", type=int, default=81)
-    ap.add_argument("--layers", type=int, default=40, help="DiT depth (40 = Wan2.1-14B; smaller only for dry runs)")
+    ap.add_argument("--frames", type=int, default=None, help="default 81 (wan) / 93 (longcat)")
+    ap.add_argument("--model", default="wan", choices=["wan", "longcat"],
+                    help="wan: Wan2.1-I2V-14B guided sampling (BASELINE configs[1], the headline); longcat: LongCat-Video distilled "
+                         "16-step guided i2v (configs[3]; 93 frames unless --frames is given)")
+    ap.add_argument("--layers", type=int, default=None, help="DiT depth (default: 40 for Wan2.1-14B, 48 for LongCat; smaller only for dry runs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the PyTorch + flash-attn comparator leg (N=1 only)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    a.frames = a.frames if a.frames is not None else (81 if a.model == "wan" else 93)
+    a.layers = a.layers if a.layers is not None else (40 if a.model == "wan" else 48)
+    return a
 
 
 def peaks():
@@ -326,7 +332,7 @@ def run_ours(args):
     launches = lib.launches
     attn = list(lib.timed_attention or [])
     lib.timed_attention = None
-    attn_ms = [a.elapsed_time(b) for a, b in attn]
+    attn_ms = [a.elapsed_time(b) for a, b, _, _ in attn]
     e2e = None
     if not args.no_e2e:
         ms_e, h2d, d2h, _ = run(from_host=True)
@@ -374,10 +380,122 @@ def run_ours(args):
     emit(line)
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# LongCat-Video (BASELINE configs[3]): distilled 16-step guided i2v, 480p, one GPU
+# ----------------------------------------------------------------------------------------------------------------
+
+def run_longcat(args):
+    """K outer steps of generate_i2v's loop (pipeline_longcat_video.py:828-994) on the engine: LongCat-Video 13.6 B DiT
+    (48 blocks, 4096 wide, 32 heads; no CFG in distilled mode -> one forward per IRR round), Euler scheduler, IRR
+    (resample_steps 2), FLF (VAE decode -> blend -> encode, per-channel Farneback selection on the host) and DSG.  The
+    16-step distilled run guides its first 10 steps (run_test_case.sh: 8-11): a K-step measurement keeps that 5:3 mix.
+    e2e: after every step the latents are read back to pinned host memory and every input of the next step (latents, text
+    embeddings, and for guided steps the warped clip and mask) is uploaded again, inside the timed region."""
+    import torch
+    from worldforge_b200 import lib, longcat, longcat_pipeline as wlp, synth, vae as wvae
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != 1:
+        if int(os.environ.get("RANK", "0")) == 0:
+            emit({"metric": "denoising_steps_per_sec_longcat_video", "unavailable": "LongCat context parallelism is not wired (DESIGN.md §7): run with --gpus 1"})
+        return
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    lib.load()
+    cfg = longcat.LongCatConfig(depth=args.layers)
+    dit = longcat.WfLongCatTransformer.random_init(cfg, dev, seed=1234)
+    vae = wvae.WfWanVAE.random_init(dev, seed=4321)
+    inp = synth.make_inputs(args.frames, args.height, args.width, seed=42)
+    T, h, w = (args.frames - 1) // 4 + 1, args.height // 8, args.width // 8
+    N = T * (h // 2) * (w // 2)
+    K, W = args.steps, args.warmup
+    k_guided = round(0.625 * K)
+    total, guide = W + K, W + k_guided
+    assert total <= 50, "the distilled schedule has 50 anchor steps"
+    pe = inp.prompt_embeds.unsqueeze(0)                                   # [1, 1, 512, 4096] bf16; distilled mode: no CFG batch
+    pm = torch.zeros(1, pe.shape[2], dtype=torch.int64); pm[:, :64] = 1
+    host = {k: v.contiguous().pin_memory() for k, v in dict(latents=inp.latents, pe=pe, pm=pm, video_ref=inp.video_ref, mask=inp.mask).items()}
+    devt = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    lat_host = torch.empty_like(host["latents"]).pin_memory()
+    knobs = dict(guidance_scale=1.0, do_cfg=False, use_distill=True, guided=True, resample_steps=2, guide_steps=guide,
+                 resample_round=guide, omega=4.0, omega_resample=4.0, use_pca_channel_selection=True, max_replace_threshold=3)
+    clocks = ClockSampler(0)
+    state = {}
+
+    def run(from_host: bool):
+        sched = wlp.WfFlowMatchEulerScheduler(shift=1.0)
+        ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+        cnt = dict(h2d=0, d2h=0)
+        latents = devt["latents"].clone()
+
+        def on_step(i, lat):
+            if i == W - 1:                     # the last warm-up step is done: the timed region starts here
+                torch.cuda.synchronize()
+                lib.launches = 0
+                if not from_host:
+                    lib.timed_attention = []
+                    clocks.start()
+                ev[0].record()
+            if from_host:                      # result to the host, then the next step's inputs from the host
+                lat_host.copy_(lat, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                if i >= W:
+                    cnt["d2h"] += lat_host.numel() * 4
+                if i < total - 1:
+                    nxt_guided = (i + 1) < guide
+                    lat.copy_(lat_host, non_blocking=True)
+                    devt["pe"].copy_(host["pe"], non_blocking=True); devt["pm"].copy_(host["pm"], non_blocking=True)
+                    if nxt_guided:
+                        devt["video_ref"].copy_(host["video_ref"], non_blocking=True); devt["mask"].copy_(host["mask"], non_blocking=True)
+                    if i >= W - 1:
+                        cnt["h2d"] += lat_host.numel() * 4 + host["pe"].numel() * 2 + host["pm"].numel() * 8
+                        cnt["h2d"] += (host["video_ref"].numel() * 4 + host["mask"].numel() * 4) if nxt_guided else 0
+            if i == total - 1:
+                ev[1].record()
+        wlp.denoise_loop(dit, vae, sched, latents, devt["pe"], devt["pm"], total, video_ref=devt["video_ref"], mask=devt["mask"],
+                         generator=torch.Generator().manual_seed(42), on_step=on_step, **knobs)
+        torch.cuda.synchronize()
+        state["fuse_calls"] = sched.fuse_calls
+        return ev[0].elapsed_time(ev[1]), cnt["h2d"] // max(K, 1), cnt["d2h"] // max(K, 1)
+
+    calls0 = dit.calls
+    ms, _, _ = run(False)
+    clk = clocks.stop()
+    launches = lib.launches
+    fwd = dit.calls - calls0 - 2 * W
+    attn = list(lib.timed_attention or [])
+    lib.timed_attention = None
+    e2e = None
+    if not args.no_e2e:
+        ms_e, h2d, d2h = run(True)
+        e2e = {"value": K / (ms_e / 1000.0), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+    pk = peaks()
+    roof = None
+    if attn:
+        tot_ms = sum(a.elapsed_time(b) for a, b, _, _ in attn)
+        flops = sum(4.0 * lq * lk * cfg.hidden_size for _, _, lq, lk in attn)
+        ach = flops / (tot_ms / 1000.0) / 1e12
+        roof = {"kernel": "attention_tcgen05 (self-attention: noise tokens x all tokens, condition frame x itself)", "bound": "tensor",
+                "achieved": ach, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": ach / pk["bf16"], "traffic": None,
+                "peak_source": pk["src"] + " sustained cuBLAS bf16", "launches_timed": len(attn), "share_of_step": tot_ms / ms}
+    value = K / (ms / 1000.0)
+    emit({
+        "metric": f"denoising_steps_per_sec_longcat_video_distill_480p_{args.frames}f_irr_flf_dsg", "value": value, "unit": UNIT,
+        "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"LongCat-Video 13.6B {args.height}x{args.width} {args.frames}f distilled guided i2v (IRR+FLF+DSG, no CFG), "
+                               f"{k_guided} guided + {K - k_guided} plain timed steps (the 10:6 mix of the 16-step run)",
+                   "tokens": N, "dit_layers": cfg.depth, "dit_forwards_timed": fwd, "vae": "fp32 storage, tf32 tensor-core convs",
+                   "parallelism": "single GPU", "l2_policy": "inputs larger than L2 (27 GB of weights streamed per forward)"},
+        "clocks": clk, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "dit_forwards_per_sec": fwd / (ms / 1000.0),
+        "flops_per_forward": dit.flops_per_forward(N, (h // 2) * (w // 2), 64), "cpu_baseline": None})
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.model == "longcat":
+        run_longcat(args)
     else:
         run_ours(args)
     try:

@@ -25,7 +25,7 @@ class WfError(RuntimeError):
 
 _lib = None
 launches = 0     # kernels launched through this binding (bench.py's gpu_launches)
-timed_attention = None   # bench.py: a list here collects a CUDA-event pair around every self-attention launch
+timed_attention = None   # bench.py: a list here collects (start event, end event, Lq, Lk) of every self-attention launch
 
 _vp, _i, _f, _ll, _u = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_uint
 _SIGNATURES = {
@@ -164,14 +164,14 @@ def attention_bf16(q, k, v, out, heads: int, add_in=None, softmax_scale: Optiona
         assert t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1
     scale = softmax_scale if softmax_scale is not None else 128 ** -0.5
     ev = None
-    if timed_attention is not None and q.shape[0] == k.shape[0]:
+    if timed_attention is not None and k.shape[0] >= 2048 and 2 * q.shape[0] >= k.shape[0]:     # self-attention, not the 769 / 512-key cross-attention
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()          # on the current stream = the stream the kernel is launched on
     _call("wf_attention_bf16", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
           _p(add_in), add_in.stride(0) if add_in is not None else 0, q.shape[0], k.shape[0], heads, scale, _stream())
     if ev is not None:
         ev[1].record()
-        timed_attention.append(ev)
+        timed_attention.append((ev[0], ev[1], q.shape[0], k.shape[0]))
     return out
 
 
@@ -239,7 +239,7 @@ def attention_bf16_peers(q, k, v, peer_ptrs, rows_per_peer: int, ldo: int, heads
           rows_per_peer, ldo, q.shape[0], k.shape[0], heads, scale, _stream())
     if ev is not None:
         ev[1].record()
-        timed_attention.append(ev)
+        timed_attention.append((ev[0], ev[1], q.shape[0], k.shape[0]))
 
 
 def qkv_norm_rope_scatter(qkv, weight_q, weight_k, rope, eps: float, peer_ptrs, ld_dst: int, row0: int):

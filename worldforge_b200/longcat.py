@@ -173,6 +173,43 @@ class WfLongCatTransformer:
         self.ada_b = torch.cat(ada_b, dim=0).to(device=dev, dtype=BF).contiguous()
         return self
 
+    @classmethod
+    def random_init(cls, cfg: LongCatConfig, device, seed: int = 1234) -> "WfLongCatTransformer":
+        """Random-init weights generated on the device (LongCat-Video is 13.6 B parameters, 27 GB in bf16): N(0, 0.02^2)
+        matrices and biases, norm gains 1 + N(0, 0.05^2) - the same rule as the Wan benchmark model."""
+        self = cls(cfg, device)
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        C, Fd, A = cfg.hidden_size, cfg.ffn_dim, cfg.adaln_tembed_dim
+        def m(n, k, dt=BF):
+            return (torch.randn(n, k, generator=g, device=self.device, dtype=F32) * 0.02).to(dt)
+        def v(n, dt=BF, s=0.02, base=0.0):
+            return (base + torch.randn(n, generator=g, device=self.device, dtype=F32) * s).to(dt)
+        self.patch_w, self.patch_b = m(C, cfg.in_channels * 4), v(C)
+        self.t0_w, self.t0_b, self.t2_w, self.t2_b = m(A, cfg.frequency_embedding_size), v(A), m(A, A), v(A)
+        self.y0_w, self.y0_b, self.y2_w, self.y2_b = m(C, cfg.caption_channels), v(C), m(C, C), v(C)
+        self.final_w, self.final_b = m(cfg.out_channels * 4, C).to(F32), v(cfg.out_channels * 4).to(F32)
+        for _ in range(cfg.depth):
+            b = SimpleNamespace()
+            b.qkv_w, b.qkv_b = m(3 * C, C), v(3 * C)
+            b.qn, b.kn = v(128, BF, 0.05, 1.0), v(128, BF, 0.05, 1.0)
+            b.proj_w, b.proj_b = m(C, C), v(C)
+            b.cq_w, b.cq_b, b.ckv_w, b.ckv_b = m(C, C), v(C), m(2 * C, C), v(2 * C)
+            b.cproj_w, b.cproj_b = m(C, C), v(C)
+            b.cqn, b.ckn = v(128, BF, 0.05, 1.0), v(128, BF, 0.05, 1.0)
+            b.n_w, b.n_b = v(C, BF, 0.05, 1.0).to(F32), v(C).to(F32)
+            b.w13, b.w2 = m(2 * Fd, C), m(C, Fd)
+            self.blocks.append(b)
+        self.ada_w, self.ada_b = m((6 * cfg.depth + 2) * C, A), v((6 * cfg.depth + 2) * C)
+        return self
+
+    def flops_per_forward(self, N: int, n_cond: int, ctx: int) -> float:
+        """Algorithmic FLOPs of one forward over N tokens of which n_cond are condition tokens (2 per MAC): qkv / proj / SwiGLU
+        on every token, cross-attention on the noise tokens, self-attention cond->cond and noise->all."""
+        c = self.cfg
+        C, Fd, Nn = c.hidden_size, c.ffn_dim, N - n_cond
+        per = 2 * N * (4 * C * C + 3 * C * Fd) + 2 * Nn * 2 * C * C + 2 * ctx * 2 * C * C + 4 * C * (n_cond * n_cond + Nn * N) + 4 * Nn * ctx * C
+        return float(c.depth * per)
+
     def _buffers(self, N, Nn, T):
         key = (N, Nn, T)
         if key not in self._buf:
