@@ -107,9 +107,31 @@ def test_pipeline_call_tracks_the_reference_call_fixture(cuda):
          negative_prompt_embeds=inp.negative_prompt_embeds, image_embeds=inp.image_embeds, video_ref=inp.video_ref,
          mask=inp.mask, on_step=lambda i, l: hist.append(l.detach().clone().cpu()), device=cuda, **mg.PIPE_KNOBS)
     assert len(hist) == len(gold["latents"]) == mg.PIPE_STEPS
-    for i, (a, b) in enumerate(zip(hist, gold["latents"])):
+
+    # The floor of this comparison: the ORACLE loop (bit-identical to the reference call on the CPU,
+    # tests/test_oracle_pinning.py) run with the same oracle DiT / VAE on CUDA.  Whatever it differs from the CPU fixture
+    # by is the CPU-vs-CUDA arithmetic of the shared DiT / VAE amplified by the guided trajectory - nothing the engine
+    # controls.  The engine has to stay within 1.5x of that floor at every step (plus one bf16 half-ulp of slack).
+    to = lambda t: t.to(cuda)
+    floor_hist = []
+    o_sched = unipc.OracleUniPC(flow_shift=3.0)
+    opipe.denoise_loop(adapters.OracleTransformer(PD, dcfg, amp=True), adapters.OracleVAE(PV, vcfg), o_sched,
+                       to(inp.latents.clone()), to(gold["condition"]), to(inp.prompt_embeds.to(torch.bfloat16)),
+                       to(inp.negative_prompt_embeds.to(torch.bfloat16)), to(inp.image_embeds.to(torch.bfloat16)),
+                       mg.PIPE_STEPS, 4.0, video_ref=to(inp.video_ref), mask=to(inp.mask),
+                       generator=torch.Generator().manual_seed(42),
+                       on_step=lambda i, l: floor_hist.append(l.detach().clone().cpu()), **mg.PIPE_KNOBS)
+    rel = lambda a, b: ((a.float() - b.float()).norm() / b.float().norm()).item()
+    rows = []
+    for i, (a, f, b) in enumerate(zip(hist, floor_hist, gold["latents"])):
         assert str(a.dtype) == gold["dtypes"][i], (i, a.dtype)
-        rel = ((a.float() - b.float()).norm() / b.float().norm()).item()
-        assert rel < 4e-3, (i, rel)          # bf16 latents (one ulp = 3.9e-3 per element); measured worst 2.0e-3
+        rows.append((rel(a, b), rel(f, b), rel(a, f)))
+    print("\n[floor] reference __call__ fixture (CPU) per step: engine-vs-fixture / oracle-on-CUDA-vs-fixture / engine-vs-oracle-on-CUDA")
+    for i, r in enumerate(rows):
+        print(f"  step {i:2d}: {r[0]:.3e}  {r[1]:.3e}  {r[2]:.3e}")
+    for i, (e, f, _) in enumerate(rows):
+        assert e <= 1.5 * f + 2e-3, (i, e, f)
+    assert max(r[0] for r in rows) < 2e-2
+    assert o_sched.flf_log == sched.flf_log
     picked = [len(c) for _, c in sched.flf_log]
     assert 0 in picked and 1 in picked and max(picked) >= 2
