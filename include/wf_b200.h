@@ -244,6 +244,9 @@ int wf_conv_tf32(const float* in, int in_T, int in_H, int in_W, int Cin, const f
                  int ldc, int out_H, int out_W, int t_mul, int c_split, int sy, int sx, int oy, int ox,
                  const float* resid, int planar_clamp, long long planar_cstride, int tile_w, int round_out_tf32,
                  const float* norm_gamma, float* norm_out, int norm_silu, void* stream);
+/* Development hook (tools/conv_probe.py): a device buffer of >= 16 int64 that CTA 0 of every following 3x3x3 launch fills
+   with its per-role wait / work clocks; NULL switches it off.  Not part of the reference-facing surface. */
+int wf_debug_conv_profile(long long* device_buf);
 /* RMS_norm (vae.py:51-54) over the channels of every pixel, optionally followed by SiLU (:195-197); round_tf32 = 1 stores
    the result rounded to tf32 (it feeds a convolution) */
 int wf_rms_norm_cl(const float* x, int ldx, float* out, int ldo, const float* gamma, long long pixels, int C, int silu,

@@ -50,7 +50,7 @@ int main() {
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int reps = 2000;
   for (int kind : {2, 1, 3})
-    for (int N : {64, 128, 256})
+    for (int N : {64, 96, 128, 192, 256})
       for (int da : {1, 2, 4}) {
         if (da * N > (kind == 3 ? 448 : 512)) continue;
         probe<<<1, 128, smem>>>(kind, N, reps, da, d);

@@ -72,6 +72,8 @@ struct ConvArgs {
   const float* norm_gamma;
   float* norm_out;
   int norm_silu;
+  int rows_epi;             // 1: row-per-thread epilogue with TMA stores (plain channels-last output, BN % 32 == 0, TW <= 32)
+  long long* prof;          // development: per-role wait / work clocks of CTA 0 (wf_debug_conv_profile), or null
 };
 
 // Epilogue of one 128-pixel x BN tile for epilogue warp q (rows 32q..32q+31 of the tile): TMEM -> registers -> shared-memory
@@ -201,6 +203,118 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvArgs& p, float* til
 }
 
 
+// Row-per-thread epilogue for the common placement (plain channels-last output, every channel of the N tile stored): TMEM
+// hands each thread one output PIXEL, and a pixel's channels are contiguous in memory - so nothing is transposed.  Per
+// 32-channel chunk a thread adds bias (+ residual, read with 16-byte loads from its own pixel row), writes its 128 bytes into a
+// SWIZZLE_128B staging tile (16-byte chunk c of row r at c ^ (r & 7): conflict-free) and lane 0 hands the warp's 32 rows
+// ({32 channels, TW pixels, 32 / TW rows} of the output tensor) to a TMA store, which also clips partial tiles.  The fused
+// RMS-norm is thread-local here (a thread owns all channels of its pixel): pass 1 forms v = acc + bias + residual, sums
+// v^2 and writes v back to TMEM; pass 2 re-reads it and stores v (if it has another reader) and silu(v * inv * gamma).
+// The transposing epilogue above spent 57 K clocks per 4-tile block on a plain store and 160-213 K with the fused norm
+// (1296 MMAs of the block: 98 K); this one is bounded by the ~100 instructions per chunk and thread.
+__device__ __forceinline__ void conv_epilogue_rows(const ConvArgs& p, const CUtensorMap* tmOut, const CUtensorMap* tmNorm,
+                                                   uint8_t* stage, const float* bias_s, const float* gamma_s, uint32_t t_row,
+                                                   int q, int lane, int t, int y0, int x0, int n0) {
+  const int r_in_tile = q * 32 + lane;
+  const int y = y0 + (r_in_tile >> p.tw_shift), x = x0 + (r_in_tile & (p.TW - 1));
+  const bool ok = y < p.H && x < p.W;
+  const float* rrow = p.resid ? p.resid + ((static_cast<size_t>(t) * p.out_H + y) * p.out_W + x) * p.ldc + n0 : nullptr;
+  const int nchunks = p.BN >> 5;
+  const int yq = y0 + ((q * 32) >> p.tw_shift);             // first output row of this warp's 32 pixels
+  uint8_t* srow = stage + lane * 128;
+  const int sw = lane & 7;
+  auto put = [&](const float (&o)[32], const CUtensorMap* tm, int c) {
+    if (lane == 0) bulk_wait_read_all();                    // the previous store has read the staging tile
+    __syncwarp();
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch)
+      *reinterpret_cast<float4*>(srow + ((ch ^ sw) << 4)) = make_float4(o[4 * ch], o[4 * ch + 1], o[4 * ch + 2], o[4 * ch + 3]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) { tma_store_4d(tm, stage, n0 + c * 32, x0, yq, t); bulk_commit_group(); }
+  };
+  auto load_v = [&](int c, float (&v)[32], bool add) {
+    uint32_t r[32];
+    float rs[32];
+    if (add && rrow && ok) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 v4 = *reinterpret_cast<const float4*>(rrow + c * 32 + j);
+        rs[j] = v4.x; rs[j + 1] = v4.y; rs[j + 2] = v4.z; rs[j + 3] = v4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) rs[j] = 0.f;
+    }
+    tmem_ld_32x32b_x32(t_row + c * 32, r);
+    tmem_ld_wait();
+    if (add) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = p.bias ? *reinterpret_cast<const float4*>(bias_s + n0 + c * 32 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[j] = __uint_as_float(r[j]) + b4.x + rs[j];
+        v[j + 1] = __uint_as_float(r[j + 1]) + b4.y + rs[j + 1];
+        v[j + 2] = __uint_as_float(r[j + 2]) + b4.z + rs[j + 2];
+        v[j + 3] = __uint_as_float(r[j + 3]) + b4.w + rs[j + 3];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    }
+  };
+  if (!p.norm_gamma) {
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+      float v[32];
+      load_v(c, v, true);
+      if (p.round_out) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = tf32_round(v[j]);
+      }
+      put(v, tmOut, c);
+    }
+    return;
+  }
+  float ss = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < nchunks; ++c) {
+    float v[32];
+    load_v(c, v, true);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
+    uint32_t w[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v[j]);
+    tmem_st_32x32b_x32(t_row + c * 32, w);
+  }
+  tmem_st_wait();
+  const float inv = sqrtf(static_cast<float>(p.Cout)) / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll 1
+  for (int c = 0; c < nchunks; ++c) {
+    float v[32];
+    load_v(c, v, false);
+    if (p.norm_out) {
+      float o[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) o[j] = p.round_out ? tf32_round(v[j]) : v[j];
+      put(o, tmOut, c);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 g4 = *reinterpret_cast<const float4*>(gamma_s + n0 + c * 32 + j);
+      const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float a = v[j + u] * inv * gg[u];
+        if (p.norm_silu) a = a / (1.0f + expf(-a));
+        v[j + u] = tf32_round(a);
+      }
+    }
+    put(v, p.norm_out ? tmNorm : tmOut, c);
+  }
+}
+
+
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -262,33 +376,35 @@ conv_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // -------------------------------------------------------------- MMA issuer (one lane runs the whole loop)
-    if (lane_id() == 0) {
-      const uint32_t idesc = umma_idesc(2, CV_BM, static_cast<uint32_t>(p.BN), 0, 0);   // tf32 x tf32 -> fp32
-      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(smem), 16, 1024);
-      const uint64_t b_desc0 = umma_desc_sw128(smem_u32(smem + CV_A_BYTES), 16, 1024);
-      int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+    // -------------------------------------------------------------- MMA issuer.  The whole warp runs the (uniform) loop
+    // and one elected lane issues: with the loop inside an "if (lane == 0)" the compiler cannot prove the descriptors
+    // warp-uniform and wraps EVERY tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (~19 instructions,
+    // ~90 clocks per MMA - the whole kernel was issue-bound at 123 clocks per 128x96x8 MMA against a floor of 56)
+    const uint32_t idesc = umma_idesc(2, CV_BM, static_cast<uint32_t>(p.BN), 0, 0);   // tf32 x tf32 -> fp32
+    const uint32_t a_addr0 = smem_u32(smem);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 256;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 256;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint64_t off = static_cast<uint64_t>((stage * CV_STAGE_BYTES) >> 4);
+        if (elect_one()) {
+          const uint32_t a_addr = a_addr0 + stage * CV_STAGE_BYTES;
 #pragma unroll
           for (int k = 0; k < CV_BK / 8; ++k)
-            umma_tf32_ss(d_tmem, a_desc0 + off + static_cast<uint64_t>((k * 32) >> 4), b_desc0 + off + static_cast<uint64_t>((k * 32) >> 4),
+            umma_tf32_ss(d_tmem, umma_desc_sw128(a_addr + k * 32, 16, 1024), umma_desc_sw128(a_addr + CV_A_BYTES + k * 32, 16, 1024),
                          idesc, (kb | k) != 0);
           umma_commit(&empty[stage]);
           if (kb == num_kb - 1) umma_commit(&acc_full[acc]);
-          if (++stage == CV_STAGES) { stage = 0; phase ^= 1; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == CV_STAGES) { stage = 0; phase ^= 1; }
       }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    __syncwarp();
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
     const int q = warp & 3, lane = lane_id();
@@ -338,7 +454,11 @@ constexpr int CH_TH = 16, CH_TW = 8;
 constexpr int CH_MAX_A_STAGES = 2, CH_MAX_B_STAGES = 16;
 constexpr int CH_BAR_BYTES = 512;
 constexpr int CH_SMEM_MAX = 232448;
-constexpr int CH_RING_BUDGET = CH_SMEM_MAX - 1024 - CH_BAR_BYTES - CV_EPI_BYTES;
+constexpr int CH_STAGE_BYTES = 4 * 4096;            // row epilogue: one 32-row x 128-byte SWIZZLE_128B staging tile per warp
+constexpr int CH_VEC_BYTES = 3072;                  // bias[Cout] and gamma[Cout] in shared memory (Cout <= 384)
+constexpr int CH_EPI2_BYTES = CH_STAGE_BYTES + CH_VEC_BYTES;   // >= CV_EPI_BYTES: the transposing epilogue overlays it
+static_assert(CH_EPI2_BYTES >= CV_EPI_BYTES, "epilogue overlay");
+constexpr int CH_RING_BUDGET = CH_SMEM_MAX - 1024 - CH_BAR_BYTES - CH_EPI2_BYTES;
 
 template <int MT> struct ChGeom {
   static constexpr int TX = MT == 4 ? 2 : 1, TY = MT == 1 ? 1 : 2;        // tiles per block along x / y
@@ -350,12 +470,14 @@ template <int MT> struct ChGeom {
 
 template <int MT>
 __global__ void __launch_bounds__(CV_THREADS, 1)
-conv333_halo_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvArgs p) {
+conv333_halo_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmNorm, ConvArgs p) {
   using G = ChGeom<MT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int off_b = p.a_stages * G::A_SLOT;
-  const int off_bar = off_b + p.b_stages * p.b_slot;
+  const int off_epi = off_b + p.b_stages * p.b_slot;          // 1024-byte aligned: staging tiles, then bias / gamma
+  const int off_bar = off_epi + CH_EPI2_BYTES;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + off_bar);
   uint64_t* a_empty = a_full + CH_MAX_A_STAGES;
   uint64_t* b_full = a_empty + CH_MAX_A_STAGES;
@@ -363,9 +485,13 @@ conv333_halo_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* acc_full = b_empty + CH_MAX_B_STAGES;
   uint64_t* acc_empty = acc_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
-  float* epi_tile = reinterpret_cast<float*>(smem + off_bar + CH_BAR_BYTES);
+  float* epi_tile = reinterpret_cast<float*>(smem + off_epi);
+  float* vec_s = reinterpret_cast<float*>(smem + off_epi + CH_STAGE_BYTES);   // bias[Cout] | gamma[Cout]
 
   const int warp = threadIdx.x >> 5;
+  const bool prof = p.prof != nullptr && blockIdx.x == 0;
+  long long pw[7] = {0, 0, 0, 0, 0, 0, 0};
+  const long long t_begin = clock64();
   const int blocks_x = (p.W + G::BW - 1) / G::BW, blocks_y = (p.H + G::BH - 1) / G::BH;
   const int tiles_n = (p.Cout + p.BN - 1) / p.BN;
   const int num_blocks = blocks_x * blocks_y * p.T * tiles_n;
@@ -374,7 +500,13 @@ conv333_halo_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const uint32_t b_tx = static_cast<uint32_t>(p.BN) * CV_BK * 4;
   const int acc_cols = (p.BN + 31) / 32 * 32;     // TMEM columns per tile accumulator
 
-  if (warp == 0 && elect_one()) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == 0 && elect_one()) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmOut); tma_prefetch_desc(&tmNorm); }
+  if (p.rows_epi && warp >= 4) {
+    for (int i = threadIdx.x - 128; i < p.Cout; i += 128) {
+      vec_s[i] = p.bias ? p.bias[i] : 0.f;
+      vec_s[p.Cout + i] = p.norm_gamma ? p.norm_gamma[i] : 0.f;
+    }
+  }
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
@@ -405,7 +537,9 @@ conv333_halo_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
       int t, y0, x0, n0; decode(blk, t, y0, x0, n0);
       for (int dt = 0; dt < 3; ++dt)
         for (int kc = 0; kc < kchunks; ++kc) {
+          const long long w0 = prof ? clock64() : 0;
           mbar_wait(&a_empty[stage], phase ^ 1);
+          if (prof) pw[0] += clock64() - w0;
           if (elect_one()) {
             mbar_arrive_expect_tx(&a_full[stage], G::A_BYTES);
             tma_load_4d(smem + stage * G::A_SLOT, &tmA, &a_full[stage], kc * CV_BK, x0 - 1, y0 - 1, t + dt - 2);
@@ -422,7 +556,9 @@ conv333_halo_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
       for (int dt = 0; dt < 3; ++dt)
         for (int kc = 0; kc < kchunks; ++kc)
           for (int s = 0; s < 9; ++s) {
+            const long long w0 = prof ? clock64() : 0;
             mbar_wait(&b_empty[stage], phase ^ 1);
+            if (prof) pw[1] += clock64() - w0;
             if (elect_one()) {
               mbar_arrive_expect_tx(&b_full[stage], b_tx);
               tma_load_2d(smem + off_b + stage * p.b_slot, &tmB, &b_full[stage], kc * CV_BK, (dt * 9 + s) * p.Cout + n0);
@@ -432,25 +568,31 @@ conv333_halo_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
           }
     }
   } else if (warp == 1) {
-    // -------------------------------------------------------------- MMA issuer: one lane, MT accumulator chains round-robin
-    if (lane_id() == 0) {
-      const uint32_t idesc = umma_idesc(2, CV_BM, static_cast<uint32_t>(p.BN), 0, 0);
-      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(smem), 16, G::PW * 128);
-      const uint64_t b_desc0 = umma_desc_sw128(smem_u32(smem + off_b), 16, 1024);
-      int as = 0; uint32_t aph = 0;
-      int bs = 0; uint32_t bph = 0;
-      uint32_t acc_phase = 0;
-      for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x) {
-        mbar_wait(acc_empty, acc_phase ^ 1);
-        tc_fence_after();
-        for (int ab = 0; ab < num_ab; ++ab) {
-          mbar_wait(&a_full[as], aph);
-          const uint64_t da_s = a_desc0 + static_cast<uint64_t>((as * G::A_SLOT) >> 4);
+    // -------------------------------------------------------------- MMA issuer: MT accumulator chains round-robin; the warp
+    // runs the uniform loop, one elected lane issues (see conv_tf32_tcgen05)
+    const uint32_t idesc = umma_idesc(2, CV_BM, static_cast<uint32_t>(p.BN), 0, 0);
+    const uint32_t a_addr0 = smem_u32(smem), b_addr0 = smem_u32(smem + off_b);
+    int as = 0; uint32_t aph = 0;
+    int bs = 0; uint32_t bph = 0;
+    uint32_t acc_phase = 0;
+    for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x) {
+      long long w0 = prof ? clock64() : 0;
+      mbar_wait(acc_empty, acc_phase ^ 1);
+      if (prof) pw[2] += clock64() - w0;
+      tc_fence_after();
+      for (int ab = 0; ab < num_ab; ++ab) {
+        w0 = prof ? clock64() : 0;
+        mbar_wait(&a_full[as], aph);
+        if (prof) pw[3] += clock64() - w0;
+        const uint32_t a_addr = a_addr0 + as * G::A_SLOT;
 #pragma unroll
-          for (int s = 0; s < 9; ++s) {
-            mbar_wait(&b_full[bs], bph);
-            tc_fence_after();
-            const uint64_t db_s = b_desc0 + static_cast<uint64_t>((bs * p.b_slot) >> 4);
+        for (int s = 0; s < 9; ++s) {
+          w0 = prof ? clock64() : 0;
+          mbar_wait(&b_full[bs], bph);
+          if (prof) pw[4] += clock64() - w0;
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t b_addr = b_addr0 + bs * p.b_slot;
 #pragma unroll
             for (int m = 0; m < MT; ++m) {
 #pragma unroll
@@ -458,21 +600,23 @@ conv333_halo_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 // tile m = (ty, tx) of the block; tap s = (dy + 1, dx + 1): halo row (16 ty + dy + 1) * PW + 8 tx + dx + 1
                 const int ty = m / G::TX, tx = m % G::TX;
                 const int row = (ty * CH_TH + s / 3) * G::PW + tx * CH_TW + s % 3;
-                umma_tf32_ss(tmem_base + m * acc_cols, da_s + static_cast<uint64_t>((row * 128 + k * 32) >> 4),
-                             db_s + static_cast<uint64_t>((k * 32) >> 4), idesc, (ab | s | k) != 0);
+                umma_tf32_ss(tmem_base + m * acc_cols, umma_desc_sw128(a_addr + row * 128 + k * 32, 16, G::PW * 128),
+                             umma_desc_sw128(b_addr + k * 32, 16, 1024), idesc, (ab | s | k) != 0);
               }
             }
             umma_commit(&b_empty[bs]);
-            if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+            if (s == 8) {
+              umma_commit(&a_empty[as]);
+              if (ab == num_ab - 1) umma_commit(acc_full);
+            }
           }
-          umma_commit(&a_empty[as]);
-          if (ab == num_ab - 1) umma_commit(acc_full);
-          if (++as == p.a_stages) { as = 0; aph ^= 1; }
+          __syncwarp();
+          if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
         }
-        acc_phase ^= 1;
+        if (++as == p.a_stages) { as = 0; aph ^= 1; }
       }
+      acc_phase ^= 1;
     }
-    __syncwarp();
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue: the MT tiles one after the other
     const int q = warp & 3, lane = lane_id();
@@ -480,20 +624,34 @@ conv333_halo_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint32_t acc_phase = 0;
     for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x) {
       int t, y0, x0, n0; decode(blk, t, y0, x0, n0);
+      const long long w0 = prof ? clock64() : 0;
       mbar_wait(acc_full, acc_phase);
+      const long long w1 = prof ? clock64() : 0;
+      if (prof) pw[5] += w1 - w0;
       tc_fence_after();
 #pragma unroll 1
       for (int m = 0; m < MT; ++m) {
         const int ty = m / G::TX, tx = m % G::TX;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + m * acc_cols;
-        if (y0 + ty * CH_TH < p.H && x0 + tx * CH_TW < p.W)
-          conv_epilogue_tile(p, tile_s, t_row, q, lane, t, y0 + ty * CH_TH, x0 + tx * CH_TW, n0);
+        if (y0 + ty * CH_TH < p.H && x0 + tx * CH_TW < p.W) {
+          if (p.rows_epi)
+            conv_epilogue_rows(p, &tmOut, &tmNorm, reinterpret_cast<uint8_t*>(epi_tile) + q * 4096, vec_s, vec_s + p.Cout, t_row, q, lane,
+                               t, y0 + ty * CH_TH, x0 + tx * CH_TW, n0);
+          else
+            conv_epilogue_tile(p, tile_s, t_row, q, lane, t, y0 + ty * CH_TH, x0 + tx * CH_TW, n0);
+        }
       }
       tc_fence_before();
       __syncwarp();
+      if (prof) pw[6] += clock64() - w1;
       if (lane == 0) mbar_arrive(acc_empty);
       acc_phase ^= 1;
     }
+    if (p.rows_epi && lane == 0) bulk_wait_all();      // shared memory must outlive the last TMA store's read
+  }
+  if (prof && lane_id() == 0 && (warp == 0 || warp == 1 || warp == 3 || warp == 4)) {
+    for (int i = 0; i < 7; ++i) if (pw[i]) p.prof[i] = pw[i];
+    if (warp == 1) { p.prof[7] = clock64() - t_begin; p.prof[8] = (num_blocks - blockIdx.x + gridDim.x - 1) / gridDim.x; }
   }
 
   tc_fence_before();
@@ -505,8 +663,8 @@ conv333_halo_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 
 template <int MT>
-static int launch_conv333(const float* in, int in_T, int in_H, int in_W, int Cin, const CUtensorMap& tmB, ConvArgs a, void* stream,
-                          int grid_cap) {
+static int launch_conv333(const float* in, int in_T, int in_H, int in_W, int Cin, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                          const CUtensorMap& tmNorm, ConvArgs a, void* stream, int grid_cap) {
   using G = ChGeom<MT>;
   CUtensorMap tmH;
   uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(in_W), static_cast<uint64_t>(in_H), static_cast<uint64_t>(in_T)};
@@ -519,7 +677,7 @@ static int launch_conv333(const float* in, int in_T, int in_H, int in_W, int Cin
   a.a_stages = CH_MAX_A_STAGES;                     // an A slot feeds nine B slots
   a.b_stages = std::min(CH_MAX_B_STAGES, (CH_RING_BUDGET - a.a_stages * G::A_SLOT) / a.b_slot);
   if (a.b_stages < 2) return fail(WF_EINVAL, "wf_conv_tf32: no room for the B ring");
-  const int smem = a.a_stages * G::A_SLOT + a.b_stages * a.b_slot + CH_BAR_BYTES + CV_EPI_BYTES + 1024;
+  const int smem = a.a_stages * G::A_SLOT + a.b_stages * a.b_slot + CH_BAR_BYTES + CH_EPI2_BYTES + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     WF_CUDA_OK(cudaFuncSetAttribute(conv333_halo_tcgen05<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_MAX));
@@ -527,7 +685,7 @@ static int launch_conv333(const float* in, int in_T, int in_H, int in_W, int Cin
   }
   const long long blocks = static_cast<long long>((a.W + G::BW - 1) / G::BW) * ((a.H + G::BH - 1) / G::BH) * a.T * ((a.Cout + a.BN - 1) / a.BN);
   const int grid = static_cast<int>(std::min<long long>(blocks, grid_cap));
-  conv333_halo_tcgen05<MT><<<grid, CV_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tmH, tmB, a);
+  conv333_halo_tcgen05<MT><<<grid, CV_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tmH, tmB, tmOut, tmNorm, a);
   WF_LAUNCH_OK();
   return WF_OK;
 }
@@ -535,6 +693,10 @@ static int launch_conv333(const float* in, int in_T, int in_H, int in_W, int Cin
 }  // namespace wf
 
 using namespace wf;
+
+static long long* g_conv_prof = nullptr;
+// development hook: device buffer of >= 16 int64 that CTA 0 of the next 3x3x3 launches fills with its per-role clocks
+extern "C" int wf_debug_conv_profile(long long* device_buf) { g_conv_prof = device_buf; return WF_OK; }
 
 // in: channels-last fp32 [in_T][in_H][in_W][Cin]; weights fp32 [ntaps*Cout][Cin]; taps: int8 triples (dt,dy,dx).
 extern "C" int wf_conv_tf32(const float* in, int in_T, int in_H, int in_W, int Cin, const float* weights, const float* bias,
@@ -565,6 +727,7 @@ extern "C" int wf_conv_tf32(const float* in, int in_T, int in_H, int in_W, int C
   a.planar_clamp = planar_clamp; a.planar_cstride = planar_cstride;
   a.round_out = round_out_tf32 != 0;
   a.norm_gamma = norm_gamma; a.norm_out = norm_out; a.norm_silu = norm_silu;
+  a.prof = g_conv_prof;
   if (norm_gamma) {
     WF_REQUIRE(Cout <= CV_MAX_BN && Cout % 4 == 0, "wf_conv_tf32: the fused RMS-norm needs all channels of a pixel in one N tile (Cout <= 192)");
     WF_REQUIRE(!planar_clamp && c_split == Cout && t_mul == 1 && ldc % 4 == 0, "wf_conv_tf32: the fused RMS-norm needs a plain channels-last output");
@@ -601,9 +764,28 @@ extern "C" int wf_conv_tf32(const float* in, int in_T, int in_H, int in_W, int C
   bool is333 = use_halo && ntaps == 27 && t_stride == 1 && t_off == 0 && in_H == H && in_W == W;
   for (int i = 0; is333 && i < 27; ++i)
     is333 = taps[3 * i] == i / 9 - 2 && taps[3 * i + 1] == (i / 3) % 3 - 1 && taps[3 * i + 2] == i % 3 - 1;
-  if (is333)
-    return a.BN <= 96 ? launch_conv333<4>(in, in_T, in_H, in_W, Cin, tmB, a, stream, grid_cap)
-                      : launch_conv333<2>(in, in_T, in_H, in_W, Cin, tmB, a, stream, grid_cap);
+  if (is333) {
+    // row-per-thread epilogue with TMA stores: plain dense channels-last placement, whole 32-channel chunks, 16 x 8 tiles
+    CUtensorMap tmOut = tmB, tmNorm = tmB;           // placeholders when the transposing epilogue runs
+    static const int rows_epi_on = [] { const char* e = getenv("WF_CONV_ROWS_EPI"); return e ? atoi(e) : 1; }();
+    a.rows_epi = rows_epi_on && !planar_clamp && c_split == Cout && t_mul == 1 && sy == 1 && sx == 1 && oy == 0 && ox == 0 && ldc == Cout &&
+                 Cout % a.BN == 0 && a.BN % 32 == 0 && 2 * Cout * 4 <= CH_VEC_BYTES && out_H == H && out_W == W &&
+                 reinterpret_cast<uintptr_t>(out) % 16 == 0 && (!resid || reinterpret_cast<uintptr_t>(resid) % 16 == 0) &&
+                 (!norm_out || reinterpret_cast<uintptr_t>(norm_out) % 16 == 0);
+    if (a.rows_epi) {
+      uint64_t dims[4] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(out_W), static_cast<uint64_t>(out_H), static_cast<uint64_t>(T)};
+      uint64_t strides[3] = {static_cast<uint64_t>(Cout) * 4, static_cast<uint64_t>(out_W) * Cout * 4, static_cast<uint64_t>(out_H) * out_W * Cout * 4};
+      uint32_t box[4] = {32, CH_TW, 32 / CH_TW, 1};
+      int rc = make_tmap(&tmOut, out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+      if (norm_out) {
+        rc = make_tmap(&tmNorm, norm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+      }
+    }
+    return a.BN <= 96 ? launch_conv333<4>(in, in_T, in_H, in_W, Cin, tmB, tmOut, tmNorm, a, stream, grid_cap)
+                      : launch_conv333<2>(in, in_T, in_H, in_W, Cin, tmB, tmOut, tmNorm, a, stream, grid_cap);
+  }
   const long long tiles = static_cast<long long>((W + a.TW - 1) / a.TW) * ((H + a.TH - 1) / a.TH) * T * ((Cout + a.BN - 1) / a.BN);
   const int grid = static_cast<int>(std::min<long long>(tiles, sm_count()));
   conv_tf32_tcgen05<<<grid, CV_THREADS, CV_SMEM, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, a);

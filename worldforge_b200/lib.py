@@ -67,6 +67,7 @@ _SIGNATURES = {
     "wf_cfg_zero": [_vp, _vp, _vp, _f, _ll, _vp, _vp, _vp],
     "wf_conv_tf32": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i,
                      _vp, _i, _ll, _i, _i, _vp, _vp, _i, _vp],
+    "wf_debug_conv_profile": [_vp],
     "wf_rms_norm_cl": [_vp, _i, _vp, _i, _vp, _ll, _i, _i, _i, _vp],
     "wf_planar_to_cl": [_vp, _vp, _ll, _i, _i, _i, _vp],
     "wf_round_tf32": [_vp, _vp, _ll, _vp],
