@@ -603,8 +603,6 @@ constexpr int A3_OFF_BAR = A3_OFF_RING + A3_SLOTS * A3_SLOT_BYTES;
 constexpr int A3_SMEM = A3_OFF_BAR + 256 + 1024;
 constexpr int A3_REGS_PRODUCER = 40, A3_REGS_SOFTMAX = 232;   // (2*232 + 40) * 128 = 168 * 384
 
-template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 template <uint32_t POLY_MASK>
 __global__ void __launch_bounds__(AT_THREADS, 1)

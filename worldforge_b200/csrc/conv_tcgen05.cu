@@ -72,6 +72,7 @@ struct ConvArgs {
   const float* norm_gamma;
   float* norm_out;
   int norm_silu;
+  int vec_bytes;            // shared-memory bytes reserved for bias | gamma (row epilogue), a multiple of 256
   int rows_epi;             // 1: row-per-thread epilogue with TMA stores (plain channels-last output, BN % 32 == 0, TW <= 32)
   long long* prof;          // development: per-role wait / work clocks of CTA 0 (wf_debug_conv_profile), or null
 };
@@ -215,90 +216,72 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvArgs& p, float* til
 __device__ __forceinline__ void conv_epilogue_rows(const ConvArgs& p, const CUtensorMap* tmOut, const CUtensorMap* tmNorm,
                                                    uint8_t* stage, const float* bias_s, const float* gamma_s, uint32_t t_row,
                                                    int q, int lane, int t, int y0, int x0, int n0) {
-  const int r_in_tile = q * 32 + lane;
-  const int y = y0 + (r_in_tile >> p.tw_shift), x = x0 + (r_in_tile & (p.TW - 1));
-  const bool ok = y < p.H && x < p.W;
-  const float* rrow = p.resid ? p.resid + ((static_cast<size_t>(t) * p.out_H + y) * p.out_W + x) * p.ldc + n0 : nullptr;
   const int nchunks = p.BN >> 5;
   const int yq = y0 + ((q * 32) >> p.tw_shift);             // first output row of this warp's 32 pixels
   uint8_t* srow = stage + lane * 128;
   const int sw = lane & 7;
-  auto put = [&](const float (&o)[32], const CUtensorMap* tm, int c) {
+  auto put = [&](const float (&o)[32], const CUtensorMap* tm, int c, bool round) {
     if (lane == 0) bulk_wait_read_all();                    // the previous store has read the staging tile
     __syncwarp();
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch)
-      *reinterpret_cast<float4*>(srow + ((ch ^ sw) << 4)) = make_float4(o[4 * ch], o[4 * ch + 1], o[4 * ch + 2], o[4 * ch + 3]);
+    for (int ch = 0; ch < 8; ++ch) {
+      float4 f = make_float4(o[4 * ch], o[4 * ch + 1], o[4 * ch + 2], o[4 * ch + 3]);
+      if (round) f = make_float4(tf32_round(f.x), tf32_round(f.y), tf32_round(f.z), tf32_round(f.w));
+      *reinterpret_cast<float4*>(srow + ((ch ^ sw) << 4)) = f;
+    }
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) { tma_store_4d(tm, stage, n0 + c * 32, x0, yq, t); bulk_commit_group(); }
   };
-  auto load_v = [&](int c, float (&v)[32], bool add) {
-    uint32_t r[32];
-    float rs[32];
-    if (add && rrow && ok) {
+  // The residual chunk of the warp's 32 pixels comes in by coalesced 16-byte loads (instruction i covers rows 4i .. 4i+3,
+  // lane -> row 4i + lane / 8, piece lane % 8; warp 2 prefetched the lines into L2 during the main loop), issued one chunk
+  // AHEAD into registers, and passes through the staging tile so that every thread gets its own row.
+  float4 nxt[8];
+  auto resid_issue = [&](int c) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 v4 = *reinterpret_cast<const float4*>(rrow + c * 32 + j);
-        rs[j] = v4.x; rs[j + 1] = v4.y; rs[j + 2] = v4.z; rs[j + 3] = v4.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) rs[j] = 0.f;
+    for (int i = 0; i < 8; ++i) {
+      const int rt = q * 32 + 4 * i + (lane >> 3);
+      const int yy = y0 + (rt >> p.tw_shift), xx = x0 + (rt & (p.TW - 1));
+      nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (yy < p.H && xx < p.W)
+        nxt[i] = __ldg(reinterpret_cast<const float4*>(p.resid + ((static_cast<size_t>(t) * p.out_H + yy) * p.out_W + xx) * p.ldc + n0 + c * 32) + (lane & 7));
     }
-    tmem_ld_32x32b_x32(t_row + c * 32, r);
-    tmem_ld_wait();
-    if (add) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b4 = p.bias ? *reinterpret_cast<const float4*>(bias_s + n0 + c * 32 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-        v[j] = __uint_as_float(r[j]) + b4.x + rs[j];
-        v[j + 1] = __uint_as_float(r[j + 1]) + b4.y + rs[j + 1];
-        v[j + 2] = __uint_as_float(r[j + 2]) + b4.z + rs[j + 2];
-        v[j + 3] = __uint_as_float(r[j + 3]) + b4.w + rs[j + 3];
-      }
-    } else {
+  };
+  // v = accumulator chunk c (+ bias + residual when `add`)
+  auto load_v = [&](int c, float (&v)[32], bool add) {
+    {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(t_row + c * 32, r);
+      tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
     }
-  };
-  if (!p.norm_gamma) {
-#pragma unroll 1
-    for (int c = 0; c < nchunks; ++c) {
-      float v[32];
-      load_v(c, v, true);
-      if (p.round_out) {
+    if (add && p.bias) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = tf32_round(v[j]);
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n0 + c * 32 + j);
+        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
       }
-      put(v, tmOut, c);
     }
-    return;
-  }
-  float ss = 0.f;
-#pragma unroll 1
-  for (int c = 0; c < nchunks; ++c) {
-    float v[32];
-    load_v(c, v, true);
+    if (add && p.resid) {
+      if (lane == 0) bulk_wait_read_all();
+      __syncwarp();
 #pragma unroll
-    for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
-    uint32_t w[32];
+      for (int i = 0; i < 8; ++i) {
+        const int row = 4 * i + (lane >> 3);
+        *reinterpret_cast<float4*>(stage + row * 128 + (((lane & 7) ^ (row & 7)) << 4)) = nxt[i];
+      }
+      __syncwarp();
+      if (c + 1 < nchunks) resid_issue(c + 1);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v[j]);
-    tmem_st_32x32b_x32(t_row + c * 32, w);
-  }
-  tmem_st_wait();
-  const float inv = sqrtf(static_cast<float>(p.Cout)) / fmaxf(sqrtf(ss), 1e-12f);
-#pragma unroll 1
-  for (int c = 0; c < nchunks; ++c) {
-    float v[32];
-    load_v(c, v, false);
-    if (p.norm_out) {
-      float o[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) o[j] = p.round_out ? tf32_round(v[j]) : v[j];
-      put(o, tmOut, c);
+      for (int ch = 0; ch < 8; ++ch) {
+        const float4 v4 = *reinterpret_cast<const float4*>(srow + ((ch ^ sw) << 4));
+        v[4 * ch] += v4.x; v[4 * ch + 1] += v4.y; v[4 * ch + 2] += v4.z; v[4 * ch + 3] += v4.w;
+      }
+      __syncwarp();                                         // every row read before the tile is rewritten
     }
+  };
+  auto normalise = [&](float (&v)[32], int c, float inv) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const float4 g4 = *reinterpret_cast<const float4*>(gamma_s + n0 + c * 32 + j);
@@ -306,14 +289,46 @@ __device__ __forceinline__ void conv_epilogue_rows(const ConvArgs& p, const CUte
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         float a = v[j + u] * inv * gg[u];
-        if (p.norm_silu) a = a / (1.0f + expf(-a));
-        v[j + u] = tf32_round(a);
+        if (p.norm_silu) a = __fdividef(a, 1.0f + __expf(-a));     // result is rounded to tf32: the approximate ex2 / rcp are exact enough
+        v[j + u] = a;
       }
     }
-    put(v, p.norm_out ? tmNorm : tmOut, c);
+  };
+  if (p.resid) resid_issue(0);
+  if (!p.norm_gamma) {
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+      float v[32];
+      load_v(c, v, true);
+      put(v, tmOut, c, p.round_out != 0);
+    }
+    return;
+  }
+  {
+    float ss = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+      float v[32];
+      load_v(c, v, true);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) ss = fmaf(v[j], v[j], ss);
+      uint32_t w[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v[j]);
+      tmem_st_32x32b_x32(t_row + c * 32, w);
+    }
+    tmem_st_wait();
+    const float inv = sqrtf(static_cast<float>(p.Cout)) / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+      float v[32];
+      load_v(c, v, false);
+      if (p.norm_out) put(v, tmOut, c, p.round_out != 0);
+      normalise(v, c, inv);
+      put(v, p.norm_out ? tmNorm : tmOut, c, true);
+    }
   }
 }
-
 
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvArgs p) {
@@ -454,11 +469,11 @@ constexpr int CH_TH = 16, CH_TW = 8;
 constexpr int CH_MAX_A_STAGES = 2, CH_MAX_B_STAGES = 16;
 constexpr int CH_BAR_BYTES = 512;
 constexpr int CH_SMEM_MAX = 232448;
-constexpr int CH_STAGE_BYTES = 4 * 4096;            // row epilogue: one 32-row x 128-byte SWIZZLE_128B staging tile per warp
-constexpr int CH_VEC_BYTES = 3072;                  // bias[Cout] and gamma[Cout] in shared memory (Cout <= 384)
-constexpr int CH_EPI2_BYTES = CH_STAGE_BYTES + CH_VEC_BYTES;   // >= CV_EPI_BYTES: the transposing epilogue overlays it
-static_assert(CH_EPI2_BYTES >= CV_EPI_BYTES, "epilogue overlay");
-constexpr int CH_RING_BUDGET = CH_SMEM_MAX - 1024 - CH_BAR_BYTES - CH_EPI2_BYTES;
+constexpr int CH_THREADS = 384;                     // 4 role warps + 8 epilogue warps (two per scheduler: one hides the other's latencies)
+// 384 threads x 168 registers: no setmaxnreg split - capping the role warps made ptxas spill their code, and the row epilogue fits
+constexpr int CH_STAGE_BYTES = 8 * 4096;            // row epilogue: one 32-row x 128-byte SWIZZLE_128B staging tile per warp
+constexpr int CH_VEC_BYTES = 3072;                  // bias[Cout] and gamma[Cout] in shared memory (Cout <= 384); the host sizes it per launch
+constexpr int CH_RING_BUDGET = CH_SMEM_MAX - 1024 - CH_BAR_BYTES - CH_STAGE_BYTES;   // minus the launch's bias / gamma bytes
 
 template <int MT> struct ChGeom {
   static constexpr int TX = MT == 4 ? 2 : 1, TY = MT == 1 ? 1 : 2;        // tiles per block along x / y
@@ -468,16 +483,17 @@ template <int MT> struct ChGeom {
   static constexpr int A_SLOT = (A_BYTES + 1023) / 1024 * 1024;
 };
 
-template <int MT>
-__global__ void __launch_bounds__(CV_THREADS, 1)
+template <int MT, bool PROF>
+__global__ void __launch_bounds__(CH_THREADS, 1)
 conv333_halo_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmNorm, ConvArgs p) {
+                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmNorm,
+                     const __grid_constant__ CUtensorMap tmRes, ConvArgs p) {
   using G = ChGeom<MT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int off_b = p.a_stages * G::A_SLOT;
   const int off_epi = off_b + p.b_stages * p.b_slot;          // 1024-byte aligned: staging tiles, then bias / gamma
-  const int off_bar = off_epi + CH_EPI2_BYTES;
+  const int off_bar = off_epi + CH_STAGE_BYTES + p.vec_bytes;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + off_bar);
   uint64_t* a_empty = a_full + CH_MAX_A_STAGES;
   uint64_t* b_full = a_empty + CH_MAX_A_STAGES;
@@ -489,7 +505,7 @@ conv333_halo_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
   float* vec_s = reinterpret_cast<float*>(smem + off_epi + CH_STAGE_BYTES);   // bias[Cout] | gamma[Cout]
 
   const int warp = threadIdx.x >> 5;
-  const bool prof = p.prof != nullptr && blockIdx.x == 0;
+  const bool prof = PROF && p.prof != nullptr && blockIdx.x == 0;
   long long pw[7] = {0, 0, 0, 0, 0, 0, 0};
   const long long t_begin = clock64();
   const int blocks_x = (p.W + G::BW - 1) / G::BW, blocks_y = (p.H + G::BH - 1) / G::BH;
@@ -500,9 +516,9 @@ conv333_halo_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const uint32_t b_tx = static_cast<uint32_t>(p.BN) * CV_BK * 4;
   const int acc_cols = (p.BN + 31) / 32 * 32;     // TMEM columns per tile accumulator
 
-  if (warp == 0 && elect_one()) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmOut); tma_prefetch_desc(&tmNorm); }
-  if (p.rows_epi && warp >= 4) {
-    for (int i = threadIdx.x - 128; i < p.Cout; i += 128) {
+  if (warp == 0 && elect_one()) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmOut); tma_prefetch_desc(&tmNorm); tma_prefetch_desc(&tmRes); }
+  if (warp >= 4) {
+    for (int i = threadIdx.x - 128; i < p.Cout; i += CH_THREADS - 128) {
       vec_s[i] = p.bias ? p.bias[i] : 0.f;
       vec_s[p.Cout + i] = p.norm_gamma ? p.norm_gamma[i] : 0.f;
     }
@@ -510,7 +526,7 @@ conv333_halo_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    mbar_init(acc_full, 1); mbar_init(acc_empty, 4);
+    mbar_init(acc_full, 1); mbar_init(acc_empty, 8);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -538,7 +554,7 @@ conv333_halo_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
       for (int dt = 0; dt < 3; ++dt)
         for (int kc = 0; kc < kchunks; ++kc) {
           const long long w0 = prof ? clock64() : 0;
-          mbar_wait(&a_empty[stage], phase ^ 1);
+          mbar_wait_trap(&a_empty[stage], phase ^ 1);
           if (prof) pw[0] += clock64() - w0;
           if (elect_one()) {
             mbar_arrive_expect_tx(&a_full[stage], G::A_BYTES);
@@ -557,7 +573,7 @@ conv333_halo_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int kc = 0; kc < kchunks; ++kc)
           for (int s = 0; s < 9; ++s) {
             const long long w0 = prof ? clock64() : 0;
-            mbar_wait(&b_empty[stage], phase ^ 1);
+            mbar_wait_trap(&b_empty[stage], phase ^ 1);
             if (prof) pw[1] += clock64() - w0;
             if (elect_one()) {
               mbar_arrive_expect_tx(&b_full[stage], b_tx);
@@ -566,6 +582,21 @@ conv333_halo_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
             __syncwarp();
             if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
           }
+    }
+  } else if (warp == 2 && p.resid) {
+    // ------------------------------------------------------------ residual prefetch: the block's residual boxes into L2 while
+    // its main loop runs (the epilogue reads them ~100 K clocks later at L2 instead of DRAM latency)
+    uint32_t it = 0;
+    for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x, ++it) {
+      int t, y0, x0, n0; decode(blk, t, y0, x0, n0);
+      if (it > 0) mbar_wait_trap(acc_full, (it - 1) & 1);      // one block ahead of the epilogue, not the whole launch
+      if (elect_one()) {
+        for (int m = 0; m < MT; ++m)
+          for (int qq = 0; qq < 4; ++qq)
+            for (int c = 0; c < (p.BN >> 5); ++c)
+              tma_prefetch_4d(&tmRes, n0 + c * 32, x0 + (m % G::TX) * CH_TW, y0 + (m / G::TX) * CH_TH + qq * (32 / CH_TW), t);
+      }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer: MT accumulator chains round-robin; the warp
@@ -577,18 +608,18 @@ conv333_halo_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint32_t acc_phase = 0;
     for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x) {
       long long w0 = prof ? clock64() : 0;
-      mbar_wait(acc_empty, acc_phase ^ 1);
+      mbar_wait_trap(acc_empty, acc_phase ^ 1);
       if (prof) pw[2] += clock64() - w0;
       tc_fence_after();
       for (int ab = 0; ab < num_ab; ++ab) {
         w0 = prof ? clock64() : 0;
-        mbar_wait(&a_full[as], aph);
+        mbar_wait_trap(&a_full[as], aph);
         if (prof) pw[3] += clock64() - w0;
         const uint32_t a_addr = a_addr0 + as * G::A_SLOT;
 #pragma unroll
         for (int s = 0; s < 9; ++s) {
           w0 = prof ? clock64() : 0;
-          mbar_wait(&b_full[bs], bph);
+          mbar_wait_trap(&b_full[bs], bph);
           if (prof) pw[4] += clock64() - w0;
           tc_fence_after();
           if (elect_one()) {
@@ -619,27 +650,24 @@ conv333_halo_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue: the MT tiles one after the other
-    const int q = warp & 3, lane = lane_id();
-    float* tile_s = epi_tile + q * (32 * CV_EPI_LD);
+    // warps 4-7 and 8-11 cover the four TMEM lane quarters twice and take alternate tiles: two warps per scheduler hide each
+    // other's TMEM / global / TMA-store latencies.  (Placements the row epilogue does not cover run the per-tap kernel.)
+    const int q = warp & 3, lane = lane_id(), wg = (warp - 4) >> 2;
     uint32_t acc_phase = 0;
     for (int blk = blockIdx.x; blk < num_blocks; blk += gridDim.x) {
       int t, y0, x0, n0; decode(blk, t, y0, x0, n0);
       const long long w0 = prof ? clock64() : 0;
-      mbar_wait(acc_full, acc_phase);
+      mbar_wait_trap(acc_full, acc_phase);
       const long long w1 = prof ? clock64() : 0;
       if (prof) pw[5] += w1 - w0;
       tc_fence_after();
 #pragma unroll 1
-      for (int m = 0; m < MT; ++m) {
+      for (int m = wg; m < MT; m += 2) {
         const int ty = m / G::TX, tx = m % G::TX;
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + m * acc_cols;
-        if (y0 + ty * CH_TH < p.H && x0 + tx * CH_TW < p.W) {
-          if (p.rows_epi)
-            conv_epilogue_rows(p, &tmOut, &tmNorm, reinterpret_cast<uint8_t*>(epi_tile) + q * 4096, vec_s, vec_s + p.Cout, t_row, q, lane,
-                               t, y0 + ty * CH_TH, x0 + tx * CH_TW, n0);
-          else
-            conv_epilogue_tile(p, tile_s, t_row, q, lane, t, y0 + ty * CH_TH, x0 + tx * CH_TW, n0);
-        }
+        if (y0 + ty * CH_TH < p.H && x0 + tx * CH_TW < p.W)
+          conv_epilogue_rows(p, &tmOut, &tmNorm, reinterpret_cast<uint8_t*>(epi_tile) + (warp - 4) * 4096, vec_s, vec_s + p.Cout, t_row,
+                             q, lane, t, y0 + ty * CH_TH, x0 + tx * CH_TW, n0);
       }
       tc_fence_before();
       __syncwarp();
@@ -647,9 +675,9 @@ conv333_halo_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (lane == 0) mbar_arrive(acc_empty);
       acc_phase ^= 1;
     }
-    if (p.rows_epi && lane == 0) bulk_wait_all();      // shared memory must outlive the last TMA store's read
+    if (lane == 0) bulk_wait_all();      // shared memory must outlive the last TMA store's read
   }
-  if (prof && lane_id() == 0 && (warp == 0 || warp == 1 || warp == 3 || warp == 4)) {
+  if (prof && lane_id() == 0 && (warp == 0 || warp == 1 || warp == 3 || warp == 4)) {   // (warp 4's epilogue clocks: tiles 0, 2)
     for (int i = 0; i < 7; ++i) if (pw[i]) p.prof[i] = pw[i];
     if (warp == 1) { p.prof[7] = clock64() - t_begin; p.prof[8] = (num_blocks - blockIdx.x + gridDim.x - 1) / gridDim.x; }
   }
@@ -664,7 +692,7 @@ conv333_halo_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
 template <int MT>
 static int launch_conv333(const float* in, int in_T, int in_H, int in_W, int Cin, const CUtensorMap& tmB, const CUtensorMap& tmOut,
-                          const CUtensorMap& tmNorm, ConvArgs a, void* stream, int grid_cap) {
+                          const CUtensorMap& tmNorm, const CUtensorMap& tmRes, ConvArgs a, void* stream, int grid_cap) {
   using G = ChGeom<MT>;
   CUtensorMap tmH;
   uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(in_W), static_cast<uint64_t>(in_H), static_cast<uint64_t>(in_T)};
@@ -675,17 +703,20 @@ static int launch_conv333(const float* in, int in_T, int in_H, int in_W, int Cin
   a.TW = CH_TW; a.TH = CH_TH; a.tw_shift = 3;
   a.b_slot = (a.BN * CV_BK * 4 + 1023) / 1024 * 1024;
   a.a_stages = CH_MAX_A_STAGES;                     // an A slot feeds nine B slots
-  a.b_stages = std::min(CH_MAX_B_STAGES, (CH_RING_BUDGET - a.a_stages * G::A_SLOT) / a.b_slot);
+  a.vec_bytes = (2 * a.Cout * 4 + 255) / 256 * 256;
+  a.b_stages = std::min(CH_MAX_B_STAGES, (CH_RING_BUDGET - a.vec_bytes - a.a_stages * G::A_SLOT) / a.b_slot);
   if (a.b_stages < 2) return fail(WF_EINVAL, "wf_conv_tf32: no room for the B ring");
-  const int smem = a.a_stages * G::A_SLOT + a.b_stages * a.b_slot + CH_BAR_BYTES + CH_EPI2_BYTES + 1024;
+  const int smem = a.a_stages * G::A_SLOT + a.b_stages * a.b_slot + CH_BAR_BYTES + CH_STAGE_BYTES + a.vec_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    WF_CUDA_OK(cudaFuncSetAttribute(conv333_halo_tcgen05<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_MAX));
+    WF_CUDA_OK((cudaFuncSetAttribute(conv333_halo_tcgen05<MT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_MAX)));
+    WF_CUDA_OK((cudaFuncSetAttribute(conv333_halo_tcgen05<MT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_MAX)));
     attr_set = true;
   }
   const long long blocks = static_cast<long long>((a.W + G::BW - 1) / G::BW) * ((a.H + G::BH - 1) / G::BH) * a.T * ((a.Cout + a.BN - 1) / a.BN);
   const int grid = static_cast<int>(std::min<long long>(blocks, grid_cap));
-  conv333_halo_tcgen05<MT><<<grid, CV_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tmH, tmB, tmOut, tmNorm, a);
+  if (a.prof) conv333_halo_tcgen05<MT, true><<<grid, CH_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tmH, tmB, tmOut, tmNorm, tmRes, a);
+  else conv333_halo_tcgen05<MT, false><<<grid, CH_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tmH, tmB, tmOut, tmNorm, tmRes, a);
   WF_LAUNCH_OK();
   return WF_OK;
 }
@@ -765,8 +796,8 @@ extern "C" int wf_conv_tf32(const float* in, int in_T, int in_H, int in_W, int C
   for (int i = 0; is333 && i < 27; ++i)
     is333 = taps[3 * i] == i / 9 - 2 && taps[3 * i + 1] == (i / 3) % 3 - 1 && taps[3 * i + 2] == i % 3 - 1;
   if (is333) {
-    // row-per-thread epilogue with TMA stores: plain dense channels-last placement, whole 32-channel chunks, 16 x 8 tiles
-    CUtensorMap tmOut = tmB, tmNorm = tmB;           // placeholders when the transposing epilogue runs
+    // the halo kernel has the row-per-thread epilogue with TMA stores only: plain dense channels-last placement, whole 32-channel chunks, 16 x 8 tiles
+    CUtensorMap tmOut = tmB, tmNorm = tmB, tmRes = tmB;           // placeholders when the transposing epilogue runs
     static const int rows_epi_on = [] { const char* e = getenv("WF_CONV_ROWS_EPI"); return e ? atoi(e) : 1; }();
     a.rows_epi = rows_epi_on && !planar_clamp && c_split == Cout && t_mul == 1 && sy == 1 && sx == 1 && oy == 0 && ox == 0 && ldc == Cout &&
                  Cout % a.BN == 0 && a.BN % 32 == 0 && 2 * Cout * 4 <= CH_VEC_BYTES && out_H == H && out_W == W &&
@@ -782,9 +813,14 @@ extern "C" int wf_conv_tf32(const float* in, int in_T, int in_H, int in_W, int C
         rc = make_tmap(&tmNorm, norm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
       }
+      if (resid) {
+        rc = make_tmap(&tmRes, resid, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+      }
     }
-    return a.BN <= 96 ? launch_conv333<4>(in, in_T, in_H, in_W, Cin, tmB, tmOut, tmNorm, a, stream, grid_cap)
-                      : launch_conv333<2>(in, in_T, in_H, in_W, Cin, tmB, tmOut, tmNorm, a, stream, grid_cap);
+    if (a.rows_epi)
+      return a.BN <= 96 ? launch_conv333<4>(in, in_T, in_H, in_W, Cin, tmB, tmOut, tmNorm, tmRes, a, stream, grid_cap)
+                        : launch_conv333<2>(in, in_T, in_H, in_W, Cin, tmB, tmOut, tmNorm, tmRes, a, stream, grid_cap);
   }
   const long long tiles = static_cast<long long>((W + a.TW - 1) / a.TW) * ((H + a.TH - 1) / a.TH) * T * ((Cout + a.BN - 1) / a.BN);
   const int grid = static_cast<int>(std::min<long long>(tiles, sm_count()));
