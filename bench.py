@@ -253,11 +253,20 @@ def run_ours(args):
 
     cfg = wtr.WanDitConfig(num_layers=args.layers)
     tr = wtr.WfWanTransformer.random_init(cfg, dev, seed=1234)
+    cfgp, sp_world = None, world
     if world > 1:
         from worldforge_b200 import ulysses
         # WF_ULYSSES=nccl: the all-to-all form (A/B measurements); default: q|k|v and attention output stored straight into the
-        # peers' memory over NVLink by the producing kernels
-        ulysses.enable(tr, dist.group.WORLD, peer=os.environ.get("WF_ULYSSES", "peer") != "nccl")
+        # peers' memory over NVLink by the producing kernels.  WF_LAYOUT=ulysses: every rank in one Ulysses group (A/B);
+        # default on an even rank count: the two CFG forwards in the two halves of the ranks, Ulysses inside a half
+        peer = os.environ.get("WF_ULYSSES", "peer") != "nccl"
+        if world % 2 == 0 and os.environ.get("WF_LAYOUT", "cfg") != "ulysses":
+            sp_group, cfgp = ulysses.cfg_layout(world, rank)
+            sp_world = world // 2
+            if sp_group is not None:
+                ulysses.enable(tr, sp_group, peer=peer)
+        else:
+            ulysses.enable(tr, dist.group.WORLD, peer=peer)
     vae = wvae.WfWanVAE.random_init(dev, seed=4321)
     if world > 1:
         vae.enable_row_sharding(dist.group.WORLD)      # encode / decode split by image rows; FLF scoring by channels
@@ -284,7 +293,7 @@ def run_ours(args):
 
     def run(from_host: bool):
         sched = wsched.WfUniPCScheduler(flow_shift=3.0)
-        sampler = wpipe.GuidedSampler(tr, vae, sched, generator=torch.Generator().manual_seed(42), **knobs)
+        sampler = wpipe.GuidedSampler(tr, vae, sched, generator=torch.Generator().manual_seed(42), cfg_parallel=cfgp, **knobs)
         sampler.begin(total, dev)
         latents = devt["latents"].clone()
         lat_cpu = host["latents"]
@@ -295,6 +304,7 @@ def run_ours(args):
                 barrier()
                 lib.launches = 0
                 lib.timed_attention = [] if not from_host else None
+                lib.trace = {} if (os.environ.get("WF_TRACE") and not from_host) else None
                 clocks.start() if not from_host else None
                 t_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 t_ev[0].record()
@@ -329,6 +339,12 @@ def run_ours(args):
     clocks = ClockSampler(local)
     ms, _, _, fwd = run(from_host=False)
     clk = clocks.stop()
+    if lib.trace is not None:                 # WF_TRACE=1: where the timed steps went (development; rank 0, stderr)
+        summ = lib.trace_summary()
+        lib.trace = None
+        if rank == 0:
+            for k, (n, t_ms) in sorted(summ.items(), key=lambda kv: -kv[1][1]):
+                print(f"[trace] {k:28s} {n:4d} calls {t_ms:10.1f} ms  ({t_ms / ms * 100:5.1f} % of the timed region)", file=sys.stderr, flush=True)
     launches = lib.launches
     attn = list(lib.timed_attention or [])
     lib.timed_attention = None
@@ -343,7 +359,7 @@ def run_ours(args):
     roof = None
     if attn_ms:
         mean_ms = statistics.mean(attn_ms)
-        flops = 4.0 * L * L * cfg.dim / world       # Ulysses: each rank runs heads/world of the full-sequence attention
+        flops = 4.0 * L * L * cfg.dim / sp_world    # Ulysses: each rank runs heads/P of the full-sequence attention
         ach = flops / (mean_ms / 1000.0) / 1e12
         traffic = None
         pj = os.path.join(ROOT, "profiles", "ncu_summary.json")
@@ -360,7 +376,7 @@ def run_ours(args):
         "config": {"workload": f"Wan2.1-I2V-14B {args.height}x{args.width} {args.frames}f guided sampling (IRR+FLF+DSG), "
                                f"{k_guided} guided + {K - k_guided} plain timed steps (the 15:35 mix of the 50-step run)",
                    "tokens": L, "dit_layers": args.layers, "dit_forwards_timed": fwd - 4 * W,
-                   "vae": "fp32 storage, tf32 tensor-core convs", "parallelism": "single GPU" if world == 1 else f"ulysses{world} (DiT tokens, {os.environ.get('WF_ULYSSES', 'peer')} exchange) + vae-rows{world} + flf-channels{world}",
+                   "vae": "fp32 storage, tf32 tensor-core convs", "parallelism": "single GPU" if world == 1 else (f"cfg2 x " if cfgp is not None else "") + f"ulysses{sp_world} (DiT tokens, {os.environ.get('WF_ULYSSES', 'peer')} exchange) + vae-rows{world} + flf-channels{world}",
                    "l2_policy": "inputs larger than L2 (33 GB of weights, 0.67 GB activations streamed per GEMM)"},
         "clocks": clk, "gpu_launches": launches, "e2e": e2e, "roofline": roof,
         "dit_forwards_per_sec": (fwd - 4 * W) / (ms / 1000.0),
@@ -460,6 +476,12 @@ def run_longcat(args):
     calls0 = dit.calls
     ms, _, _ = run(False)
     clk = clocks.stop()
+    if lib.trace is not None:                 # WF_TRACE=1: where the timed steps went (development; rank 0, stderr)
+        summ = lib.trace_summary()
+        lib.trace = None
+        if rank == 0:
+            for k, (n, t_ms) in sorted(summ.items(), key=lambda kv: -kv[1][1]):
+                print(f"[trace] {k:28s} {n:4d} calls {t_ms:10.1f} ms  ({t_ms / ms * 100:5.1f} % of the timed region)", file=sys.stderr, flush=True)
     launches = lib.launches
     fwd = dit.calls - calls0 - 2 * W
     attn = list(lib.timed_attention or [])

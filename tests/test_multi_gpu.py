@@ -28,5 +28,6 @@ def test_sharded_paths_on_real_ranks(cuda):
     out = r.stdout + r.stderr
     assert r.returncode == 0, out[-4000:]
     for what in ("sequence-parallel forward equal to single-GPU: True", "peer-memory forward equal to single-GPU: True",
+                 "cfg-parallel forwards equal to single-GPU: True",
                  "row-sharded VAE equal to single-GPU: encode True decode True", "rank-sharded FLF scores equal: True"):
         assert out.count(what) == n, (what, out[-4000:])

@@ -125,3 +125,32 @@ def test_peer_setup_failure_is_agreed_by_all_ranks():
     mp.spawn(_peer_setup_worker, args=(2, _store_file(), ret), nprocs=2, join=True)
     assert ret[0].startswith("agreed:") and ret[1].startswith("agreed:")
     assert "no device memory" in ret[1] and "a peer could not" in ret[0]
+
+
+def _cfg_worker(rank, world, store, ret):
+    _init(rank, world, store)
+    try:
+        from worldforge_b200 import ulysses
+        sp_group, cfgp = ulysses.cfg_layout(world, rank)
+        half = world // 2
+        assert cfgp.branch == rank // half
+        assert (sp_group is None) == (half == 1)
+        if sp_group is not None:
+            assert dist.get_world_size(sp_group) == half and dist.get_rank(sp_group) == rank % half
+        # every rank of a half computes the same prediction (the Ulysses forward ends in an all-reduce inside the half)
+        mine = torch.full((1, 4, 2, 3, 5), 10.0 * cfgp.branch + 1.0)
+        v_c, v_u = cfgp.exchange(mine)
+        ret[rank] = (v_c.unique().tolist(), v_u.unique().tolist(), cfgp.exchanges)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_cfg_parallel_layout(world):
+    """CFG x Ulysses layout: rank r and r + P/2 swap the conditional / unconditional predictions."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_cfg_worker, args=(world, _store_file(), ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(world):
+        assert ret[r] == ([1.0], [11.0], 1), (r, ret[r])

@@ -34,6 +34,23 @@ peer_ok = torch.equal(single, par2) and torch.equal(single, par3)
 print(f"rank {rank}/{world}: peer-memory forward equal to single-GPU: {peer_ok} (max diff {(single.float() - par2.float()).abs().max().item()}), "
       f"barriers {psp.barriers}, a2a calls still {sp.a2a_calls}", flush=True)
 md = max(md, 0.0 if peer_ok else 1.0)
+# CFG x Ulysses layout: the two halves of the ranks run the conditional / unconditional forward (Ulysses inside a half, over
+# peer memory) and swap the predictions - both must equal the single-GPU forwards bit for bit
+ctx_u = torch.randn(1, 16, 64, generator=g).to(torch.bfloat16).to(dev)
+m.sp = None
+single_u = m(x, t, ctx_u, clip)[0].clone()
+cfg_ok = True
+if world % 2 == 0:
+    sp_group, cfgp = ulysses.cfg_layout(world, rank)
+    m._psp = {}
+    if sp_group is not None:
+        ulysses.enable(m, sp_group, peer=True)
+    mine = m(x, t, ctx_u if cfgp.branch else ctx, clip)[0]
+    v_c, v_u = cfgp.exchange(mine)
+    torch.cuda.synchronize()
+    cfg_ok = torch.equal(v_c, single) and torch.equal(v_u, single_u)
+print(f"rank {rank}/{world}: cfg-parallel forwards equal to single-GPU: {cfg_ok}", flush=True)
+md = max(md, 0.0 if cfg_ok else 1.0)
 from worldforge_b200 import flf_select, vae as wvae
 v = wvae.WfWanVAE.random_init(dev, dim=16, seed=3)
 video = (torch.rand(1, 3, 9, 128, 96, generator=g) * 2 - 1).to(dev)

@@ -25,6 +25,35 @@ class WfError(RuntimeError):
 
 _lib = None
 launches = 0     # kernels launched through this binding (bench.py's gpu_launches)
+trace = None             # bench.py (WF_TRACE=1): a dict name -> [(start event, end event)] filled by ``phase``
+
+
+class phase:
+    """``with lib.phase("vae.decode"):`` - CUDA-event bracket on the current stream when ``lib.trace`` is a dict (a development
+    breakdown of a step; costs nothing otherwise)."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if trace is not None:
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record()
+        return self
+
+    def __exit__(self, *a):
+        if trace is not None:
+            self.ev[1].record()
+            trace.setdefault(self.name, []).append(self.ev)
+        return False
+
+
+def trace_summary():
+    """name -> (calls, total ms) of the recorded phases (synchronises)."""
+    torch.cuda.synchronize()
+    return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (trace or {}).items()}
+
+
 timed_attention = None   # bench.py: a list here collects (start event, end event, Lq, Lk) of every self-attention launch
 
 _vp, _i, _f, _ll, _u = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_uint

@@ -46,8 +46,9 @@ class GuidedSampler:
     def __init__(self, transformer, vae, scheduler, guidance_scale: float, guided: bool = False, resample_steps: int = 1,
                  guide_steps: int = 20, omega: float = 1.8, omega_resample: float = 1.0, resample_round: int = 20,
                  use_pca_channel_selection: bool = False, static: bool = False,
-                 generator: Optional[torch.Generator] = None):
+                 generator: Optional[torch.Generator] = None, cfg_parallel=None):
         self.transformer, self.vae, self.scheduler = transformer, vae, scheduler
+        self.cfg_parallel = cfg_parallel       # worldforge_b200.ulysses.CfgParallel: this rank runs ONE of the two CFG forwards
         self.guidance_scale, self.guided, self.resample_steps = guidance_scale, guided, resample_steps
         self.guide_steps, self.omega, self.omega_resample, self.resample_round = guide_steps, omega, omega_resample, resample_round
         self.use_pca_channel_selection, self.static, self.generator = use_pca_channel_selection, static, generator
@@ -80,27 +81,43 @@ class GuidedSampler:
                 sch.set_resample_mode(False)
                 t_model = t.expand(latents.shape[0])
             model_in = torch.cat([latents, condition], dim=1).to(tdtype)
-            v = tr(hidden_states=model_in, timestep=t_model, encoder_hidden_states=prompt_embeds,
-                   encoder_hidden_states_image=image_embeds, attention_kwargs=None, return_dict=False)[0]
-            self.forwards += 1
-            if do_cfg:
-                v_u = tr(hidden_states=model_in, timestep=t_model, encoder_hidden_states=negative_prompt_embeds,
-                         encoder_hidden_states_image=image_embeds, attention_kwargs=None, return_dict=False)[0]
+            if do_cfg and self.cfg_parallel is not None:
+                mine = negative_prompt_embeds if self.cfg_parallel.branch else prompt_embeds
+                with lib.phase("dit.forward"):
+                    v = tr(hidden_states=model_in, timestep=t_model, encoder_hidden_states=mine,
+                           encoder_hidden_states_image=image_embeds, attention_kwargs=None, return_dict=False)[0]
+                self.forwards += 2                 # both forwards of the step ran, one in each half of the ranks
+                with lib.phase("cfg.exchange"):
+                    v, v_u = self.cfg_parallel.exchange(v)
+                v = lib.cfg_combine(v.contiguous(), v_u.contiguous(), self.guidance_scale)
+                if r < 1:
+                    sch.derivative_history.append(v)
+            else:
+                with lib.phase("dit.forward"):
+                    v = tr(hidden_states=model_in, timestep=t_model, encoder_hidden_states=prompt_embeds,
+                           encoder_hidden_states_image=image_embeds, attention_kwargs=None, return_dict=False)[0]
+                self.forwards += 1
+            if do_cfg and self.cfg_parallel is None:
+                with lib.phase("dit.forward"):
+                    v_u = tr(hidden_states=model_in, timestep=t_model, encoder_hidden_states=negative_prompt_embeds,
+                             encoder_hidden_states_image=image_embeds, attention_kwargs=None, return_dict=False)[0]
                 self.forwards += 1
                 v = lib.cfg_combine(v.contiguous(), v_u.contiguous(), self.guidance_scale)
                 if r < 1:
                     sch.derivative_history.append(v)
-            out = sch.step(v, t, latents, mask=mask, guided=self.guided and i < self.guide_steps and r < self.resample_steps,
-                           video_latents=video_ref, vae=self.vae, resampling=r > 0, return_dict=True, current_step=i,
-                           resample_count=self.resample_steps, is_resample_round=i < self.resample_round,
-                           use_pca_channel_selection=self.use_pca_channel_selection, static=self.static)
+            with lib.phase("scheduler.step"):
+                out = sch.step(v, t, latents, mask=mask, guided=self.guided and i < self.guide_steps and r < self.resample_steps,
+                               video_latents=video_ref, vae=self.vae, resampling=r > 0, return_dict=True, current_step=i,
+                               resample_count=self.resample_steps, is_resample_round=i < self.resample_round,
+                               use_pca_channel_selection=self.use_pca_channel_selection, static=self.static)
             if hasattr(out, "pred_x0"):
                 x0 = out.pred_x0
             if i >= self.resample_round:
                 break
             if r < self.resample_steps - 1 and x0 is not None:
                 if self.generator is not None:   # CPU generator: the noise stream is part of the result (:643-645)
-                    noise = torch.randn(x0.shape, generator=self.generator).pin_memory().to(device=device, non_blocking=True)
+                    with lib.phase("irr.noise_draw_upload"):
+                        noise = torch.randn(x0.shape, generator=self.generator).pin_memory().to(device=device, non_blocking=True)
                 else:
                     noise = torch.randn(x0.shape, device=device)
                 t_noise = sch.get_resample_timestep(i)
@@ -136,11 +153,11 @@ def denoise_loop(transformer, vae, scheduler, latents, condition, prompt_embeds,
                  guided: bool = False, resample_steps: int = 1, guide_steps: int = 20, omega: float = 1.8,
                  omega_resample: float = 1.0, resample_round: int = 20, use_pca_channel_selection: bool = False,
                  static: bool = False, generator: Optional[torch.Generator] = None,
-                 on_step: Optional[Callable] = None, max_steps: Optional[int] = None) -> torch.Tensor:
+                 on_step: Optional[Callable] = None, max_steps: Optional[int] = None, cfg_parallel=None) -> torch.Tensor:
     """``latents`` [1,16,f,h,w] fp32 on the device -> latents after the last step."""
     device = latents.device
     sampler = GuidedSampler(transformer, vae, scheduler, guidance_scale, guided, resample_steps, guide_steps, omega,
-                            omega_resample, resample_round, use_pca_channel_selection, static, generator)
+                            omega_resample, resample_round, use_pca_channel_selection, static, generator, cfg_parallel)
     timesteps = sampler.begin(num_inference_steps, device)
     if video_ref is not None and guided:
         video_ref = video_ref.to(device=device, dtype=torch.float32)
@@ -162,6 +179,7 @@ class WfWanI2VPipeline:
     def __init__(self, transformer, vae, scheduler):
         self.transformer, self.vae, self.scheduler = transformer, vae, scheduler
         self.vae_scale_factor_temporal, self.vae_scale_factor_spatial = 4, 8
+        self.cfg_parallel = None               # set to a worldforge_b200.ulysses.CfgParallel for the CFG x Ulysses layout
 
     def to(self, *a, **k):
         return self
@@ -191,7 +209,7 @@ class WfWanI2VPipeline:
                            guided=guided, resample_steps=resample_steps, guide_steps=guide_steps, omega=omega,
                            omega_resample=omega_resample, resample_round=resample_round,
                            use_pca_channel_selection=use_pca_channel_selection, static=static, generator=generator,
-                           on_step=on_step)
+                           on_step=on_step, cfg_parallel=self.cfg_parallel)
         if output_type == "latent":
             return out
         from .scheduler import latent_stats

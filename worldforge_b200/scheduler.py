@@ -254,14 +254,16 @@ class WfUniPCScheduler:
         x0 = pred_original_sample.contiguous()
         mean_h, inv_std_h = latent_stats(vae.config.latents_mean, vae.config.latents_std, x0.dtype)
         z = lib.latent_denorm(x0, mean_h, inv_std_h)
-        dec = vae.decode(z, return_dict=False)[0]
+        with lib.phase("flf.vae_decode"):
+            dec = vae.decode(z, return_dict=False)[0]
         if tuple(video_latents.shape) != tuple(dec.shape) or tuple(mask.shape) != (dec.shape[0], 1) + tuple(dec.shape[2:]):
             raise ValueError("video_ref / mask must be pre-sized to the decoded clip "
                              f"(got {tuple(video_latents.shape)}, {tuple(mask.shape)}, decoded {tuple(dec.shape)})")
         ref = video_latents if video_latents.dtype == torch.float32 else video_latents.to(torch.float32)
         m = mask if mask.dtype == torch.float32 else mask.to(torch.float32)
         fused = lib.flf_blend(dec.contiguous(), ref.contiguous(), m.contiguous())
-        enc = vae.encode(fused).latent_dist.mode().contiguous()
+        with lib.phase("flf.vae_encode"):
+            enc = vae.encode(fused).latent_dist.mode().contiguous()
         chans: List[int] = []
         if kw.get("use_pca_channel_selection") and not kw.get("resampling", False):
             step = kw.get("current_step", 0)
@@ -272,7 +274,8 @@ class WfUniPCScheduler:
                     sh = getattr(vae, "shard", None)      # one process per GPU: the ranks share the scoring work too
                     self._selector = flf_select.FlowChannelSelector() if sh is None or sh.world == 1 else \
                         flf_select.FlowChannelSelector(group=sh.group, world=sh.world, rank=sh.rank)
-                chans = self._selector.select(x0, fused_lat, step)
+                with lib.phase("flf.channel_scoring"):
+                    chans = self._selector.select(x0, fused_lat, step)
             self.flf_log.append((step, list(chans)))
         return lib.latent_norm_replace(enc, x0, mean_h, inv_std_h, chans)
 

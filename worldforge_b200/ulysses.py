@@ -149,6 +149,37 @@ class PeerSequenceParallel(SequenceParallel):
         return self.att[par]
 
 
+class CfgParallel:
+    """The two forwards of classifier-free guidance (conditional / unconditional: pipeline_wan_i2v_clean.py:593-610) are
+    independent, so on an even number of GPUs the ranks split into two halves that each run ONE of them - Ulysses inside a
+    half, over half as many ranks (twice the token shard per rank, half the exchange volume, half the barriers; SURVEY.md
+    §8e) - and rank r swaps its 8 MB prediction with rank r + P/2 before the CFG combination.  Both halves then hold both
+    predictions and everything after the combination stays replicated exactly as before.  The sequence-parallel forward is
+    bit-identical to the single-GPU one, so the result does not depend on the layout."""
+
+    def __init__(self, pair_group, branch: int):
+        self.group, self.branch = pair_group, branch           # branch 0: conditional, 1: unconditional
+        self.exchanges = 0
+
+    def exchange(self, v: torch.Tensor):
+        """This rank's prediction -> (conditional, unconditional)."""
+        both = [torch.empty_like(v), torch.empty_like(v)]
+        dist.all_gather(both, v.contiguous(), group=self.group)
+        self.exchanges += 1
+        return both[0], both[1]
+
+
+def cfg_layout(world: int, rank: int):
+    """Process groups of the CFG x Ulysses layout: (sequence-parallel group of this rank's half or None, CfgParallel).
+    Every rank creates every group, in the same order (torch.distributed requirement)."""
+    if world < 2 or world % 2:
+        raise ValueError("the CFG-parallel layout needs an even number of ranks")
+    half = world // 2
+    halves = [dist.new_group(list(range(b * half, (b + 1) * half))) if half > 1 else None for b in range(2)]
+    pairs = [dist.new_group([r, r + half]) for r in range(half)]
+    return halves[rank // half], CfgParallel(pairs[rank % half], rank // half)
+
+
 def enable(transformer, group=None, peer: bool = False) -> SequenceParallel:
     """``peer=True``: exchange through NVLink peer memory (built lazily at the first forward, when the token count is known)."""
     sp = SequenceParallel(group)
