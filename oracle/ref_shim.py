@@ -281,6 +281,45 @@ def load_longcat_dit_module(bsa: bool = False):
     return importlib.import_module("longcat_video.modules.longcat_video_dit")
 
 
+def load_longcat_vae_module():
+    """longcat_video/modules/autoencoder_kl_wan.py - the vendored copy of diffusers' ``AutoencoderKLWan`` (the class
+    infer_worldforge.py:185-189 loads) - over the shim, for pinning the diffusers <-> WanVAE_ parameter-name map."""
+    install_diffusers_shim()
+    import torch.nn as nn
+
+    def mod(name):
+        m = types.ModuleType(name)
+        sys.modules[name] = m
+        return m
+    ld = sys.modules.get("diffusers.loaders") or mod("diffusers.loaders")
+    ld.FromOriginalModelMixin = type("FromOriginalModelMixin", (), {})
+    au = mod("diffusers.utils.accelerate_utils")
+    au.apply_forward_hook = lambda f: f
+    act = mod("diffusers.models.activations")
+    act.get_activation = lambda name: {"silu": nn.SiLU(), "swish": nn.SiLU(), "gelu": nn.GELU()}[name]
+    class _AttrOut(dict):
+        __getattr__ = dict.__getitem__
+
+    mo = mod("diffusers.models.modeling_outputs")
+    mo.AutoencoderKLOutput = _AttrOut
+    ae = mod("diffusers.models.autoencoders"); av = mod("diffusers.models.autoencoders.vae")
+    av.DecoderOutput = _AttrOut
+
+    class _Diag:
+        def __init__(self, parameters):
+            self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+
+        def mode(self):
+            return self.mean
+    av.DiagonalGaussianDistribution = _Diag
+    ae.vae = av
+    path = os.path.join(REF_ROOT, "longcat_for_worldforge", "longcat_video", "modules", "autoencoder_kl_wan.py")
+    spec = importlib.util.spec_from_file_location("_wf_ref_autoencoder_kl_wan", path)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
 def load_longcat_scheduler_module():
     assert os.path.isdir(REF_LONGCAT)
     install_diffusers_shim()

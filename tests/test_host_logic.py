@@ -214,3 +214,64 @@ def test_context_cache_is_keyed_by_content_not_by_address():
     assert len(c) == 1 and c.get((held_alive, img)) == "A2"            # the stale entry was dropped
     c.put((b, img), "B"); c.put((torch.randn(4, 8), img), "C")
     assert len(c) == 2 and c.get((b, img)) == "B"                      # capacity 2: oldest evicted
+
+
+def test_longcat_lora_surface_folds_and_restores():
+    """load_lora / enable_loras / disable_all_loras of the reference DiT (longcat_video_dit.py:197-270; used at
+    run_longcat_worldforge_single.py:213-214, 449-451, 490) on the engine's transformer: enabling folds exactly what
+    ``merge_lora`` computes into the weights the decorated Linears own (fused qkv / kv / w1|w3 / adaLN rows included),
+    two LoRAs add up, and disabling restores the original weights bit for bit.  (Plain torch on the host: the fold never
+    touches a kernel.)"""
+    import torch
+    from oracle import longcat_dit as old
+    from worldforge_b200 import longcat
+    ocfg = old.LongCatConfig(hidden_size=128, depth=2, num_heads=1, caption_channels=32, adaln_tembed_dim=16, frequency_embedding_size=16)
+    sd = old.init_params(ocfg, 3)
+    cfg = longcat.LongCatConfig(hidden_size=128, depth=2, num_heads=1, caption_channels=32, adaln_tembed_dim=16, frequency_embedding_size=16)
+    m = longcat.WfLongCatTransformer.from_state_dict(sd, cfg, "cpu")
+    H, r = "___lorahyphen___", 4
+    g = torch.Generator().manual_seed(11)
+    C, Fd = cfg.hidden_size, cfg.ffn_dim
+
+    def lora_for(mods, seed):
+        g = torch.Generator().manual_seed(seed)
+        out = {}
+        for mod, (n_out, n_in, nsep) in mods.items():
+            name = "lora" + H + mod.replace(".", H)
+            out[name + ".lora_down.weight"] = torch.randn(nsep * r, n_in, generator=g) * 0.1
+            if nsep == 1:
+                out[name + ".lora_up.weight"] = torch.randn(n_out, r, generator=g) * 0.1
+            else:
+                for i in range(nsep):
+                    out[f"{name}.lora_up.blocks.{i}.weight"] = torch.randn(n_out // nsep, r, generator=g) * 0.1
+        return out
+    la = lora_for({"blocks.0.attn.qkv": (3 * C, C, 3), "blocks.1.cross_attn.kv_linear": (2 * C, C, 2), "blocks.1.ffn.w3": (Fd, C, 1),
+                   "blocks.0.adaLN_modulation.1": (6 * C, 16, 1), "final_layer.linear": (64, C, 1)}, 5)
+    lb = lora_for({"blocks.0.attn.qkv": (3 * C, C, 3), "blocks.1.ffn.w1": (Fd, C, 1)}, 6)
+    before = {k: v.clone() for k, v in (("qkv0", m.blocks[0].qkv_w), ("ckv1", m.blocks[1].ckv_w), ("w13_1", m.blocks[1].w13),
+                                        ("ada", m.ada_w), ("final", m.final_w), ("proj0", m.blocks[0].proj_w))}
+    m.load_lora(la, "a", multiplier=0.7, lora_network_dim=r, lora_network_alpha=2)
+    m.load_lora(lb, "b", multiplier=1.0, lora_network_dim=r, lora_network_alpha=2)
+    m.enable_loras(["a", "b"])
+    assert m.active_loras == ["a", "b"]
+    folded = longcat.merge_lora(longcat.merge_lora({k: v.to(torch.bfloat16).float() for k, v in sd.items()}, la, 0.7, r, 2), lb, 1.0, r, 2)
+    bf = torch.bfloat16
+    assert torch.equal(m.blocks[0].qkv_w, folded["blocks.0.attn.qkv.weight"].to(bf))
+    assert torch.equal(m.blocks[1].ckv_w, folded["blocks.1.cross_attn.kv_linear.weight"].to(bf))
+    assert torch.equal(m.blocks[1].w13, torch.cat([folded["blocks.1.ffn.w1.weight"], folded["blocks.1.ffn.w3.weight"]]).to(bf))
+    assert torch.equal(m.ada_w[:6 * C], folded["blocks.0.adaLN_modulation.1.weight"].to(bf))
+    assert torch.equal(m.ada_w[6 * C:], before["ada"][6 * C:])                        # untouched rows
+    assert torch.equal(m.final_w, folded["final_layer.linear.weight"].to(bf).float())
+    assert torch.equal(m.blocks[0].proj_w, before["proj0"]) and not torch.equal(m.blocks[0].qkv_w, before["qkv0"])
+    m.enable_loras(["a"])                                                             # re-enabling starts from the originals
+    only_a = longcat.merge_lora({k: v.to(bf).float() for k, v in sd.items()}, la, 0.7, r, 2)
+    assert torch.equal(m.blocks[0].qkv_w, only_a["blocks.0.attn.qkv.weight"].to(bf)) and m.active_loras == ["a"]
+    assert torch.equal(m.blocks[1].w13[:Fd], before["w13_1"][:Fd])
+    m.disable_all_loras()
+    assert m.active_loras == []
+    for k, v in (("qkv0", m.blocks[0].qkv_w), ("ckv1", m.blocks[1].ckv_w), ("w13_1", m.blocks[1].w13), ("ada", m.ada_w),
+                 ("final", m.final_w)):
+        assert torch.equal(v, before[k]), k
+    with pytest.raises(Exception):
+        m.load_lora(lora_for({"blocks.0.attn.q_norm": (128, 128, 1)}, 7), "bad", lora_network_dim=r)
+        m.enable_loras(["bad"])

@@ -129,3 +129,53 @@ def test_row_sharded_vae_is_bit_identical(cuda, world, F_, H, W):
     assert torch.equal(mu, want_mu)
     x = m._conv(wvae.lib.planar_to_cl(z[0].contiguous(), m.z_dim, round_tf32=True), "conv2", wvae.TAPS_1, m.z_dim, round_out=True)
     assert torch.equal(run("dec", x).unsqueeze(0), want_dec)
+
+
+def test_diffusers_state_dict_names_load(cuda):
+    """The engine's VAE built from a state dict under diffusers' ``AutoencoderKLWan`` names (what ``pipe.vae.state_dict()``
+    hands over in infer_worldforge.py) equals the one built from ``WanVAE_`` names (the map itself is pinned against both
+    reference classes in tests/test_oracle_pinning.py)."""
+    import re
+    from worldforge_b200 import vae as wvae
+    a = wvae.WfWanVAE.random_init(cuda, dim=16, seed=9)
+    sd = {}
+    # invert the map on the vendored-name dict the random init produces
+    vend = wvae.random_state_dict(dim=16, seed=9)
+    res = {"residual.0": "norm1", "residual.2": "conv1", "residual.3": "norm2", "residual.6": "conv2", "shortcut": "conv_shortcut"}
+
+    def resnet(rest):
+        for k, v in res.items():
+            if rest.startswith(k + "."):
+                return v + rest[len(k):]
+        return rest
+    for k, v in vend.items():
+        if k.startswith("conv1."):
+            sd["quant_conv." + k[6:]] = v; continue
+        if k.startswith("conv2."):
+            sd["post_quant_conv." + k[6:]] = v; continue
+        side, rest = k.split(".", 1)
+        if rest.startswith("conv1."):
+            nk = "conv_in." + rest[6:]
+        elif rest.startswith("head.0."):
+            nk = "norm_out." + rest[7:]
+        elif rest.startswith("head.2."):
+            nk = "conv_out." + rest[7:]
+        elif rest.startswith("middle."):
+            i, tail = rest[7:].split(".", 1)
+            nk = f"mid_block.attentions.0.{tail}" if i == "1" else f"mid_block.resnets.{int(i) // 2}.{resnet(tail)}"
+        elif rest.startswith("downsamples."):
+            i, tail = rest[12:].split(".", 1)
+            nk = f"down_blocks.{i}.{resnet(tail)}"
+        else:
+            m = re.match(r"upsamples\.(\d+)\.(.*)", rest)
+            idx, tail = int(m.group(1)), m.group(2)
+            blk, j = divmod(idx, 4)
+            nk = f"up_blocks.{blk}.upsamplers.0.{tail}" if j == 3 else f"up_blocks.{blk}.resnets.{j}.{resnet(tail)}"
+        sd[side + "." + nk] = v
+    assert any(k.startswith("decoder.up_blocks.2.upsamplers.0.") for k in sd) and "quant_conv.weight" in sd
+    b = wvae.WfWanVAE(sd, cuda, dim=16)
+    g = torch.Generator().manual_seed(2)
+    z = torch.randn(1, 16, 2, 8, 12, generator=g).to(cuda)
+    assert torch.equal(a.decode(z)[0], b.decode(z)[0])
+    video = (torch.rand(1, 3, 5, 64, 96, generator=g) * 2 - 1).to(cuda)
+    assert torch.equal(a.encode(video).latent_dist.mode(), b.encode(video).latent_dist.mode())

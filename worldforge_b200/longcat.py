@@ -107,9 +107,89 @@ class WfLongCatTransformer:
         self.calls = 0
         self.bsa_params = None          # the checkpoint's bsa_params (longcat_video_dit.py:32,56)
         self._bsa_on = False
+        self.lora_dict, self.active_loras, self._lora_saved = {}, [], {}
 
     def to(self, *a, **k):
         return self
+
+    # ---------------------------------------------------------------------------------- LoRA surface
+    # longcat_video_dit.py:197-270, used by run_longcat_worldforge_single.py:213-214 (cfg_step_lora of the distilled mode)
+    # and :449-451 / :490 (refinement_lora around the 720p pass).  The reference hooks two bf16 side GEMMs into every
+    # decorated Linear at run time; here enable_loras FOLDS the active LoRAs into the weights those Linears own
+    # (W' = bf16(W + sum multiplier * alpha/rank * up @ down), exactly ``merge_lora``) and disable_all_loras restores the
+    # saved originals - the step itself runs the same kernels with or without a LoRA.
+    def _lora_targets(self):
+        """module path (as the LoRA keys spell it) -> (tensor that holds the weight, first row, rows, fp32 island?)"""
+        c = self.cfg
+        C, Fd = c.hidden_size, c.ffn_dim
+        t = {"final_layer.linear": (self.final_w, 0, self.final_w.shape[0], True),
+             "final_layer.adaLN_modulation.1": (self.ada_w, 6 * C * c.depth, 2 * C, False),
+             "t_embedder.mlp.0": (self.t0_w, 0, self.t0_w.shape[0], False), "t_embedder.mlp.2": (self.t2_w, 0, self.t2_w.shape[0], False),
+             "y_embedder.y_proj.0": (self.y0_w, 0, self.y0_w.shape[0], False), "y_embedder.y_proj.2": (self.y2_w, 0, self.y2_w.shape[0], False)}
+        for i, b in enumerate(self.blocks):
+            p = f"blocks.{i}."
+            t[p + "attn.qkv"] = (b.qkv_w, 0, 3 * C, False)
+            t[p + "attn.proj"] = (b.proj_w, 0, C, False)
+            t[p + "cross_attn.q_linear"] = (b.cq_w, 0, C, False)
+            t[p + "cross_attn.kv_linear"] = (b.ckv_w, 0, 2 * C, False)
+            t[p + "cross_attn.proj"] = (b.cproj_w, 0, C, False)
+            t[p + "ffn.w1"] = (b.w13, 0, Fd, False)
+            t[p + "ffn.w3"] = (b.w13, Fd, Fd, False)
+            t[p + "ffn.w2"] = (b.w2, 0, C, False)
+            t[p + "adaLN_modulation.1"] = (self.ada_w, 6 * C * i, 6 * C, False)
+        return t
+
+    def load_lora(self, lora_path, lora_key, multiplier=1.0, lora_network_dim=128, lora_network_alpha=64):
+        """``lora_path``: a .safetensors file (as in the reference) or an already loaded dict of tensors."""
+        if isinstance(lora_path, dict):
+            sd = lora_path
+        else:
+            from safetensors.torch import load_file
+            sd = load_file(lora_path, device="cpu")
+        self.lora_dict[lora_key] = SimpleNamespace(sd=sd, multiplier=multiplier, dim=lora_network_dim, alpha=lora_network_alpha)
+
+    def enable_loras(self, lora_key_list=()):
+        self.disable_all_loras()
+        targets = self._lora_targets()
+        deltas = {}
+        for key in lora_key_list:
+            if key not in self.lora_dict:
+                continue
+            net = self.lora_dict[key]
+            scale = net.multiplier * ((net.alpha / net.dim) if net.alpha else 1.0)
+            names = sorted(k[: -len(".lora_down.weight")] for k in net.sd if k.endswith(".lora_down.weight"))
+            for name in names:
+                module = name.replace("lora___lorahyphen___", "").replace("___lorahyphen___", ".")
+                if module not in targets:
+                    raise lib.WfError(f"LoRA '{key}' decorates '{module}', which is not a Linear of this engine")
+                down = net.sd[name + ".lora_down.weight"].to(self.device, F32)
+                if name + ".lora_up.weight" in net.sd:
+                    delta = net.sd[name + ".lora_up.weight"].to(self.device, F32) @ down
+                else:                                  # LoRAUPParallel (lora_utils.py:15-24): block-diagonal up over the fused outputs
+                    ups = []
+                    while f"{name}.lora_up.blocks.{len(ups)}.weight" in net.sd:
+                        ups.append(net.sd[f"{name}.lora_up.blocks.{len(ups)}.weight"].to(self.device, F32))
+                    r = down.shape[0] // len(ups)
+                    delta = torch.cat([u @ down[j * r:(j + 1) * r] for j, u in enumerate(ups)], dim=0)
+                deltas[module] = deltas.get(module, 0) + scale * delta
+            self.active_loras.append(key)
+        for module, delta in deltas.items():
+            w, r0, n, island = targets[module]
+            view = w[r0:r0 + n]
+            self._lora_saved[module] = view.clone()
+            view.copy_((view.to(F32) + delta).to(BF).to(view.dtype) if island else (view.to(F32) + delta).to(view.dtype))
+        if deltas:
+            self._ctx_cache = ContextCache(4)           # cached context K/V came from the weights that just changed
+
+    def disable_all_loras(self):
+        targets = self._lora_targets() if self._lora_saved else {}
+        for module, saved in self._lora_saved.items():
+            w, r0, n, _ = targets[module]
+            w[r0:r0 + n].copy_(saved)
+        if self._lora_saved:
+            self._ctx_cache = ContextCache(4)
+        self._lora_saved = {}
+        self.active_loras = []
 
     # block-sparse self-attention of the 720p refine pass (longcat_video_dit.py:272-278, attention.py:56-67)
     def enable_bsa(self):

@@ -130,6 +130,64 @@ class _Dist:
         return self._mean
 
 
+def to_vendored_vae_names(sd: Dict[str, torch.Tensor], num_res_blocks: int = 2) -> Dict[str, torch.Tensor]:
+    """Accept the state dict of diffusers' ``AutoencoderKLWan`` - the class the entry script loads
+    (wan_for_worldforge/infer_worldforge.py:185-189; vendored twin longcat_video/modules/autoencoder_kl_wan.py:505-604
+    encoder, :783-870 decoder, :1029-1052 quant convs) - and return it under the key names of the reference's
+    ``WanVAE_`` (wan/modules/vae.py), which is what ``WfWanVAE`` consumes.  A dict that already uses them passes through.
+
+      encoder.conv_in / conv_out / norm_out            -> encoder.conv1 / head.2 / head.0
+      encoder.down_blocks.N  (resnet | resample)        -> encoder.downsamples.N
+      *.mid_block.resnets.{0,1} / attentions.0          -> *.middle.{0,2} / middle.1
+      decoder.up_blocks.I.resnets.J / upsamplers.0      -> decoder.upsamples.{I*(R+2)+J} / {I*(R+2)+R+1}   (R = num_res_blocks)
+      resnet: norm1 / conv1 / norm2 / conv2 / conv_shortcut -> residual.0 / .2 / .3 / .6 / shortcut
+      quant_conv / post_quant_conv                      -> conv1 / conv2
+    """
+    if not any(k.startswith(("quant_conv.", "post_quant_conv.", "encoder.conv_in.", "decoder.conv_in.")) for k in sd):
+        return sd
+    res = {"norm1": "residual.0", "conv1": "residual.2", "norm2": "residual.3", "conv2": "residual.6", "conv_shortcut": "shortcut"}
+    R = num_res_blocks
+
+    def resnet(rest: str) -> str:
+        head, _, tail = rest.partition(".")
+        return res[head] + "." + tail if head in res else rest
+
+    out = {}
+    for k, v in sd.items():
+        p = k.split(".")
+        if p[0] == "quant_conv":
+            out["conv1." + ".".join(p[1:])] = v
+        elif p[0] == "post_quant_conv":
+            out["conv2." + ".".join(p[1:])] = v
+        elif p[0] in ("encoder", "decoder"):
+            side, rest = p[0], p[1:]
+            if rest[0] == "conv_in":
+                nk = "conv1." + ".".join(rest[1:])
+            elif rest[0] == "norm_out":
+                nk = "head.0." + ".".join(rest[1:])
+            elif rest[0] == "conv_out":
+                nk = "head.2." + ".".join(rest[1:])
+            elif rest[0] == "mid_block":
+                if rest[1] == "resnets":
+                    nk = f"middle.{2 * int(rest[2])}." + resnet(".".join(rest[3:]))
+                else:                                   # attentions.0
+                    nk = "middle.1." + ".".join(rest[3:])
+            elif rest[0] == "down_blocks":
+                nk = f"downsamples.{rest[1]}." + resnet(".".join(rest[2:]))
+            elif rest[0] == "up_blocks":
+                i = int(rest[1])
+                if rest[2] == "resnets":
+                    nk = f"upsamples.{i * (R + 2) + int(rest[3])}." + resnet(".".join(rest[4:]))
+                else:                                   # upsamplers.0
+                    nk = f"upsamples.{i * (R + 2) + R + 1}." + ".".join(rest[4:])
+            else:
+                nk = ".".join(rest)
+            out[side + "." + nk] = v
+        else:
+            out[k] = v
+    return out
+
+
 class WfWanVAE:
     """Weights prepared once on the device; ``encode`` / ``decode`` are sequences of C-ABI launches."""
 
@@ -144,7 +202,7 @@ class WfWanVAE:
         self.enc_plan, self.dec_plan = self._plans()
         self.spatial_scale = 2 ** (len(self.dim_mult) - 1)
         self.shard = None                  # set by enable_row_sharding
-        sd = {k: v.to(device=self.device, dtype=F32) for k, v in state_dict.items()}
+        sd = {k: v.to(device=self.device, dtype=F32) for k, v in to_vendored_vae_names(state_dict, num_res_blocks).items()}
         self.w: Dict[str, torch.Tensor] = {}
         self._prepare(sd)
 
@@ -558,39 +616,45 @@ class WfWanVAE:
     @classmethod
     def random_init(cls, device, seed: int = 4321, **kw):
         """Random-init weights with the reference network's shapes."""
-        proto = cls.__new__(cls)
-        proto.dim = kw.get("dim", 96); proto.z_dim = kw.get("z_dim", 16)
-        proto.dim_mult = tuple(kw.get("dim_mult", (1, 2, 4, 4))); proto.num_res_blocks = kw.get("num_res_blocks", 2)
-        proto.temperal_downsample = list(kw.get("temporal_downsample", (False, True, True)))
-        enc, dec = proto._plans()
-        g = torch.Generator().manual_seed(seed)
-        sd = {}
-        def conv(name, cin, cout, k):
-            fan = cin * k[0] * k[1] * k[2] if len(k) == 3 else cin * k[0] * k[1]
-            sd[name + ".weight"] = torch.randn(cout, cin, *k, generator=g) / fan ** 0.5
-            sd[name + ".bias"] = 0.02 * torch.randn(cout, generator=g)
-        def gam(name, c, nd):
-            sd[name] = (1.0 + 0.05 * torch.randn(c, generator=g)).reshape(c, *([1] * nd))
-        for plan in (enc, dec):
-            for kind, name, cin, cout in plan:
-                if kind == "conv":
-                    conv(name, cin, cout, (3, 3, 3))
-                elif kind == "res":
-                    gam(name + ".residual.0.gamma", cin, 3); conv(name + ".residual.2", cin, cout, (3, 3, 3))
-                    gam(name + ".residual.3.gamma", cout, 3); conv(name + ".residual.6", cout, cout, (3, 3, 3))
-                    if cin != cout:
-                        conv(name + ".shortcut", cin, cout, (1, 1, 1))
-                elif kind == "attn":
-                    gam(name + ".norm.gamma", cin, 2); conv(name + ".to_qkv", cin, 3 * cin, (1, 1)); conv(name + ".proj", cin, cin, (1, 1))
-                elif kind in ("down2d", "down3d"):
-                    conv(name + ".resample.1", cin, cin, (3, 3))
-                    if kind == "down3d":
-                        conv(name + ".time_conv", cin, cin, (3, 1, 1))
-                elif kind in ("up2d", "up3d"):
-                    conv(name + ".resample.1", cin, cin // 2, (3, 3))
-                    if kind == "up3d":
-                        conv(name + ".time_conv", cin, 2 * cin, (3, 1, 1))
-                elif kind == "head":
-                    gam(name + ".0.gamma", cin, 3); conv(name + ".2", cin, cout, (3, 3, 3))
-        conv("conv1", 2 * proto.z_dim, 2 * proto.z_dim, (1, 1, 1)); conv("conv2", proto.z_dim, proto.z_dim, (1, 1, 1))
-        return cls(sd, device, **kw)
+        return cls(random_state_dict(seed=seed, **kw), device, **kw)
+
+
+def random_state_dict(seed: int = 4321, **kw) -> Dict[str, torch.Tensor]:
+    """A random state dict under the reference's ``WanVAE_`` parameter names (CPU tensors)."""
+    proto = WfWanVAE.__new__(WfWanVAE)
+    proto.dim = kw.get("dim", 96); proto.z_dim = kw.get("z_dim", 16)
+    proto.dim_mult = tuple(kw.get("dim_mult", (1, 2, 4, 4))); proto.num_res_blocks = kw.get("num_res_blocks", 2)
+    proto.temperal_downsample = list(kw.get("temporal_downsample", (False, True, True)))
+    enc, dec = proto._plans()
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    def conv(name, cin, cout, k):
+        fan = cin * k[0] * k[1] * k[2] if len(k) == 3 else cin * k[0] * k[1]
+        sd[name + ".weight"] = torch.randn(cout, cin, *k, generator=g) / fan ** 0.5
+        sd[name + ".bias"] = 0.02 * torch.randn(cout, generator=g)
+    def gam(name, c, nd):
+        sd[name] = (1.0 + 0.05 * torch.randn(c, generator=g)).reshape(c, *([1] * nd))
+    for plan in (enc, dec):
+        for kind, name, cin, cout in plan:
+            if kind == "conv":
+                conv(name, cin, cout, (3, 3, 3))
+            elif kind == "res":
+                gam(name + ".residual.0.gamma", cin, 3); conv(name + ".residual.2", cin, cout, (3, 3, 3))
+                gam(name + ".residual.3.gamma", cout, 3); conv(name + ".residual.6", cout, cout, (3, 3, 3))
+                if cin != cout:
+                    conv(name + ".shortcut", cin, cout, (1, 1, 1))
+            elif kind == "attn":
+                gam(name + ".norm.gamma", cin, 2); conv(name + ".to_qkv", cin, 3 * cin, (1, 1)); conv(name + ".proj", cin, cin, (1, 1))
+            elif kind in ("down2d", "down3d"):
+                conv(name + ".resample.1", cin, cin, (3, 3))
+                if kind == "down3d":
+                    conv(name + ".time_conv", cin, cin, (3, 1, 1))
+            elif kind in ("up2d", "up3d"):
+                conv(name + ".resample.1", cin, cin // 2, (3, 3))
+                if kind == "up3d":
+                    conv(name + ".time_conv", cin, 2 * cin, (3, 1, 1))
+            elif kind == "head":
+                gam(name + ".0.gamma", cin, 3); conv(name + ".2", cin, cout, (3, 3, 3))
+    conv("conv1", 2 * proto.z_dim, 2 * proto.z_dim, (1, 1, 1)); conv("conv2", proto.z_dim, proto.z_dim, (1, 1, 1))
+    return sd
+
