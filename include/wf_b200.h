@@ -187,6 +187,15 @@ int wf_dsg(const void* g, const void* w, void* out, int is_bf16, float omega, lo
  * decoded/ref/out [channels, plane], mask [plane] broadcast over channels. */
 int wf_flf_blend(const float* decoded, const float* ref, const float* mask, float* out, int channels,
                  long long plane, void* stream);
+/* Input preparation of the entry script (wan_for_worldforge/infer_worldforge.py).
+ * wf_soften_mask replaces soften_mask (:105-150) for one clip: mask / out fp32 [frames][H][W]; a set pixel (!= 0) whose exact
+ * Euclidean distance d to the nearest unset pixel of its frame satisfies d*d <= max_d2 becomes lut[d*d]; every other pixel is
+ * copied.  radius = floor(transition_distance) <= 31, max_d2 = floor(transition_distance^2), lut: device float[max_d2 + 1]
+ * holding smooth(sqrt(d2) / transition_distance) as the reference's float64 numpy expression rounds it to fp32.
+ * wf_clip_from_u8 replaces the frame stacking of :232-238: uint8 [pixels][3] -> planar fp32 [3][pixels] / 255. */
+int wf_soften_mask(const float* mask, float* out, int frames, int H, int W, int radius, int max_d2, const float* lut,
+                   void* stream);
+int wf_clip_from_u8(const unsigned char* frames, float* out, long long pixels, void* stream);
 /* LongCat generate_refine step 5 (longcat_video/pipeline_longcat_video.py:1393-1419): stage-1 video uint8 [F,H0,W0,3]
  * -> bilinear (align_corners) to [H,W] -> /255 -> trilinear to F2 frames -> *2-1, bf16 intermediates as in the reference,
  * first / last frame repeated pad_front / pad_back times.  out: planar fp32 [3][pad_front+F2+pad_back][H][W]. */

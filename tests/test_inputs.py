@@ -1,0 +1,73 @@
+"""Input preparation: the oracle against the reference's own soften_mask (committed fixture + live),
+the device kernels against the oracle (bit for bit)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import inputs as oin
+from oracle import make_inputs_golden as mig
+
+GOLD = torch.load(os.path.join(os.path.dirname(__file__), "golden", "inputs_golden.pt"), weights_only=False)
+CASES = ((15, "sine"), (7, "linear"), (10, "exponential"), (4, "cosine"))
+
+
+def test_oracle_soften_mask_matches_reference_fixture():
+    arr = oin.stack_masks(GOLD["masks_u8"].numpy())
+    assert np.array_equal(GOLD["masks_u8"].numpy(), mig.masks())
+    for td, kind in CASES:
+        got = oin.soften_mask(arr, td, kind)
+        assert got.dtype == np.float32
+        assert np.array_equal(got, GOLD[f"soft_{td}_{kind}"].numpy()), (td, kind)
+    soft = GOLD["soft_15_sine"].numpy()
+    assert 0.0 < soft[0][soft[0] > 0].min() < 0.2 and np.array_equal(soft[3], np.ones_like(soft[3])) and not soft[4].any()
+
+
+@pytest.mark.skipif(not os.path.exists(mig.REF), reason="/root/reference is not mounted")
+def test_oracle_soften_mask_matches_live_reference():
+    ref = oin.reference_soften_mask(mig.REF)
+    rng = np.random.default_rng(5)
+    arr = (rng.random((3, 50, 64)) > 0.3).astype(np.float64)
+    arr[1, 20:30, 20:40] = 1.0
+    for td, kind in CASES + ((2.5, "sine"),):
+        assert np.array_equal(oin.soften_mask(arr, td, kind), ref(arr, td, kind))
+
+
+def test_ramp_table_is_the_reference_expression():
+    from worldforge_b200 import inputs
+    for td, kind in CASES + ((2.5, "sine"),):
+        table, radius, max_d2 = inputs._ramp_table(td, kind)
+        assert radius == int(np.floor(td)) and max_d2 == int(np.floor(td * td)) and len(table) == max_d2 + 1
+        d = np.sqrt(np.arange(max_d2 + 1, dtype=np.float64))
+        assert np.array_equal(table, oin.smooth_transition(d / td, kind).astype(np.float32))
+    assert np.array_equal(inputs._U8_TO_UNIT.numpy(), (np.arange(256) / 255.0).astype(np.float32))
+
+
+@pytest.mark.gpu
+def test_device_soften_mask_is_bit_identical(cuda):
+    from worldforge_b200 import inputs
+    mu8 = GOLD["masks_u8"].to(cuda)
+    for td, kind in CASES:
+        got = inputs.soften_mask(mu8, td, kind)
+        assert torch.equal(got.cpu(), GOLD[f"soft_{td}_{kind}"]), (td, kind)
+    # a full-size clip with ragged edges against the oracle (not a multiple of the 32-pixel tile), fractional distance
+    rng = np.random.default_rng(9)
+    arr = (rng.random((4, 123, 211)) > 0.004).astype(np.float32)
+    arr[2, 40:80, 100:160] = 0.0
+    for td, kind in ((15, "sine"), (2.5, "cosine"), (31, "linear")):
+        want = oin.soften_mask(arr.astype(np.float64), td, kind)
+        got = inputs.soften_mask(torch.from_numpy(arr).to(cuda), td, kind)
+        assert torch.equal(got.cpu(), torch.from_numpy(want)), (td, kind)
+    assert inputs.prepare_mask(mu8).shape == (1, 1) + tuple(mu8.shape)
+
+
+@pytest.mark.gpu
+def test_device_frame_stacking(cuda):
+    from worldforge_b200 import inputs
+    g = torch.Generator().manual_seed(0)
+    frames = torch.randint(0, 256, (5, 37, 53, 3), generator=g, dtype=torch.uint8)
+    got = inputs.clip_from_frames(frames.to(cuda))
+    assert torch.equal(got.cpu(), torch.from_numpy(oin.stack_frames(frames.numpy())))
+    want = torch.stack([torch.tensor(np.array(f)).permute(2, 0, 1).float() / 255.0 for f in frames.numpy()]).unsqueeze(0).permute(0, 2, 1, 3, 4)
+    assert torch.equal(got.cpu(), want)                              # the reference's own expression (:232-238)

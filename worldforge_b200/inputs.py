@@ -1,0 +1,77 @@
+"""Input preparation of the entry script on the device.
+
+Stands where ``wan_for_worldforge/infer_worldforge.py`` prepares the warped reference clip and its mask: ``soften_mask``
+(:105-150, same name and arguments), the frame stacking (:232-238) and the mask stacking (:244-251).  PIL's resize of the
+PNG frames (:225, :231, :245) stays on the host - it happens once per video on 8-bit images.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import lib
+
+
+def _ramp_table(transition_distance, decay_type: str):
+    """smooth(sqrt(d2) / transition_distance) for every integer d2 <= transition_distance^2, evaluated with the reference's
+    float64 numpy expressions (:126-137, :141-143) and stored to float32 as the reference's assignment does (:143)."""
+    td = float(transition_distance)
+    max_d2 = int(np.floor(td * td))
+    d = np.sqrt(np.arange(max_d2 + 1, dtype=np.float64))
+    t = np.clip(d / transition_distance, 0.0, 1.0)
+    if decay_type == "linear":
+        v = t
+    elif decay_type == "exponential":
+        v = 1.0 - np.exp(-3.0 * t)
+    elif decay_type == "sine":
+        v = np.sin(np.pi / 2 * t)
+    elif decay_type == "cosine":
+        v = 1.0 - np.cos(np.pi / 2 * t)
+    else:
+        raise ValueError(f"Unsupported decay type: {decay_type}")
+    return v.astype(np.float32), int(np.floor(td)), max_d2
+
+
+_U8_TO_UNIT = torch.from_numpy((np.arange(256) / 255.0).astype(np.float32))     # float32(u8 / 255.0 in float64), :246 then :117
+
+
+def mask_from_u8(masks_u8: torch.Tensor) -> torch.Tensor:
+    """uint8 [F,H,W] on the device -> fp32 [F,H,W] = float32(np.array(mask) / 255.0)."""
+    return _U8_TO_UNIT.to(masks_u8.device)[masks_u8.long()]
+
+
+def soften_mask(mask_array, transition_distance=15, decay_type: str = "sine") -> torch.Tensor:
+    """``mask_array`` [F,H,W]: CUDA tensor (fp32 values 0..1, or uint8 0..255) or a numpy array (uploaded) -> fp32 CUDA tensor,
+    the reference's softened mask bit for bit."""
+    if isinstance(mask_array, np.ndarray):
+        mask_array = torch.from_numpy(np.ascontiguousarray(mask_array)).to("cuda")
+    if not mask_array.is_cuda:
+        raise lib.WfError("soften_mask runs on CUDA tensors only (no CPU fallback)")
+    m = mask_from_u8(mask_array) if mask_array.dtype == torch.uint8 else mask_array.to(torch.float32)
+    m = m.contiguous()
+    assert m.dim() == 3
+    if transition_distance > 31:
+        raise lib.WfError("soften_mask: transition_distance above 31 pixels is not supported on the device")
+    table, radius, max_d2 = _ramp_table(transition_distance, decay_type)
+    lut = torch.from_numpy(table).to(m.device)
+    out = torch.empty_like(m)
+    lib._call("wf_soften_mask", m.data_ptr(), out.data_ptr(), m.shape[0], m.shape[1], m.shape[2], radius, max_d2, lut.data_ptr(),
+              lib._stream())
+    return out
+
+
+def clip_from_frames(frames_u8: torch.Tensor) -> torch.Tensor:
+    """uint8 [F,H,W,3] on the device -> video_ref [1,3,F,H,W] fp32 in [0,1] (:232-238)."""
+    if not frames_u8.is_cuda or frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or frames_u8.shape[-1] != 3:
+        raise lib.WfError("clip_from_frames: expected a CUDA uint8 tensor [F,H,W,3]")
+    f = frames_u8.contiguous()
+    F_, H, W = f.shape[:3]
+    out = torch.empty(1, 3, F_, H, W, dtype=torch.float32, device=f.device)
+    lib._call("wf_clip_from_u8", f.data_ptr(), out.data_ptr(), F_ * H * W, lib._stream())
+    return out
+
+
+def prepare_mask(masks_u8: torch.Tensor, soften: bool = True, transition_distance=15, decay_type: str = "sine") -> torch.Tensor:
+    """uint8 [F,H,W] -> mask [1,1,F,H,W] fp32 (:244-251)."""
+    m = soften_mask(masks_u8, transition_distance, decay_type) if soften else mask_from_u8(masks_u8)
+    return m.unsqueeze(0).unsqueeze(0)
