@@ -71,6 +71,12 @@ int wf_bsa_mean_pool(const void* x, int ldx, void* out, int T, int H, int W, int
  * ascending chunk order (the order topk_sort gives, :530-534); ties at the threshold take the lower chunk index. */
 int wf_bsa_select_topk(const void* q_cmp, const void* k_cmp, int32_t* idx, int Nq, int Nk, int heads, int n_sel,
                        void* stream);
+/* get_select_indices_cdf / get_select_indices_cdf_topk (bsa_interface.py:234-275): idx [heads][Nq][Nk] = the key chunks of
+ * every query chunk sorted by softmax(score / sqrt(128)) descending (ties: lower chunk first), lens [heads][Nq] = how many
+ * of them have a cumulative softmax mass <= cdf_threshold (searchsorted right=True; may be 0), raised to n_floor (the
+ * top-k count int((1 - sparsity) * Nk), or 0 for the plain cdf rule). */
+int wf_bsa_select_cdf(const void* q_cmp, const void* k_cmp, int32_t* idx, int32_t* lens, int Nq, int Nk, int heads,
+                      float cdf_threshold, int n_floor, void* stream);
 
 /* flash_attn_bsa_3d minus the gating (bsa_interface.py:612-659 -> _attn_fwd_bsa_varlen_align,
  * flash_attn_bsa_varlen_mask.py:174-285): every query chunk attends to the key chunks block_idx[h][chunk][0 ..

@@ -126,3 +126,47 @@ def test_dense_equivalence(cuda):
     lib.attention_bsa_bf16(q, k, v, a, heads, idx, None, grid, grid, chunk)
     lib.attention_bf16(q, k, v, b, heads)
     assert (a.float() - b.float()).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("Nq,Nk,thr,sparsity", [(16, 16, 0.5, None), (37, 70, 0.9, None), (9, 300, 0.6, 0.9), (5, 33, 0.99, 0.5),
+                                                (8, 880, 0.8, 0.9375)])
+def test_select_cdf(cuda, Nq, Nk, thr, sparsity):
+    """get_select_indices_cdf(_topk) (bsa_interface.py:234-275) on the device against the oracle's torch restatement: the
+    sorted order is the descending order of the bf16 scores, and the selected count equals the oracle's up to the one chunk
+    whose cumulative mass sits within fp32 summation noise of the threshold."""
+    from oracle import longcat_bsa as ob
+    from worldforge_b200 import lib
+    heads = 3
+    g = torch.Generator().manual_seed(Nq * 1000 + Nk)
+    qc = (torch.randn(heads, Nq, 128, generator=g) * 1.5).to(BF).to(cuda)
+    kc = torch.randn(heads, Nk, 128, generator=g).to(BF).to(cuda)
+    n_floor = int((1 - sparsity) * Nk) if sparsity is not None else 0
+    idx, lens = lib.bsa_select_cdf(qc, kc, thr, n_floor)
+    assert idx.shape == (heads, Nq, Nk) and lens.shape == (heads, Nq)
+    score = torch.matmul(qc, kc.transpose(-1, -2)).float().cpu()            # bf16 x bf16 -> bf16, as cal_score does on the GPU
+    idx_c, lens_c = idx.cpu().long(), lens.cpu()
+    assert (torch.sort(idx_c, dim=-1).values == torch.arange(Nk)).all()     # a permutation of the key chunks
+    sorted_scores = torch.gather(score, -1, idx_c)
+    ulp = sorted_scores.abs() * 2 ** -7 + 1e-6
+    assert (sorted_scores[..., :-1] + ulp[..., :-1] >= sorted_scores[..., 1:]).all()     # descending up to accumulation-order noise
+    _, want = ob.select(score.unsqueeze(0), sparsity, thr, 128)
+    want = want[0]
+    assert (lens_c - want).abs().max() <= 1, (lens_c - want).abs().max()
+    assert ((lens_c - want) != 0).float().mean() < 0.1
+    assert int(lens_c.min()) >= n_floor and int(lens_c.max()) <= Nk
+
+
+def test_cdf_selection_through_the_attention(cuda):
+    """enable_bsa() with a cdf_threshold: the selected lists (variable lengths) drive the sparse kernel like the oracle's."""
+    from worldforge_b200 import lib
+    grid, chunk, heads = (8, 8, 16), (4, 4, 4), 2
+    q, k, v = _qkv(grid, grid, heads, 3, cuda)
+    qd, kd, vd = q.to(cuda), k.to(cuda), v.to(cuda)
+    q_cmp, k_cmp = lib.bsa_mean_pool(qd, grid, chunk, heads), lib.bsa_mean_pool(kd, grid, chunk, heads)
+    idx, lens = lib.bsa_select_cdf(q_cmp, k_cmp, 0.7, 2)
+    out = torch.empty_like(qd)
+    lib.attention_bsa_bf16(qd, kd, vd, out, heads, idx, lens, grid, grid, chunk)
+    want = _oracle_sparse(q, k, v, idx.cpu(), lens.cpu(), grid, grid, chunk, heads)
+    rel = ((out.cpu().float() - want.float()).norm() / want.float().norm()).item()
+    assert rel < 8e-3, rel
+    assert int(lens.min()) >= 2 and int(lens.max()) > int(lens.min())

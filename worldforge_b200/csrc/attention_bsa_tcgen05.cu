@@ -502,6 +502,109 @@ bsa_select_topk_kernel(const bf16* __restrict__ q_cmp, const bf16* __restrict__ 
   }
 }
 
+
+// get_select_indices_cdf / _cdf_topk (bsa_interface.py:234-275): per query chunk the key chunks sorted by softmax(score /
+// sqrt(128)) in descending order and the number of them whose cumulative mass stays <= cdf_threshold (torch.searchsorted,
+// right=True), optionally floored by the top-k count.  Scores are the same bf16 values as above, so sorting the 16-bit
+// keys sorts the weights; ties go to the lower chunk index.  One CTA = 8 query chunks of one head, one warp per row: a
+// bitonic sort of (key << 16 | 0xffff - index) in shared memory, then a running sum over the sorted weights.
+__device__ __forceinline__ float bf16_from_key(uint32_t key) {
+  const uint32_t b = (key & 0x8000u) ? (key & 0x7fffu) : (~key & 0xffffu);
+  return __uint_as_float(b << 16);
+}
+
+__global__ void __launch_bounds__(SEL_THREADS)
+bsa_select_cdf_kernel(const bf16* __restrict__ q_cmp, const bf16* __restrict__ k_cmp, int32_t* __restrict__ idx,
+                      int32_t* __restrict__ lens, int Nq, int Nk, int Npad, float cdf_threshold, int n_floor, float scale_log2) {
+  extern __shared__ uint8_t sel_smem[];
+  float* qs = reinterpret_cast<float*>(sel_smem);                              // [SEL_ROWS][128]
+  uint32_t* comp = reinterpret_cast<uint32_t*>(qs + SEL_ROWS * BS_D);          // [SEL_ROWS][Npad]
+  const int head = blockIdx.y, r0 = blockIdx.x * SEL_ROWS;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < SEL_ROWS * BS_D; i += SEL_THREADS) {
+    const int r = r0 + i / BS_D;
+    qs[i] = r < Nq ? __bfloat162float(q_cmp[(static_cast<size_t>(head) * Nq + r) * BS_D + (i % BS_D)]) : 0.f;
+  }
+  __syncthreads();
+  for (int n = tid; n < Npad; n += SEL_THREADS) {
+    if (n >= Nk) {
+#pragma unroll
+      for (int r = 0; r < SEL_ROWS; ++r) comp[r * Npad + n] = 0u;              // padding sorts to the end
+      continue;
+    }
+    const uint4* kr = reinterpret_cast<const uint4*>(k_cmp + (static_cast<size_t>(head) * Nk + n) * BS_D);
+    float acc[SEL_ROWS];
+#pragma unroll
+    for (int r = 0; r < SEL_ROWS; ++r) acc[r] = 0.f;
+#pragma unroll 4
+    for (int v = 0; v < BS_D / 8; ++v) {
+      const uint4 kk = __ldg(kr + v);
+      const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kk);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float2 f = __bfloat1622float2(k2[u]);
+#pragma unroll
+        for (int r = 0; r < SEL_ROWS; ++r) {
+          acc[r] = fmaf(qs[r * BS_D + v * 8 + 2 * u], f.x, acc[r]);
+          acc[r] = fmaf(qs[r * BS_D + v * 8 + 2 * u + 1], f.y, acc[r]);
+        }
+      }
+    }
+    // keys are >= 1 for every real score (bf16_key never returns 0 for a finite value: -max maps to 0x0080), padding is 0
+#pragma unroll
+    for (int r = 0; r < SEL_ROWS; ++r)
+      comp[r * Npad + n] = (bf16_key(__float2bfloat16_rn(acc[r])) << 16) | (0xffffu - static_cast<uint32_t>(n));
+  }
+  __syncthreads();
+  const int row = r0 + warp;
+  if (row >= Nq) return;
+  uint32_t* c = comp + warp * Npad;
+  // bitonic sort, descending
+  for (int k = 2; k <= Npad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < Npad; i += 32) {
+        const int l = i ^ j;
+        if (l > i) {
+          const uint32_t a = c[i], b = c[l];
+          const bool desc = (i & k) == 0;
+          if (desc ? (a < b) : (a > b)) { c[i] = b; c[l] = a; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  // softmax statistics over the row (the maximum is the first sorted element)
+  const float smax = bf16_from_key(c[0] >> 16);
+  float sum = 0.f;
+  for (int n = lane; n < Nk; n += 32) sum += exp2f((bf16_from_key(c[n] >> 16) - smax) * scale_log2);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.0f / sum;
+  int32_t* dst = idx + (static_cast<size_t>(head) * Nq + row) * Nk;
+  float carry = 0.f;
+  int count = 0;
+  bool open = true;                               // the cumulative mass has not passed the threshold yet
+  for (int n0 = 0; n0 < Nk; n0 += 32) {
+    const int n = n0 + lane;
+    const uint32_t v = n < Nk ? c[n] : 0u;
+    if (n < Nk) dst[n] = static_cast<int32_t>(0xffffu - (v & 0xffffu));
+    if (open) {
+      float w = n < Nk ? exp2f((bf16_from_key(v >> 16) - smax) * scale_log2) * inv : 0.f;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      const float cdf = carry + w;
+      const uint32_t in = __ballot_sync(0xffffffffu, n < Nk && cdf <= cdf_threshold);
+      count += __popc(in);
+      if (in != 0xffffffffu) open = false;
+      carry = __shfl_sync(0xffffffffu, cdf, 31);
+    }
+  }
+  if (lane == 0) lens[static_cast<size_t>(head) * Nq + row] = min(max(count, n_floor), Nk);
+}
+
 }  // namespace wf
 
 extern "C" int wf_bsa_mean_pool(const void* x, int ldx, void* out, int T, int H, int W, int ct, int ch, int cw, int heads,
@@ -529,6 +632,24 @@ extern "C" int wf_bsa_select_topk(const void* q_cmp, const void* k_cmp, int32_t*
   WF_CUDA_OK(cudaFuncSetAttribute(bsa_select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   bsa_select_topk_kernel<<<dim3((Nq + SEL_ROWS - 1) / SEL_ROWS, heads), SEL_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(q_cmp), static_cast<const bf16*>(k_cmp), idx, Nq, Nk, n_sel);
+  WF_LAUNCH_OK();
+  return WF_OK;
+}
+
+extern "C" int wf_bsa_select_cdf(const void* q_cmp, const void* k_cmp, int32_t* idx, int32_t* lens, int Nq, int Nk, int heads,
+                                 float cdf_threshold, int n_floor, void* stream) {
+  using namespace wf;
+  WF_REQUIRE(q_cmp && k_cmp && idx && lens, "wf_bsa_select_cdf: null pointer");
+  WF_REQUIRE(Nq > 0 && Nk > 0 && Nk < 65536 && heads > 0, "wf_bsa_select_cdf: empty problem (or more than 65535 key chunks)");
+  WF_REQUIRE(n_floor >= 0 && n_floor <= Nk, "wf_bsa_select_cdf: need 0 <= n_floor <= Nk");
+  int Npad = 32;
+  while (Npad < Nk) Npad <<= 1;
+  const size_t smem = SEL_ROWS * BS_D * 4 + static_cast<size_t>(SEL_ROWS) * Npad * 4;
+  WF_REQUIRE(smem <= 200 * 1024, "wf_bsa_select_cdf: too many key chunks for the shared-memory sort");
+  WF_CUDA_OK(cudaFuncSetAttribute(bsa_select_cdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  bsa_select_cdf_kernel<<<dim3((Nq + SEL_ROWS - 1) / SEL_ROWS, heads), SEL_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(q_cmp), static_cast<const bf16*>(k_cmp), idx, lens, Nq, Nk, Npad, cdf_threshold, n_floor,
+      1.4426950408889634f / sqrtf(static_cast<float>(BS_D)));
   WF_LAUNCH_OK();
   return WF_OK;
 }

@@ -62,6 +62,7 @@ _SIGNATURES = {
     "wf_attention_bf16": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _f, _vp],
     "wf_bsa_mean_pool": [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "wf_bsa_select_topk": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "wf_bsa_select_cdf": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp],
     "wf_attention_bsa_bf16": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp],
     "wf_layer_norm": [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _vp],
     "wf_rms_norm_rope": [_vp, _i, _vp, _vp, _i, _i, _f, _vp],
@@ -223,6 +224,17 @@ def bsa_select_topk(q_cmp, k_cmp, n_sel: int):
     idx = torch.empty(heads, Nq, n_sel, dtype=torch.int32, device=q_cmp.device)
     _call("wf_bsa_select_topk", _p(q_cmp), _p(k_cmp), _p(idx), Nq, k_cmp.shape[1], heads, n_sel, _stream())
     return idx
+
+
+def bsa_select_cdf(q_cmp, k_cmp, cdf_threshold: float, n_floor: int = 0):
+    """[heads, Nq, 128], [heads, Nk, 128] bf16 -> (int32 [heads, Nq, Nk] sorted by weight, int32 [heads, Nq] selected counts)."""
+    assert q_cmp.is_contiguous() and k_cmp.is_contiguous() and q_cmp.dtype == k_cmp.dtype == torch.bfloat16
+    heads, Nq, _ = q_cmp.shape
+    Nk = k_cmp.shape[1]
+    idx = torch.empty(heads, Nq, Nk, dtype=torch.int32, device=q_cmp.device)
+    lens = torch.empty(heads, Nq, dtype=torch.int32, device=q_cmp.device)
+    _call("wf_bsa_select_cdf", _p(q_cmp), _p(k_cmp), _p(idx), _p(lens), Nq, Nk, heads, float(cdf_threshold), int(n_floor), _stream())
+    return idx, lens
 
 
 def attention_bsa_bf16(q, k, v, out, heads: int, block_idx, block_lens, grid_q, grid_k, chunk,

@@ -195,8 +195,8 @@ class WfLongCatTransformer:
     def enable_bsa(self):
         if self.bsa_params is None:
             raise lib.WfError("enable_bsa(): no bsa_params (set .bsa_params to the checkpoint's dict first)")
-        if self.bsa_params.get("cdf_threshold") is not None:
-            raise lib.WfError("BSA selection by cdf_threshold is not implemented on the device (top-k sparsity only)")
+        if self.bsa_params.get("sparsity", 0.875) is None and self.bsa_params.get("cdf_threshold") is None:
+            raise lib.WfError("enable_bsa(): bsa_params needs a sparsity and / or a cdf_threshold (bsa_interface.py:261-270)")
         self._bsa_on = True
 
     def disable_bsa(self):
@@ -213,7 +213,11 @@ class WfLongCatTransformer:
             raise lib.WfError("BSA with different query / key chunk shapes is not implemented")
         q_cmp = lib.bsa_mean_pool(q, grid_q, chunk, Hn)
         k_cmp = lib.bsa_mean_pool(k, grid_k, chunk, Hn)
-        n_sel = int((1 - bp.get("sparsity", 0.875)) * k_cmp.shape[1])           # bsa_interface.py:223
+        sparsity, cdf = bp.get("sparsity", 0.875), bp.get("cdf_threshold")      # flash_attn_bsa_3d's defaults (bsa_interface.py:619)
+        n_sel = int((1 - sparsity) * k_cmp.shape[1]) if sparsity is not None else 0   # :223
+        if cdf is not None:                                                    # softmax-mass rule, floored by the top-k count (:234-275)
+            idx, lens = lib.bsa_select_cdf(q_cmp, k_cmp, cdf, n_sel)
+            return lib.attention_bsa_bf16(q, k, v, out, Hn, idx, lens, grid_q, grid_k, chunk)
         if n_sel < 1:
             out.zero_()                                                        # nothing selected: the kernel's acc = 0, l = 1
             return out
