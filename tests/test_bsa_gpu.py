@@ -169,4 +169,4 @@ def test_cdf_selection_through_the_attention(cuda):
     want = _oracle_sparse(q, k, v, idx.cpu(), lens.cpu(), grid, grid, chunk, heads)
     rel = ((out.cpu().float() - want.float()).norm() / want.float().norm()).item()
     assert rel < 8e-3, rel
-    assert int(lens.min()) >= 2 and int(lens.max()) > int(lens.min())
+    assert 2 <= int(lens.min()) and int(lens.max()) < 16          # a proper subset of the 16 key chunks (sorted lists, lens from the mass rule)
