@@ -76,13 +76,25 @@ class OracleLongCatDit:
         self.cp_split_hw = [1, 1]
         self.calls = 0
 
-    def __call__(self, hidden_states, timestep, encoder_hidden_states, encoder_attention_mask=None, num_cond_latents=0, **kw):
-        outs = []
+    def __call__(self, hidden_states, timestep, encoder_hidden_states, encoder_attention_mask=None, num_cond_latents=0,
+                 return_kv=False, kv_cache_dict=None, skip_crs_attn=False, **kw):
+        outs, caches = [], []
         for s in range(hidden_states.shape[0]):
             ctx = encoder_hidden_states[s, 0]
-            if encoder_attention_mask is not None:
+            if encoder_attention_mask is not None and not skip_crs_attn:
                 ctx = ctx[encoder_attention_mask[s].reshape(-1) != 0]
             self.calls += 1
-            outs.append(self._ld.dit_forward(self.P, self.cfg, hidden_states[s].cpu(), timestep[s].cpu(), ctx.cpu(),
-                                             num_cond_latents=num_cond_latents, amp=self.amp, bsa=self.bsa))
-        return torch.stack(outs).to(hidden_states.device)
+            cache_s = None
+            if kv_cache_dict:                                   # [B, N, H, D] per layer; batch 1 is shared (attention.py:163-166)
+                cache_s = {i: (kv[0][min(s, kv[0].shape[0] - 1)], kv[1][min(s, kv[1].shape[0] - 1)]) for i, kv in kv_cache_dict.items()}
+            r = self._ld.dit_forward(self.P, self.cfg, hidden_states[s].cpu(), timestep[s].cpu(), ctx.cpu(),
+                                     num_cond_latents=num_cond_latents, amp=self.amp, bsa=self.bsa, return_kv=return_kv,
+                                     kv_cache_dict=cache_s, skip_crs_attn=skip_crs_attn)
+            if return_kv:
+                outs.append(r[0]); caches.append(r[1])
+            else:
+                outs.append(r)
+        out = torch.stack(outs).to(hidden_states.device)
+        if not return_kv:
+            return out
+        return out, {i: (torch.stack([c[i][0] for c in caches]), torch.stack([c[i][1] for c in caches])) for i in caches[0]}

@@ -172,9 +172,13 @@ def bsa_attention(q, k, v, grid_q, grid_k, bsa):
     return o[0].permute(1, 0, 2)
 
 
-def block_forward(P, cfg: LongCatConfig, i, x, y, t, grid, num_cond, amp, bsa=None):
+def block_forward(P, cfg: LongCatConfig, i, x, y, t, grid, num_cond, amp, bsa=None, return_kv=False, kv_cache=None, skip_crs=False):
     """x [N, C] (one sample), y [M, C] valid text tokens, t [T, A] fp32.  ``bsa``: the checkpoint's bsa_params dict when
-    the block-sparse self-attention of the refine pass is enabled (Attention.enable_bsa, attention.py:56), else None."""
+    the block-sparse self-attention of the refine pass is enabled (Attention.enable_bsa, attention.py:56), else None.
+    ``return_kv``: also return (k, v) [N,H,D] after the q/k norm and BEFORE RoPE (attention.py:119-120); ``kv_cache``: such a
+    pair from the clean condition frames - the video-continuation path Attention.forward_with_kv_cache (:149-181): x holds
+    the noise frames only, keys/values are [cache | own] and RoPE runs over T + num_cond frames; cross-attention then sees
+    every token (longcat_video_dit.py:105-108).  ``skip_crs``: no cross-attention (the caching pass, :104)."""
     b = f"blocks.{i}."
     C, Hn, D = cfg.hidden_size, cfg.num_heads, cfg.head_dim
     T = grid[0]
@@ -193,10 +197,23 @@ def block_forward(P, cfg: LongCatConfig, i, x, y, t, grid, num_cond, amp, bsa=No
     qkv = lin(xm, P[b + "attn.qkv.weight"], P[b + "attn.qkv.bias"], amp).view(N, 3, Hn, D)
     q, k, v = qkv[:, 0], qkv[:, 1], qkv[:, 2]
     q, k = rms_head(q, P[b + "attn.q_norm.weight"], amp), rms_head(k, P[b + "attn.k_norm.weight"], amp)
-    fr = rope_freqs(D, grid)
-    q, k = rope_apply(q, fr), rope_apply(k, fr)
+    kv_out = (k.clone(), v.clone()) if return_kv else None
+    if kv_cache is not None:
+        k_c, v_c = kv_cache
+        k = torch.cat([k_c.to(k.dtype), k], dim=0)
+        v = torch.cat([v_c.to(v.dtype), v], dim=0)
+        fr = rope_freqs(D, (T + num_cond, grid[1], grid[2]))
+        q, k = rope_apply(q, fr[-N:]), rope_apply(k, fr)
+        grid_k = (T + num_cond, grid[1], grid[2])
+        a = bsa_attention(q, k, v, grid, grid_k, bsa) if (bsa is not None and T > 1) else attention(q, k, v, amp)
+        num_cond = 0                                                  # from here on every token of x is a noise token
+    else:
+        fr = rope_freqs(D, grid)
+        q, k = rope_apply(q, fr), rope_apply(k, fr)
     nc = num_cond * per
-    if bsa is not None and T > 1:                                   # "bsa will not be used in image training / sampling"
+    if kv_cache is not None:
+        pass
+    elif bsa is not None and T > 1:                                   # "bsa will not be used in image training / sampling"
         gH, gW = grid[1], grid[2]
         if nc > 0:
             a = torch.cat([bsa_attention(q[:nc], k[:nc], v[:nc], (num_cond, gH, gW), (num_cond, gH, gW), bsa),
@@ -211,6 +228,8 @@ def block_forward(P, cfg: LongCatConfig, i, x, y, t, grid, num_cond, amp, bsa=No
     x = (x + (g_a * xs.view(T, per, C)).view(N, C)).to(x_dtype)
 
     # cross attention: noise tokens only; condition tokens receive zero (attention.py:262-273)
+    if skip_crs:
+        return _ffn(P, b, x, T, per, C, sh_m, sc_m, g_m, amp, x_dtype, kv_out)
     xn = F.layer_norm(x.float(), (C,), P[b + "pre_crs_attn_norm.weight"].float() if not amp else _rb(P[b + "pre_crs_attn_norm.weight"]),
                       P[b + "pre_crs_attn_norm.bias"].float() if not amp else _rb(P[b + "pre_crs_attn_norm.bias"]), 1e-6).to(x_dtype)
     qc = lin(xn[nc:], P[b + "cross_attn.q_linear.weight"], P[b + "cross_attn.q_linear.bias"], amp).view(-1, Hn, D)
@@ -220,16 +239,24 @@ def block_forward(P, cfg: LongCatConfig, i, x, y, t, grid, num_cond, amp, bsa=No
     oc = lin(attention(qc, kc, vc, amp).reshape(-1, C), P[b + "cross_attn.proj.weight"], P[b + "cross_attn.proj.bias"], amp)
     x = torch.cat([x[:nc], x[nc:] + oc], dim=0)
 
-    # SwiGLU feed-forward
-    xm = modulate(x, sh_m, sc_m)
+    return _ffn(P, b, x, T, per, C, sh_m, sc_m, g_m, amp, x_dtype, kv_out)
+
+
+def _ffn(P, b, x, T, per, C, sh_m, sc_m, g_m, amp, x_dtype, kv_out):
+    """SwiGLU feed-forward with modulation (longcat_video_dit.py:110-115)."""
+    N = x.shape[0]
+    n = F.layer_norm(x.view(T, per, C).float(), (C,), None, None, 1e-6)
+    xm = (n * (sc_m + 1) + sh_m).to(x.dtype).view(N, C)
     h = F.silu(lin(xm, P[b + "ffn.w1.weight"], None, amp)) * lin(xm, P[b + "ffn.w3.weight"], None, amp)
     xs = lin(h, P[b + "ffn.w2.weight"], None, amp)
     x = (x + (g_m * xs.view(T, per, C)).view(N, C)).to(x_dtype)
-    return x
+    return x if kv_out is None else (x, kv_out)
 
 
-def dit_forward(P, cfg: LongCatConfig, x, timestep, context, num_cond_latents: int = 1, amp: bool = True, bsa=None):
-    """LongCatVideoTransformer3DModel.forward for one sample.
+def dit_forward(P, cfg: LongCatConfig, x, timestep, context, num_cond_latents: int = 1, amp: bool = True, bsa=None,
+                return_kv: bool = False, kv_cache_dict=None, skip_crs_attn: bool = False):
+    """LongCatVideoTransformer3DModel.forward for one sample (``return_kv`` / ``kv_cache_dict`` / ``skip_crs_attn``:
+    longcat_video_dit.py:285-287, 339-356 - the video-continuation path; returns (out, {layer: (k, v)}) with return_kv).
 
     x [C_in, T, H, W]; timestep [T] (per latent frame, the condition frames at 0, pipeline_longcat_video.py:864-865);
     context [M, caption_channels] = the valid text tokens.  Returns fp32 [C_out, T, H, W]."""
@@ -246,8 +273,14 @@ def dit_forward(P, cfg: LongCatConfig, x, timestep, context, num_cond_latents: i
                         P["t_embedder.mlp.2.weight"], P["t_embedder.mlp.2.bias"], amp)          # [T, A] fp32
     y = lin(F.gelu(lin(context.to(dt), P["y_embedder.y_proj.0.weight"], P["y_embedder.y_proj.0.bias"], amp), approximate="tanh"),
             P["y_embedder.y_proj.2.weight"], P["y_embedder.y_proj.2.bias"], amp)
+    kv_ret = {}
     for i in range(cfg.depth):
-        tok = block_forward(P, cfg, i, tok, y, t, grid, num_cond_latents, amp, bsa)
+        r = block_forward(P, cfg, i, tok, y, t, grid, num_cond_latents, amp, bsa, return_kv=return_kv,
+                          kv_cache=None if not kv_cache_dict else kv_cache_dict.get(i), skip_crs=skip_crs_attn)
+        if return_kv:
+            tok, kv_ret[i] = r
+        else:
+            tok = r
     mod = lin_fp32_island(F.silu(t), P["final_layer.adaLN_modulation.1.weight"], P["final_layer.adaLN_modulation.1.bias"], amp)
     shift, scale = [m.unsqueeze(1) for m in mod.chunk(2, dim=-1)]
     per = N // T
@@ -256,4 +289,5 @@ def dit_forward(P, cfg: LongCatConfig, x, timestep, context, num_cond_latents: i
     out = lin_fp32_island(h, P["final_layer.linear.weight"], P["final_layer.linear.bias"], amp)   # fp32 [N, pt*ph*pw*Cout]
     c = cfg.out_channels
     u = out.view(grid[0], grid[1], grid[2], pt, ph, pw, c).permute(6, 0, 3, 1, 4, 2, 5)
-    return u.reshape(c, grid[0] * pt, grid[1] * ph, grid[2] * pw).to(F32)
+    out = u.reshape(c, grid[0] * pt, grid[1] * ph, grid[2] * pw).to(F32)
+    return (out, kv_ret) if return_kv else out

@@ -351,3 +351,55 @@ def refine_loop(dit, scheduler, latents, prompt_embeds, prompt_attention_mask, n
         if on_step is not None:
             on_step(i, latents)
     return latents
+
+
+def vc_timesteps(scheduler, num_inference_steps: int, use_distill: bool = False, enhance_hf: bool = True, device=None):
+    """generate_vc steps 4 (pipeline_longcat_video.py:1151-1164): the i2v schedule, with enhance_hf its tail below t = 500
+    replaced by 10 uniform steps 500 -> 50 and the sigmas rebuilt as timesteps / 1000 (+ a final 0)."""
+    import numpy as np
+    assert not (use_distill and enhance_hf)
+    scheduler.set_timesteps(num_inference_steps, sigmas=timesteps_sigmas(num_inference_steps, use_distill), device=device)
+    timesteps = scheduler.timesteps
+    if enhance_hf:
+        tail = list(np.linspace(500, 0, 10, dtype=np.float32, endpoint=False))
+        tail = [torch.tensor(t, device=device).unsqueeze(0) for t in tail]
+        head = [t.unsqueeze(0) for t in timesteps if t > 500]
+        timesteps = torch.cat(head + tail)
+        scheduler.timesteps = timesteps
+        scheduler.sigmas = torch.cat([timesteps / 1000, torch.zeros(1, device=timesteps.device)])
+    return timesteps
+
+
+def vc_loop(dit, scheduler, latents, prompt_embeds, prompt_attention_mask, num_cond_latents: int, timesteps,
+            guidance_scale: float = 4.0, use_kv_cache: bool = True, do_cfg: bool = True, dit_dtype=torch.bfloat16, on_step=None):
+    """generate_vc's loop (:1192-1250): the clean condition frames either go through the DiT once (no cross-attention) to
+    fill the KV cache and only the noise frames are denoised against it, or ride along at timestep 0; CFG-zero, sign flip,
+    plain Euler steps.  ``prompt_embeds`` is the [negative, positive] batch with CFG.  Returns the full latents."""
+    kv = {}
+    cond = None
+    if use_kv_cache:
+        cond = latents[:, :, :num_cond_latents]
+        ts0 = torch.zeros(cond.shape[0], cond.shape[2]).to(device=latents.device, dtype=dit_dtype)
+        empty = torch.zeros([cond.shape[0], 1, prompt_embeds.shape[2], prompt_embeds.shape[3]], device=latents.device, dtype=dit_dtype)
+        _, kv = dit(hidden_states=cond.to(dit_dtype), timestep=ts0, encoder_hidden_states=empty, return_kv=True, skip_crs_attn=True)
+        latents = latents[:, :, num_cond_latents:]
+    for i, t in enumerate(timesteps):
+        x = (torch.cat([latents] * 2) if do_cfg else latents).to(dit_dtype)
+        ts = t.expand(x.shape[0]).to(dit_dtype).unsqueeze(-1).repeat(1, x.shape[2])
+        if not use_kv_cache:
+            ts[:, :num_cond_latents] = 0
+        pred = dit(hidden_states=x, timestep=ts, encoder_hidden_states=prompt_embeds, encoder_attention_mask=prompt_attention_mask,
+                   num_cond_latents=num_cond_latents, kv_cache_dict=kv)
+        if do_cfg:
+            pred = cfg_zero(pred, guidance_scale)
+        pred = -pred
+        if use_kv_cache:
+            latents = scheduler.step(pred, t, latents, return_dict=False)[0]
+        else:
+            latents[:, :, num_cond_latents:] = scheduler.step(pred[:, :, num_cond_latents:], t, latents[:, :, num_cond_latents:],
+                                                              return_dict=False)[0]
+        if on_step is not None:
+            on_step(i, latents)
+    if use_kv_cache:
+        latents = torch.cat([cond, latents], dim=2)
+    return latents

@@ -326,12 +326,46 @@ class WfLongCatTransformer:
         return kvs
 
     @torch.no_grad()
-    def __call__(self, hidden_states, timestep, encoder_hidden_states, encoder_attention_mask=None, num_cond_latents: int = 0, **kw):
+    def __call__(self, hidden_states, timestep, encoder_hidden_states, encoder_attention_mask=None, num_cond_latents: int = 0,
+                 return_kv: bool = False, kv_cache_dict=None, skip_crs_attn: bool = False, offload_kv_cache: bool = False, **kw):
+        """``return_kv`` / ``kv_cache_dict`` / ``skip_crs_attn`` / ``offload_kv_cache``: the video-continuation surface of the
+        reference forward (longcat_video_dit.py:280-370; pipeline_longcat_video.py:336-350, 1196-1209).  With return_kv the
+        call returns (out, {layer: (k, v)}): per layer the self-attention keys / values of the given (clean condition) frames,
+        bf16 [B, tokens, C] - an opaque cache for THIS engine: keys are held before the q/k norm and RoPE (the reference caches
+        them after the norm; the fused norm+RoPE kernel re-applies both over [cache | own] when the cache is used, which is
+        the same arithmetic).  With a kv_cache_dict, hidden_states holds the noise frames only and num_cond_latents is the
+        number of cached frames."""
         if not hidden_states.is_cuda:
             raise lib.WfError("WfLongCatTransformer runs on CUDA tensors only (no CPU fallback)")
         B = hidden_states.shape[0]
         if timestep.dim() == 1:
             timestep = timestep.unsqueeze(1).expand(-1, hidden_states.shape[2])
+        if return_kv or kv_cache_dict:
+            outs, caches = [], []
+            for s in range(B):
+                ctx = encoder_hidden_states[s, 0]
+                if encoder_attention_mask is not None and not skip_crs_attn:
+                    m = encoder_attention_mask[s].reshape(-1) != 0
+                    ctx = ctx[m] if not bool(m[:int(m.sum())].all()) else ctx[:int(m.sum())]
+                cache_s = None
+                if kv_cache_dict:
+                    cache_s = {i: (kv[0][min(s, kv[0].shape[0] - 1)].to(self.device), kv[1][min(s, kv[1].shape[0] - 1)].to(self.device))
+                               for i, kv in kv_cache_dict.items()}
+                r = self._forward_one(hidden_states[s], timestep[s], ctx, 0 if kv_cache_dict else num_cond_latents,
+                                      return_kv=return_kv, kv_cache=cache_s, cached_frames=num_cond_latents if kv_cache_dict else 0,
+                                      skip_crs=skip_crs_attn)
+                if return_kv:
+                    outs.append(r[0]); caches.append(r[1])
+                else:
+                    outs.append(r)
+            out = torch.stack(outs)
+            if not return_kv:
+                return out
+            ret = {}
+            for i in caches[0]:
+                k = torch.stack([c[i][0] for c in caches]); v = torch.stack([c[i][1] for c in caches])
+                ret[i] = (k.cpu(), v.cpu()) if offload_kv_cache else (k, v)
+            return out, ret
         outs = []
         for s in range(B):
             ctx = encoder_hidden_states[s, 0]
@@ -345,7 +379,7 @@ class WfLongCatTransformer:
             outs.append(self._forward_one(hidden_states[s], timestep[s], ctx, num_cond_latents))
         return torch.stack(outs)
 
-    def _forward_one(self, x, timestep, ctx, num_cond):
+    def _forward_one(self, x, timestep, ctx, num_cond, return_kv=False, kv_cache=None, cached_frames=0, skip_crs=False):
         c = self.cfg
         self.calls += 1
         C, Hn, Fd = c.hidden_size, c.num_heads, c.ffn_dim
@@ -357,9 +391,16 @@ class WfLongCatTransformer:
         nc = num_cond * per
         Nn = N - nc
         Bf = self._buffers(N, Nn, T)
-        if grid not in self._rope:
-            self._rope[grid] = rope_table(grid).to(self.device)
-        rope = self._rope[grid]
+        rgrid = (T + cached_frames, grid[1], grid[2])           # RoPE runs over [cached | own] frames (attention.py:171)
+        if rgrid not in self._rope:
+            self._rope[rgrid] = rope_table(rgrid).to(self.device)
+        Nc = cached_frames * per                                # cached condition tokens in front of this call's tokens
+        rope_all = self._rope[rgrid]
+        rope = rope_all[Nc:]
+        kv_ret = {}
+        if kv_cache is not None:
+            kfull = torch.empty(Nc + N, C, dtype=BF, device=self.device)
+            vfull = torch.empty(Nc + N, C, dtype=BF, device=self.device)
 
         lib.patchify(xb, Bf.cols)
         lib.gemm_bf16(Bf.cols, self.patch_w, self.patch_b, Bf.x, lib.EPI_BF16)
@@ -370,32 +411,42 @@ class WfLongCatTransformer:
         lib.small_gemm_f32(Bf.t1, self.t2_w, self.t2_b, Bf.t, silu_in=True)
         lib.small_gemm_f32(Bf.t, self.ada_w, self.ada_b, Bf.mod, silu_in=True)
         mod = Bf.mod.view(T, 6 * c.depth + 2, C).permute(1, 0, 2).contiguous()      # [table, T, C]: each table contiguous
-        kvs = self._context(ctx)
+        kvs = None if skip_crs else self._context(ctx)
 
         for i, b in enumerate(self.blocks):
             # [T, C] tables of this block: shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp (chunk order, :83-85)
             tab = [mod[6 * i + j] for j in range(6)]
             lib.layer_norm(Bf.x, Bf.h, 1e-6, scale=tab[1], shift=tab[0], rows_per_group=per)
             lib.gemm_bf16(Bf.h, b.qkv_w, b.qkv_b, Bf.qkv, lib.EPI_BF16)
+            if return_kv:                                   # before the in-place norm + RoPE (see __call__)
+                kv_ret[i] = (Bf.qkv[:, C:2 * C].clone(), Bf.qkv[:, 2 * C:].clone())
             lib.rms_norm_head_rope_(Bf.qkv[:, :C], b.qn, 1e-6, rope)
-            lib.rms_norm_head_rope_(Bf.qkv[:, C:2 * C], b.kn, 1e-6, rope)
+            if kv_cache is not None:                        # forward_with_kv_cache (attention.py:149-181)
+                kfull[:Nc].copy_(kv_cache[i][0]); kfull[Nc:].copy_(Bf.qkv[:, C:2 * C])
+                vfull[:Nc].copy_(kv_cache[i][1]); vfull[Nc:].copy_(Bf.qkv[:, 2 * C:])
+                lib.rms_norm_head_rope_(kfull, b.kn, 1e-6, rope_all)
+            else:
+                lib.rms_norm_head_rope_(Bf.qkv[:, C:2 * C], b.kn, 1e-6, rope)
             q, k, v = Bf.qkv[:, :C], Bf.qkv[:, C:2 * C], Bf.qkv[:, 2 * C:]
             # in the reference BSA is skipped for single-frame inputs as a whole (shape[0] > 1, attention.py:56)
             sparse = self._bsa_on and T > 1
             gq = lambda t: (t, grid[1], grid[2])
-            if nc > 0:      # condition tokens see only condition tokens; noise tokens see everything (attention.py:124-135)
+            if kv_cache is not None:
+                self._self_attention(q, kfull, vfull, Bf.att, gq(T), gq(T + cached_frames), sparse)
+            elif nc > 0:      # condition tokens see only condition tokens; noise tokens see everything (attention.py:124-135)
                 self._self_attention(q[:nc], k[:nc], v[:nc], Bf.att[:nc], gq(num_cond), gq(num_cond), sparse)
                 self._self_attention(q[nc:], k, v, Bf.att[nc:], gq(T - num_cond), gq(T), sparse)
             else:
                 self._self_attention(q, k, v, Bf.att, gq(T), gq(T), sparse)
             lib.gemm_bf16(Bf.att, b.proj_w, b.proj_b, Bf.x, lib.EPI_RESID_BF16, gate=tab[2], gate_rows=per)
             # cross attention, noise tokens only
-            lib.layer_norm(Bf.x, Bf.h, 1e-6, weight=b.n_w, bias=b.n_b)
-            lib.gemm_bf16(Bf.h[nc:], b.cq_w, b.cq_b, Bf.cq, lib.EPI_BF16)
-            lib.rms_norm_head_rope_(Bf.cq, b.cqn, 1e-6, None)
-            kv = kvs[i]
-            lib.attention_bf16(Bf.cq, kv[:, :C], kv[:, C:], Bf.ca, Hn)
-            lib.gemm_bf16(Bf.ca, b.cproj_w, b.cproj_b, Bf.x[nc:], lib.EPI_RESID_BF16)
+            if not skip_crs:
+                lib.layer_norm(Bf.x, Bf.h, 1e-6, weight=b.n_w, bias=b.n_b)
+                lib.gemm_bf16(Bf.h[nc:], b.cq_w, b.cq_b, Bf.cq, lib.EPI_BF16)
+                lib.rms_norm_head_rope_(Bf.cq, b.cqn, 1e-6, None)
+                kv = kvs[i]
+                lib.attention_bf16(Bf.cq, kv[:, :C], kv[:, C:], Bf.ca, Hn)
+                lib.gemm_bf16(Bf.ca, b.cproj_w, b.cproj_b, Bf.x[nc:], lib.EPI_RESID_BF16)
             # SwiGLU feed-forward
             lib.layer_norm(Bf.x, Bf.h, 1e-6, scale=tab[4], shift=tab[3], rows_per_group=per)
             lib.gemm_bf16(Bf.h, b.w13, None, Bf.h13, lib.EPI_BF16)
@@ -405,4 +456,4 @@ class WfLongCatTransformer:
         shift, scale = mod[6 * c.depth], mod[6 * c.depth + 1]
         out = torch.empty(c.out_channels, T, H, W, dtype=F32, device=self.device)
         lib.dit_head(Bf.x, scale, shift, self.final_w, self.final_b, out, grid, 1e-6, rows_per_group=per, round_bf16=True)
-        return out
+        return (out, kv_ret) if return_kv else out

@@ -372,3 +372,56 @@ def refine_loop(dit, scheduler, latents, prompt_embeds, prompt_attention_mask, n
         if on_step is not None:
             on_step(i, latents)
     return latents
+
+
+# ------------------------------------------------------------------------------------ video continuation (KV cache)
+def vc_timesteps(scheduler, num_inference_steps: int, use_distill: bool = False, enhance_hf: bool = True, device=None):
+    """generate_vc step 4 (pipeline_longcat_video.py:1151-1164): the i2v schedule; with ``enhance_hf`` its part below t = 500
+    is replaced by 10 uniform steps 500 -> 50 and the sigmas are rebuilt as timesteps / 1000 plus a final 0."""
+    if use_distill and enhance_hf:
+        raise ValueError("use_distill and enhance_hf cannot both be True")
+    scheduler.set_timesteps(num_inference_steps, sigmas=timesteps_sigmas(num_inference_steps, use_distill), device=device)
+    timesteps = scheduler.timesteps
+    if enhance_hf:
+        tail = [torch.tensor(t, device=device).unsqueeze(0) for t in np.linspace(500, 0, 10, dtype=np.float32, endpoint=False)]
+        head = [t.unsqueeze(0) for t in timesteps if t > 500]
+        timesteps = torch.cat(head + tail)
+        scheduler.timesteps = timesteps
+        scheduler.sigmas = torch.cat([timesteps / 1000, torch.zeros(1, device=timesteps.device)])
+    return timesteps
+
+
+def vc_loop(dit, scheduler, latents, prompt_embeds, prompt_attention_mask, num_cond_latents: int, timesteps,
+            guidance_scale: float = 4.0, use_kv_cache: bool = True, offload_kv_cache: bool = False, do_cfg: bool = True, on_step=None):
+    """The denoising loop of generate_vc (pipeline_longcat_video.py:1192-1250, LongCat's long-video continuation): the
+    clean latents of the condition frames go through the DiT once, without cross-attention, to fill every layer's K/V cache
+    (_cache_clean_latents, :336-350); each step then runs the noise frames alone against [cache | own] keys.  Without the
+    cache the condition frames ride along at timestep 0.  CFG-zero + sign flip (``wf_cfg_zero``), plain Euler steps.
+    latents [1,16,T,h,w] fp32 on the device with the clean condition latents in front; returns the full latents."""
+    device, dit_dtype = latents.device, dit.dtype
+    kv, cond = {}, None
+    if use_kv_cache:
+        cond = latents[:, :, :num_cond_latents]
+        ts0 = torch.zeros(cond.shape[0], cond.shape[2], device=device, dtype=dit_dtype)
+        empty = torch.zeros([cond.shape[0], 1, prompt_embeds.shape[2], prompt_embeds.shape[3]], device=device, dtype=dit_dtype)
+        _, kv = dit(hidden_states=cond.to(dit_dtype), timestep=ts0, encoder_hidden_states=empty, return_kv=True, skip_crs_attn=True,
+                    offload_kv_cache=offload_kv_cache)
+        latents = latents[:, :, num_cond_latents:].contiguous()
+    for i, t in enumerate(timesteps):
+        x = (torch.cat([latents] * 2) if do_cfg else latents).to(dit_dtype)
+        ts = t.expand(x.shape[0]).to(device=device, dtype=dit_dtype).unsqueeze(-1).repeat(1, x.shape[2])
+        if not use_kv_cache:
+            ts[:, :num_cond_latents] = 0
+        pred = dit(hidden_states=x, timestep=ts, encoder_hidden_states=prompt_embeds, encoder_attention_mask=prompt_attention_mask,
+                   num_cond_latents=num_cond_latents, kv_cache_dict=kv)
+        pred = lib.cfg_zero(pred[1:2].contiguous(), pred[0:1].contiguous(), guidance_scale) if do_cfg else -pred   # sign flip included
+        if use_kv_cache:
+            latents = scheduler.step(pred, t, latents, return_dict=False)[0]
+        else:
+            latents[:, :, num_cond_latents:] = scheduler.step(pred[:, :, num_cond_latents:], t, latents[:, :, num_cond_latents:],
+                                                              return_dict=False)[0]
+        if on_step is not None:
+            on_step(i, latents)
+    if use_kv_cache:
+        latents = torch.cat([cond, latents], dim=2)
+    return latents
