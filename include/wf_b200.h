@@ -202,6 +202,17 @@ int wf_flf_blend(const float* decoded, const float* ref, const float* mask, floa
 int wf_soften_mask(const float* mask, float* out, int frames, int H, int W, int radius, int max_d2, const float* lut,
                    void* stream);
 int wf_clip_from_u8(const unsigned char* frames, float* out, long long pixels, void* stream);
+/* Encoders (once per video).
+ * wf_attention_small_bf16: attention over <= 1024 keys, head_dim 64 (UMT5-XXL, wan/modules/t5.py:86-116) or 80 (CLIP ViT-H/14,
+ * wan/modules/clip.py:74-86); q/k/v/out bf16 [tokens][heads*head_dim] views.  mode 0 = the rounding points of T5Attention's
+ * bf16 einsum form (scores and score + bias rounded to bf16, keys >= Lk_valid at finfo.min, fp32 softmax, bf16 probabilities,
+ * no scale) with bias_emb bf16 [buckets][heads] and bias_bucket int32 [2*Lk-1] (bucket of relative distance d = j - i at
+ * index d + Lk - 1; both NULL for no bias); mode 1 = flash-attention rounding (fp32 scores * scale).
+ * wf_geglu_bf16: h bf16 [rows][2F] = [gate | fc1] -> out [rows][F] = fc1 * GELU_tanh(gate), bf16 intermediates (t5.py:48-50,136). */
+int wf_attention_small_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
+                            const void* bias_emb, const int* bias_bucket, int Lq, int Lk, int Lk_valid, int heads, int head_dim,
+                            float scale, int mode, void* stream);
+int wf_geglu_bf16(const void* h, void* out, long long rows, int F, void* stream);
 /* LongCat generate_refine step 5 (longcat_video/pipeline_longcat_video.py:1393-1419): stage-1 video uint8 [F,H0,W0,3]
  * -> bilinear (align_corners) to [H,W] -> /255 -> trilinear to F2 frames -> *2-1, bf16 intermediates as in the reference,
  * first / last frame repeated pad_front / pad_back times.  out: planar fp32 [3][pad_front+F2+pad_back][H][W]. */

@@ -167,6 +167,25 @@ def load_wan_model_module(cpu_autocast: bool = False):
     return model
 
 
+def load_wan_encoder_modules():
+    """(wan.modules.t5, wan.modules.clip) of the reference - the UMT5 text encoder and the CLIP ViT image encoder - with the
+    tokenizer's ``ftfy`` dependency stubbed (not installed; tokenisation is not on the path) and flash_attention replaced for
+    the CPU."""
+    load_wan_model_module()
+    if "ftfy" not in sys.modules:
+        f = types.ModuleType("ftfy"); f.fix_text = lambda t: t
+        sys.modules["ftfy"] = f
+    cur = torch.cuda.current_device                 # t5.py:478 evaluates it in a default argument at import time
+    torch.cuda.current_device = lambda: 0
+    try:
+        t5 = importlib.import_module("wan.modules.t5")
+        clip = importlib.import_module("wan.modules.clip")
+    finally:
+        torch.cuda.current_device = cur
+    clip.flash_attention = _sdpa_flash_attention
+    return t5, clip
+
+
 def load_wan_vae_module():
     assert available()
     _add_path()

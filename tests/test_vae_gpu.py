@@ -101,13 +101,15 @@ def test_vae_rejects_cpu(cuda):
         m.decode(torch.zeros(1, 16, 1, 4, 4))
 
 
+@pytest.mark.parametrize("cuts", [True, False])
 @pytest.mark.parametrize("world,F_,H,W", [(2, 5, 64, 48), (4, 9, 96, 32), (8, 5, 128, 32), (3, 1, 48, 32), (8, 33, 64, 32)])
-def test_row_sharded_vae_is_bit_identical(cuda, world, F_, H, W):
+def test_row_sharded_vae_is_bit_identical(cuda, world, F_, H, W, cuts):
     """enable_row_sharding: the stages of the sharded evaluation (row slabs with recomputed halo; the mid-block attention
     by frames), every rank's share stitched in rank order between stages, equal the single-GPU evaluation bit for bit -
     simulated here by running the ranks one after the other on one GPU (tools/ulysses_check.py does it with real ranks)."""
     from worldforge_b200 import vae as wvae
     m = wvae.WfWanVAE.random_init(cuda, dim=8, seed=3)
+    m.level_cuts = cuts                                             # default True: one row stage per resolution level
     video = (torch.rand(1, 3, F_, H, W, generator=g(21)) * 2 - 1).to(cuda)
     z = torch.randn(1, 16, (F_ - 1) // 4 + 1, H // 8, W // 8, generator=g(22)).to(cuda)
     want_mu = m.encode(video).latent_dist.mode()
@@ -115,7 +117,7 @@ def test_row_sharded_vae_is_bit_identical(cuda, world, F_, H, W):
 
     def run(which, full):
         stages = m.sharded_stages(which, full, world)
-        assert len(stages) == 3                                     # rows | frames (attention) | rows
+        assert len(stages) == (3 if not cuts else 6 if which == "enc" else 5)      # rows | frames (attention) | rows, + level cuts
         for stage in stages:
             parts, dim = [], None
             for r in range(world):

@@ -129,9 +129,11 @@ class _StagedStandIn(_StandIn):
         return 2.0 * x
 
 
+@pytest.mark.parametrize("cuts", [False, True])
 @pytest.mark.parametrize("world", [2, 3, 8])
-def test_encode_stages_rows_frames_rows(world, monkeypatch):
-    """sharded_stages('enc'): [rows | frames | rows] with a gather between stages reproduces the unsharded evaluation."""
+def test_encode_stages_rows_frames_rows(world, cuts, monkeypatch):
+    """sharded_stages('enc'): [rows | frames | rows] with a gather between stages reproduces the unsharded evaluation;
+    with ``level_cuts`` the row stages additionally end after every downsampling layer (one stage per resolution level)."""
     monkeypatch.setattr(wvae.lib, "planar_to_cl", lambda src, Cp, round_tf32=False: src.permute(1, 2, 3, 0).contiguous())
     torch.manual_seed(1)
     m = _StagedStandIn(torch.randn(1, 1, 3, 3) * 0.3)               # fp32: the first stage casts the video like the engine does
@@ -141,8 +143,10 @@ def test_encode_stages_rows_frames_rows(world, monkeypatch):
     for layer in m.enc_plan:
         x = m._attn(x, "a", 0) if layer[0] == "attn" else m._run([layer], x)
     want = m._conv(x, "conv1", None, 2)
+    m.level_cuts = cuts
     stages = m.sharded_stages("enc", video, world)
-    assert len(stages) == 3
+    n_down = sum(1 for l in m.enc_plan if l[0] in m.DOWNS)
+    assert len(stages) == 3 + (n_down if cuts else 0) and n_down >= 2
     full = video
     for stage in stages:
         parts, dim = [], None

@@ -17,7 +17,7 @@ CSRC = os.path.join(ROOT, "csrc")
 OUT = os.path.join(ROOT, "libwf_b200.so")
 OBJ_DIR = os.path.join(ROOT, "build")
 SOURCES = ["wf_api.cu", "gemm_tcgen05.cu", "attention_tcgen05.cu", "dit_ops.cu", "sampler_ops.cu", "vae_ops.cu",
-           "conv_tcgen05.cu", "attention_bsa_tcgen05.cu", "flow_ops.cu", "input_ops.cu"]
+           "conv_tcgen05.cu", "attention_bsa_tcgen05.cu", "flow_ops.cu", "input_ops.cu", "encoder_ops.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -457,7 +457,7 @@ conv_tf32_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 //    (39 %), and neither cheaper addressing, nor a leaner issue loop, nor deeper TMA rings moved it.  Independent chains DO
 //    overlap: the CTA therefore owns MT pixel tiles (MT x BN = 384 accumulator columns) and issues their MMAs round-robin.
 //  * a SWIZZLE_128B K-major operand may start at any 128-byte row and use any row-group pitch (the swizzle follows absolute
-//    address bits).  The MT tiles of 16 x 8 pixels form one block (2 x 2 or 2 x 1 tiles) whose halo is ONE 4-D TMA box per
+//    address bits).  The MT tiles of 16 x 8 pixels form one block (MT tiles side by side, 16 rows tall) whose halo is ONE 4-D TMA box per
 //    (dt, chunk) (out-of-bounds zero fill = padding and causal history); the A operand of tile (ty, tx) and tap (dy, dx) is
 //    that box read through a descriptor starting at halo row (16 ty + dy + 1) * PW + 8 tx + dx + 1 with group pitch PW rows.
 // One B tile (a tap's [BN, 32] weight slice) feeds all MT tiles: B traffic per MMA drops MT-fold, A traffic ~6-fold.
@@ -476,7 +476,9 @@ constexpr int CH_VEC_BYTES = 3072;                  // bias[Cout] and gamma[Cout
 constexpr int CH_RING_BUDGET = CH_SMEM_MAX - 1024 - CH_BAR_BYTES - CH_STAGE_BYTES;   // minus the launch's bias / gamma bytes
 
 template <int MT> struct ChGeom {
-  static constexpr int TX = MT == 4 ? 2 : 1, TY = MT == 1 ? 1 : 2;        // tiles per block along x / y
+  // tiles per block along x / y: the MT tiles of 16 x 8 pixels sit side by side (a block is 16 rows tall), so that the row
+  // slabs of the sharded VAE (60 rows + halo at 8 ranks) quantise to 16 rows instead of 32; the halo box has the same size
+  static constexpr int TX = MT, TY = 1;
   static constexpr int BW = TX * CH_TW, BH = TY * CH_TH;                   // block of output pixels
   static constexpr int PW = BW + 2, PH = BH + 2;                           // halo box
   static constexpr int A_BYTES = PW * PH * CV_BK * 4;

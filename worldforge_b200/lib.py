@@ -98,6 +98,8 @@ _SIGNATURES = {
     "wf_conv_tf32": [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i,
                      _vp, _i, _ll, _i, _i, _vp, _vp, _i, _vp],
     "wf_debug_conv_profile": [_vp],
+    "wf_attention_small_bf16": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp],
+    "wf_geglu_bf16": [_vp, _vp, _ll, _i, _vp],
     "wf_soften_mask": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "wf_clip_from_u8": [_vp, _vp, _ll, _vp],
     "wf_rms_norm_cl": [_vp, _i, _vp, _i, _vp, _ll, _i, _i, _i, _vp],

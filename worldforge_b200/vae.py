@@ -490,10 +490,20 @@ class WfWanVAE:
         lo, hi = need[-1]
         return x[:, lo - a:hi - a], lo
 
+    # Where a row stage ends besides the attention: after every downsampling layer of the encoder and before the first two
+    # upsampling layers of the decoder - i.e. at the SMALLEST tensor between two resolution levels.  Inside one stage a
+    # rank's halo grows by a row per 3x3 convolution and doubles at every resampling layer towards the high-resolution
+    # side, so a stage that spans all four levels recomputes 3.8x (encode) / 2.2x (decode) of its share at 8 ranks; cut per
+    # level the halo restarts at ~5-7 rows of the level's own resolution (1.2x at full resolution), for an all-gather of
+    # 0.2-3 GB of features per cut.  The last upsampling layer is not cut (its input is 6 GB at 81 x 240 x 416 x 192).
+    level_cuts = True
+
     def _segments(self, plan):
-        """Cut a layer plan at its attention blocks: [("rows", layers), ("frames", [attn]), ("rows", layers), ...].
+        """Cut a layer plan into row / frame stages: [("rows", layers), ("frames", [attn]), ("rows", layers), ...].
         Everything but the mid-block attention is local in space (row-shardable with a halo); the attention is one
-        full-frame softmax per frame and shards by frames instead."""
+        full-frame softmax per frame and shards by frames instead.  Cuts fall only where the unsharded evaluation fuses
+        nothing across (before / after a resampling layer, around the attention), so the stitched result stays bit-identical."""
+        ups_left = sum(1 for l in plan if l[0] in self.UPS)
         segs, cur = [], []
         for layer in plan:
             if layer[0] == "attn":
@@ -501,8 +511,16 @@ class WfWanVAE:
                     segs.append(("rows", cur))
                 segs.append(("frames", [layer]))
                 cur = []
-            else:
-                cur.append(layer)
+                continue
+            if self.level_cuts and layer[0] in self.UPS:
+                if ups_left > 1 and cur:
+                    segs.append(("rows", cur))
+                    cur = []
+                ups_left -= 1
+            cur.append(layer)
+            if self.level_cuts and layer[0] in self.DOWNS:
+                segs.append(("rows", cur))
+                cur = []
         if cur:
             segs.append(("rows", cur))
         return segs
