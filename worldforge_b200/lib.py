@@ -383,6 +383,28 @@ def rms_norm_head_rope_(x, gain, eps: float, rope=None):
     return x
 
 
+def attention_small(q, k, v, out, heads: int, head_dim: int, mode: int = 1, scale: float = 1.0, n_valid: Optional[int] = None,
+                    bias_emb=None, bias_bucket=None):
+    """Attention of the encoders (head_dim 64 / 80, <= 1024 keys); see wf_attention_small_bf16 in include/wf_b200.h."""
+    for t in (q, k, v, out):
+        assert t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1
+    Lq, Lk = q.shape[0], k.shape[0]
+    if bias_emb is not None:
+        assert bias_emb.dtype == torch.bfloat16 and bias_emb.is_contiguous() and bias_emb.shape[1] == heads
+        assert bias_bucket.dtype == torch.int32 and bias_bucket.numel() == 2 * Lk - 1 and bias_bucket.is_contiguous()
+    _call("wf_attention_small_bf16", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
+          _p(bias_emb), _p(bias_bucket), Lq, Lk, Lk if n_valid is None else n_valid, heads, head_dim, float(scale), mode, _stream())
+    return out
+
+
+def geglu_bf16(inp, out):
+    """inp bf16 [rows, 2F] = [gate | fc1] -> out [rows, F] = fc1 * GELU_tanh(gate) (T5FeedForward, bf16 intermediates)."""
+    rows, F2 = inp.shape
+    assert inp.dtype == torch.bfloat16 and inp.is_contiguous() and out.is_contiguous() and out.shape == (rows, F2 // 2)
+    _call("wf_geglu_bf16", _p(inp), _p(out), rows, F2 // 2, _stream())
+    return out
+
+
 def swiglu_bf16(inp, out):
     rows, F2 = inp.shape
     assert inp.dtype == torch.bfloat16 and inp.is_contiguous() and out.is_contiguous() and out.shape == (rows, F2 // 2)
