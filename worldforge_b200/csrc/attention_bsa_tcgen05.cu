@@ -679,12 +679,13 @@ extern "C" int wf_attention_bsa_bf16(const void* q, int ldq, const void* k, int 
   if ((rc = mk(&tmQ, q, ldq, Tq, ct))) return rc;
   if ((rc = mk(&tmK, k, ldk, Tk, ct / 2))) return rc;
   if ((rc = mk(&tmV, v, ldv, Tk, ct / 2))) return rc;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  rc = once.run([] {
     WF_CUDA_OK((cudaFuncSetAttribute(attention_bsa_tcgen05<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, BS_SMEM)));
     WF_CUDA_OK((cudaFuncSetAttribute(attention_bsa_tcgen05<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, BS_SMEM)));
-    configured = true;
-  }
+    return static_cast<int>(WF_OK);
+  });
+  if (rc) return rc;
   BsaArgs a;
   a.idx = block_idx; a.lens = block_lens; a.max_sel = max_sel;
   a.nhq = H / ch; a.nwq = W / cw; a.nhk = a.nhq; a.nwk = a.nwq;

@@ -910,8 +910,11 @@ static int attention_launch(const void* q, int ldq, const void* k, int ldk, cons
   if (variant == 0) {
     const char* e = getenv("WF_ATTN");
     forced = e != nullptr;
-    variant = e ? atoi(e) : 9;
-    if (variant < 1 || variant > 9) variant = 9;
+    int vv = e ? atoi(e) : 9;
+    variant = (vv < 1 || vv > 9) ? 9 : vv;
+  }
+  static PerDeviceOnce once;         // the shared-memory opt-in is a per-device function attribute
+  rc = once.run([] {
     WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v3<0x00u>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM)));
     WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v3<0x88u>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM)));
     WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v3<0xa4u>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM)));
@@ -921,7 +924,9 @@ static int attention_launch(const void* q, int ldq, const void* k, int ldk, cons
     WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v2<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)));
     WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v2<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)));
     WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v2<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)));
-  }
+    return static_cast<int>(WF_OK);
+  });
+  if (rc) return rc;
   AttnArgs args{};
   args.Lq = Lq; args.Lk = Lk; args.out = static_cast<bf16*>(out); args.ldo = ldo;
   args.add_in = static_cast<const bf16*>(add_in); args.ld_add = ld_add; args.scale_log2 = softmax_scale * 1.4426950408889634f;

@@ -709,12 +709,13 @@ static int launch_conv333(const float* in, int in_T, int in_H, int in_W, int Cin
   a.b_stages = std::min(CH_MAX_B_STAGES, (CH_RING_BUDGET - a.vec_bytes - a.a_stages * G::A_SLOT) / a.b_slot);
   if (a.b_stages < 2) return fail(WF_EINVAL, "wf_conv_tf32: no room for the B ring");
   const int smem = a.a_stages * G::A_SLOT + a.b_stages * a.b_slot + CH_BAR_BYTES + CH_STAGE_BYTES + a.vec_bytes + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  rc = once.run([] {
     WF_CUDA_OK((cudaFuncSetAttribute(conv333_halo_tcgen05<MT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_MAX)));
     WF_CUDA_OK((cudaFuncSetAttribute(conv333_halo_tcgen05<MT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_MAX)));
-    attr_set = true;
-  }
+    return static_cast<int>(WF_OK);
+  });
+  if (rc) return rc;
   const long long blocks = static_cast<long long>((a.W + G::BW - 1) / G::BW) * ((a.H + G::BH - 1) / G::BH) * a.T * ((a.Cout + a.BN - 1) / a.BN);
   const int grid = static_cast<int>(std::min<long long>(blocks, grid_cap));
   if (a.prof) conv333_halo_tcgen05<MT, true><<<grid, CH_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tmH, tmB, tmOut, tmNorm, tmRes, a);
@@ -781,10 +782,17 @@ extern "C" int wf_conv_tf32(const float* in, int in_T, int in_H, int in_W, int C
     int rc = make_tmap(&tmB, weights, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
+  static PerDeviceOnce once;
+  {
+    const int rc1 = once.run([] {
+      WF_CUDA_OK(cudaFuncSetAttribute(conv_tf32_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM));
+      return static_cast<int>(WF_OK);
+    });
+    if (rc1) return rc1;
+  }
   static bool attr_set = false;
   static int use_halo = 1, grid_cap = 0;
   if (!attr_set) {
-    WF_CUDA_OK(cudaFuncSetAttribute(conv_tf32_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM));
     const char* e = getenv("WF_CONV_HALO");            // 0: always the per-tap kernel (A/B measurements)
     use_halo = e ? atoi(e) : 1;
     const char* g = getenv("WF_CONV_GRID");            // cap on the number of CTAs (development)

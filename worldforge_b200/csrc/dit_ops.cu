@@ -596,11 +596,12 @@ extern "C" int wf_layer_norm(const void* x, int ldx, int x_is_bf16, void* out, i
   const int slot = (D * esize + 127) & ~127;
   // many rows: persistent CTAs with a shared-memory row ring (cp.async.bulk needs 16-byte aligned rows)
   if (rows >= 4 * sm_count() && al16(x) && (static_cast<long long>(ldx) * esize) % 16 == 0 && (D * esize) % 16 == 0) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    const int rc1 = once.run([] {
       WF_CUDA_OK(cudaFuncSetAttribute(layer_norm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NORM_RING * 32768));
-      configured = true;
-    }
+      return static_cast<int>(WF_OK);
+    });
+    if (rc1) return rc1;
     const int grid = std::min(rows, 3 * sm_count());
     layer_norm_kernel<true><<<grid, LN_THREADS, NORM_RING * slot, static_cast<cudaStream_t>(stream)>>>(a, rows);
   } else {
@@ -617,11 +618,12 @@ extern "C" int wf_rms_norm_rope(void* x, int ldx, const float* weight, const dou
   WF_REQUIRE(rope == nullptr || D % 128 == 0, "wf_rms_norm_rope: RoPE needs head_dim 128");
   RmsArgs a{static_cast<bf16*>(x), ldx, weight, rope, D, eps};
   if (rows >= 4 * sm_count() && reinterpret_cast<uintptr_t>(x) % 16 == 0 && D % 8 == 0) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    const int rc1 = once.run([] {
       WF_CUDA_OK(cudaFuncSetAttribute(rms_norm_rope_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NORM_RING * 16384));
-      configured = true;
-    }
+      return static_cast<int>(WF_OK);
+    });
+    if (rc1) return rc1;
     const int slot = (D * 2 + 127) & ~127;
     const int grid = std::min(rows, 4 * sm_count());
     rms_norm_rope_kernel<true><<<grid, RMS_THREADS, NORM_RING * slot, static_cast<cudaStream_t>(stream)>>>(a, rows);

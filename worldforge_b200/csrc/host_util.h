@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <string>
 
 #include "../../include/wf_b200.h"
@@ -38,6 +39,24 @@ int fail(int code, const std::string& msg);
 int make_tmap(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, int rank, const uint64_t* dims,
               const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle);
 
-int sm_count();
+int sm_count();     // of the current device
+
+// Runs `f` (returns a WF_* code) the first time it is reached on each CUDA device, under a lock: function attributes such as
+// cudaFuncAttributeMaxDynamicSharedMemorySize are per device, so a process that launches on a second GPU must set them
+// again there (one process per GPU is the deployed form, but the C ABI does not forbid more).
+struct PerDeviceOnce {
+  std::mutex m;
+  unsigned long long seen = 0;
+  template <class F> int run(F f) {
+    int d = 0;
+    cudaGetDevice(&d);
+    std::lock_guard<std::mutex> g(m);
+    const unsigned long long bit = 1ull << (d & 63);
+    if (seen & bit) return 0;
+    const int rc = f();
+    if (rc == 0) seen |= bit;
+    return rc;
+  }
+};
 
 }  // namespace wf

@@ -72,11 +72,12 @@ extern "C" int wf_soften_mask(const float* mask, float* out, int frames, int H, 
              "wf_soften_mask: transition distance out of range (0..31 pixels)");
   dim3 grid((W + SM_TILE - 1) / SM_TILE, (H + SM_TILE - 1) / SM_TILE, frames);
   const int span = SM_TILE + 2 * radius;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce once;
+  const int rc = once.run([] {
     WF_CUDA_OK(cudaFuncSetAttribute(soften_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (SM_TILE + 2 * SM_MAX_R) * (SM_TILE + 2 * SM_MAX_R)));
-    attr = true;
-  }
+    return static_cast<int>(WF_OK);
+  });
+  if (rc) return rc;
   soften_mask_kernel<<<grid, SM_TILE * SM_TILE, span * span, static_cast<cudaStream_t>(stream)>>>(mask, out, H, W, radius, max_d2, lut);
   WF_LAUNCH_OK();
   return WF_OK;

@@ -310,6 +310,25 @@ class PeerBuffer:
             raise WfError(f"wf_peer_alloc failed ({rc}): {lib.wf_last_error().decode()}")
         self.ptr, self.handle, self.nbytes = ptr.value, handle.raw, nbytes
 
+    def free(self):
+        """Release the allocation (idempotent).  The caller makes sure no kernel or peer still uses it (PeerSequenceParallel.close
+        synchronises the ranks first)."""
+        if self.ptr:
+            load().wf_peer_free(C.c_void_p(self.ptr))
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:        # noqa: BLE001 - interpreter shutdown
+            pass
+
+    @staticmethod
+    def close_mapping(ptr: int):
+        """Unmap a peer's allocation opened with ``open``."""
+        if ptr:
+            load().wf_peer_close(C.c_void_p(ptr))
+
     def tensor(self, shape, dtype, device):
         """A torch view of the allocation (no ownership)."""
         n = 1

@@ -310,6 +310,9 @@ class WfWanTransformer:
         if sp is not None and getattr(sp, "peer", False):
             if (L, Ll) not in self._psp:
                 from . import ulysses
+                for old in self._psp.values():         # another clip shape: release the previous exchange's buffers and mappings
+                    old.close()
+                self._psp.clear()
                 try:
                     self._psp[(L, Ll)] = ulysses.PeerSequenceParallel(sp.group, L, Ll, nh, self.device)
                 except ulysses.PeerSetupError as ex:   # raised on every rank alike: all of them keep the NCCL all-to-all form

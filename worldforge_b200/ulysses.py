@@ -105,6 +105,7 @@ class PeerSequenceParallel(SequenceParallel):
         # exchange what they have, try, and then AGREE on the outcome - either all of them use peer memory or all of them
         # raise PeerSetupError (the caller then keeps the NCCL all-to-all form; nothing hangs on a half-built exchange).
         err = None
+        self._bufs, self._ptrs = [], []
         try:
             self._bufs = [lib.PeerBuffer(L * self.ld_full * 2), lib.PeerBuffer(Ll * self.ld_att * 2), lib.PeerBuffer(Ll * self.ld_att * 2)]
             mine = [b.handle for b in self._bufs]
@@ -123,6 +124,7 @@ class PeerSequenceParallel(SequenceParallel):
         oks = [None] * P
         dist.all_gather_object(oks, err is None, group=self.group)
         if not all(oks):
+            self.close(sync=False)                      # whatever this rank allocated or mapped before the failure
             raise PeerSetupError(f"peer-memory exchange unavailable on rank(s) {[r for r, ok in enumerate(oks) if not ok]}: {err}")
         self.full = self._bufs[0].tensor((L, self.ld_full), torch.bfloat16, device)
         self.att = [self._bufs[1 + i].tensor((Ll, self.ld_att), torch.bfloat16, device) for i in range(2)]
@@ -133,6 +135,23 @@ class PeerSequenceParallel(SequenceParallel):
     def barrier(self):
         dist.all_reduce(self._flag, group=self.group)
         self.barriers += 1
+
+    def close(self, sync: bool = True):
+        """Unmap the peers' buffers and free this rank's (a change of resolution / frame count builds a new exchange; without
+        this the old allocations and IPC mappings stayed for the life of the process).  Collective when ``sync``."""
+        from . import lib
+        if sync:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)              # no peer is still reading or writing these buffers
+        for i, row in enumerate(self._ptrs):
+            for r, p in enumerate(row):
+                if r != self.rank:
+                    lib.PeerBuffer.close_mapping(p)
+        self._ptrs = []
+        for b in self._bufs:
+            b.free()
+        self._bufs = []
+        self.full, self.att = None, []
 
     def exchange_attention(self, qkv: torch.Tensor, norm_q, norm_k, rope, eps: float) -> torch.Tensor:
         """qkv [Ll, 3*H*128] bf16 straight from the projection (NOT yet normalised) -> attention output [Ll, H*128]."""
