@@ -108,13 +108,18 @@ def _peer_setup_worker(rank, world, store, ret):
                     raise lib.WfError("no device memory")
                 self.ptr, self.handle, self.nbytes = 4096, b"h" * 64, nbytes
             open = staticmethod(lambda handle: 8192)
+            freed = []
+
+            def free(self):                                     # the failed set-up releases what this rank had allocated
+                FakeBuffer.freed.append(self.nbytes)
+            close_mapping = staticmethod(lambda ptr: None)
 
         lib.PeerBuffer = FakeBuffer
         try:
             ulysses.PeerSequenceParallel(None, 64, 32, 4, torch.device("cpu"))
             ret[rank] = "built"
         except ulysses.PeerSetupError as ex:
-            ret[rank] = "agreed:" + str(ex)
+            ret[rank] = "agreed:" + str(ex) + f" freed={len(FakeBuffer.freed)}"
     finally:
         dist.destroy_process_group()
 
@@ -125,6 +130,7 @@ def test_peer_setup_failure_is_agreed_by_all_ranks():
     mp.spawn(_peer_setup_worker, args=(2, _store_file(), ret), nprocs=2, join=True)
     assert ret[0].startswith("agreed:") and ret[1].startswith("agreed:")
     assert "no device memory" in ret[1] and "a peer could not" in ret[0]
+    assert ret[0].endswith("freed=3") and ret[1].endswith("freed=0")      # rank 0 releases its three buffers, rank 1 had none
 
 
 def _cfg_worker(rank, world, store, ret):
