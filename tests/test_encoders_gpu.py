@@ -46,6 +46,8 @@ def test_t5_kernels(cuda):
 def test_t5_encoder_matches_oracle(cuda):
     from worldforge_b200 import encoders
     P = oe.init_params(oe.t5_shapes(**T5), 3)
+    for i in range(2):                                  # T5 has no softmax scale: keep the random-weight logits O(1) so that one
+        P[f"blocks.{i}.attn.q.weight"] *= 0.25          # flipped bf16 rounding of a score is not amplified by a saturated softmax
     m = encoders.WfT5Encoder(P, cuda, dim=128, dim_attn=128, dim_ffn=256, num_heads=2, num_layers=2)
     g = torch.Generator().manual_seed(1)
     ids = torch.randint(0, 50, (2, 24), generator=g)
@@ -53,8 +55,12 @@ def test_t5_encoder_matches_oracle(cuda):
     got = m(ids.to(cuda), mask.to(cuda)).last_hidden_state
     for s in range(2):
         want = oe.t5_encoder(P, ids[s], mask[s], 2, 2, amp=True)
+        exact = oe.t5_encoder(P, ids[s], mask[s], 2, 2, amp=False)
         n = int(mask[s].sum())
-        assert rel(got[s, :n].cpu(), want[:n]) < 6e-3, (s, rel(got[s, :n].cpu(), want[:n]))
+        floor = rel(want[:n], exact[:n])                # what the reference's own bf16 module loses against fp32
+        e_fp32, e_model = rel(got[s, :n].cpu(), exact[:n]), rel(got[s, :n].cpu(), want[:n])
+        print(f"\n[floor] T5 encoder sample {s}: bf16-module-vs-fp32 {floor:.3e}  engine-vs-fp32 {e_fp32:.3e}  engine-vs-bf16-module {e_model:.3e}")
+        assert e_fp32 <= 1.25 * floor + 1e-3 and e_model <= 1.5 * floor + 1e-3, (s, floor, e_fp32, e_model)
     pe = encoders.t5_prompt_embeds(m, ids.to(cuda), mask.to(cuda), max_sequence_length=32)
     assert pe.shape == (2, 32, 128) and not pe[0, 17:].any() and torch.equal(pe[1, :24], got[1])
     # transformers' UMT5EncoderModel parameter names load to the same network
