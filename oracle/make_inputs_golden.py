@@ -77,6 +77,67 @@ def ref_kv():
                 k0=cache[0][0][0].clone(), v1=cache[1][1][0].clone())
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# LongCat generate_i2v, the loop itself: python -m oracle.make_inputs_golden i2v -> tests/golden/longcat_i2v_golden.pt
+# ---------------------------------------------------------------------------------------------------------------------
+I2V_OUT = os.path.join(os.path.dirname(OUT), "longcat_i2v_golden.pt")
+I2V_STEPS = 8
+
+
+def ref_generate_i2v(distill: bool):
+    """LongCatVideoPipeline.generate_i2v of the reference (pipeline_longcat_video.py:619-1006), UNMODIFIED, driving the
+    reference's own FlowMatchEulerDiscreteScheduler over the oracle DiT / VAE objects: encode_prompt's masking and batching,
+    prepare_latents, the IRR inner loop, CFG-zero, the sign flip, re-noise and DSG.  Two things are handed in rather than
+    computed: the prompt embeddings (FixedTextEncoder) and the output size (the bucket lookup would pick 480 x 832; the run
+    uses 64 x 96).  The VAE adapter's posterior sample is its mode.  Recorded: the prepared latents, the DiT's input latents
+    at EVERY forward (every IRR round of every step) and the final latents."""
+    from oracle import adapters, longcat_dit, make_golden as mg, ref_shim, wan_vae
+    pm_mod = ref_shim.load_longcat_pipeline_module()
+    sm = ref_shim.load_longcat_scheduler_module()
+    cfg, vcfg = longcat_dit.LongCatConfig(**mg.LC_SCHED_DIT), wan_vae.VaeConfig(dim=8)
+    P, PV = longcat_dit.init_params(cfg, 3), wan_vae.init_params(vcfg, 2)
+    inp, pe, pmask = mg.longcat_sched_inputs()
+    table = {"neg": (pe[0, 0], int(pmask[0].sum())), "pos": (pe[1, 0], int(pmask[1].sum()))}
+    enc = ref_shim.FixedTextEncoder(table, pe.shape[2], pe.shape[3])
+    vae = adapters.OracleVAE(PV, vcfg)
+    vae.config.scale_factor_temporal, vae.config.scale_factor_spatial = 4, 8
+    enc_fn = vae.encode
+    def encode(x):
+        o = enc_fn(x)
+        o.latent_dist.sample = lambda generator=None: o.latent_dist.mode()
+        return o
+    vae.encode = encode
+    dit = adapters.OracleLongCatDit(P, cfg, amp=True)
+    seen = []
+    call = dit.__call__
+    class Rec:
+        dtype, config, cp_split_hw = dit.dtype, dit.config, dit.cp_split_hw
+        def __call__(self, hidden_states, **kw):
+            seen.append(hidden_states[-1].clone())
+            return call(hidden_states=hidden_states, **kw)
+    sched = sm.FlowMatchEulerDiscreteScheduler(num_train_timesteps=1000, shift=1.0)
+    pipe = pm_mod.LongCatVideoPipeline(tokenizer=enc.tokenizer, text_encoder=enc, vae=vae, scheduler=sched, dit=Rec())
+    pipe.device = "cpu"
+    pipe.get_condition_shape = lambda image, resolution, scale_factor_spatial=32: (64, 96)
+    prepared = []
+    prep = pipe.prepare_latents
+    def prepare_latents(**kw):
+        out = prep(**kw)
+        prepared.append(out.clone())
+        return out
+    pipe.prepare_latents = prepare_latents
+    image = inp.video_ref[:, :, 0] * 2 - 1
+    knobs = dict(mg.LC_KNOBS)
+    final = pipe.generate_i2v(image=image, prompt="pos", negative_prompt="neg", num_frames=9, num_inference_steps=I2V_STEPS,
+                              use_distill=distill, generator=torch.Generator().manual_seed(42), output_type="latent",
+                              max_sequence_length=pe.shape[2], video_ref=inp.video_ref, mask=inp.mask, **knobs)
+    return dict(prepared=prepared[0], dit_inputs=torch.stack(seen), final=final.clone(), flf=[len(c) for _, c in getattr(sched, "flf_log", [])])
+
+
+if __name__ == "__main__" and len(__import__("sys").argv) > 1 and __import__("sys").argv[1] == "i2v":
+    torch.save({"standard": ref_generate_i2v(False), "distill": ref_generate_i2v(True)}, I2V_OUT)
+    print("wrote", I2V_OUT, os.path.getsize(I2V_OUT), "bytes")
+
 if __name__ == "__main__" and len(__import__("sys").argv) > 1 and __import__("sys").argv[1] == "kv":
     torch.save(ref_kv(), KV_OUT)
     print("wrote", KV_OUT, os.path.getsize(KV_OUT), "bytes")

@@ -461,6 +461,56 @@ def load_wan_pipeline_module():
     return m
 
 
+def load_longcat_pipeline_module():
+    """longcat_video/pipeline_longcat_video.py, unmodified: ``LongCatVideoPipeline`` (a plain class).  Its own package
+    imports resolve to the reference tree (DiT / scheduler / VAE modules over the shims above); ``loguru`` and ``ftfy`` are
+    not installed and get no-op stand-ins (logging and prompt cleaning only)."""
+    assert os.path.isdir(REF_LONGCAT)
+    install_pipeline_shim()
+    load_longcat_vae_module()                       # registers the diffusers names autoencoder_kl_wan.py imports
+    _fake_xformers()
+    if "loguru" not in sys.modules:
+        lg = types.ModuleType("loguru")
+        lg.logger = types.SimpleNamespace(info=lambda *a, **k: None, warning=lambda *a, **k: None, error=lambda *a, **k: None,
+                                          debug=lambda *a, **k: None)
+        sys.modules["loguru"] = lg
+    if "ftfy" not in sys.modules:
+        f = types.ModuleType("ftfy"); f.fix_text = lambda t: t
+        sys.modules["ftfy"] = f
+    if REF_LONGCAT not in sys.path:
+        sys.path.insert(0, REF_LONGCAT)
+    for name in [m for m in sys.modules if m == "longcat_video" or m.startswith("longcat_video.")]:
+        del sys.modules[name]
+    return importlib.import_module("longcat_video.pipeline_longcat_video")
+
+
+class FixedTextEncoder:
+    """``text_encoder`` stand-in for LongCatVideoPipeline.encode_prompt (pipeline_longcat_video.py:90-189), with its
+    ``tokenizer`` twin: the prompt string selects one of the given (embedding [L, C], valid length) pairs; everything the
+    pipeline does with them afterwards (masking, the [negative, positive] batch) is the reference's own code."""
+
+    def __init__(self, table, max_len: int, dim: int):
+        self.table, self.max_len = table, max_len
+        self.dtype = torch.bfloat16
+        self.config = types.SimpleNamespace(d_model=dim)
+        self._order = list(table)
+        enc = self
+
+        class _Tokenizer:
+            def __call__(self, prompt, **kw):
+                ids = torch.zeros(len(prompt), enc.max_len, dtype=torch.long)
+                mask = torch.zeros(len(prompt), enc.max_len, dtype=torch.long)
+                for i, p in enumerate(prompt):
+                    ids[i, 0] = enc._order.index(p)
+                    mask[i, :enc.table[p][1]] = 1
+                return types.SimpleNamespace(input_ids=ids, attention_mask=mask)
+        self.tokenizer = _Tokenizer()
+
+    def __call__(self, ids, mask):
+        hs = torch.stack([self.table[self._order[int(i[0])]][0] for i in ids])
+        return types.SimpleNamespace(last_hidden_state=hs)
+
+
 class FixedImageEncoder:
     """``image_processor`` + ``image_encoder`` stand-ins for encode_image (pipeline_wan_i2v_clean.py:205-209): the
     reference refuses ``image`` together with ``image_embeds`` (:362-363) but needs ``image`` for prepare_latents, so the
