@@ -12,16 +12,18 @@
 // Layout: q,k,v,out are the [tokens, heads*128] row-major matrices the q/k/v projections
 // produce - head h is the 128-column slice at h*128; nothing is transposed or re-packed.
 //
-// One CTA owns TWO 128-row query tiles of one head and walks the keys in blocks of 64:
-//   warp 0   TMA producer   (Q once; K/V blocks through a 4-stage mbarrier ring)
-//   warp 1   MMA issuer     S_t = Q_t K^T (128x64, K=128)  and  O_t += P_t V (128x128, K=64)
-//   warp 2   TMEM allocator (S_0,S_1: 64 columns each; O_0,O_1: 128 columns each)
+// One CTA owns TWO 128-row query tiles of one head and walks the keys in blocks:
+//   warp 0   TMA producer   (Q once; K/V blocks through an mbarrier ring)
+//   warp 1   MMA issuer     S_t = Q_t K^T  and  O_t += P_t V
+//   warp 2   TMEM allocator
 //   warps 4-7 / 8-11  softmax for tile 0 / tile 1: one thread per query row
 // The issuer alternates the two tiles so that while tile 0's rows are in softmax the tensor
 // core runs tile 1's MMAs (and vice versa).  V is consumed as an MN-major UMMA operand
-// straight from its TMA box; P goes through 128-byte-swizzled shared memory.  O stays in
-// TMEM for the whole key loop; it is rescaled there only when a row maximum grows by more
-// than 2^8 (lazy rescaling), so the common path never touches O.
+// straight from its TMA box.  O stays in TMEM for the whole key loop; it is rescaled there
+// only when a row maximum grows by more than 2^8 (lazy rescaling), so the common path never
+// touches O.  Two kernels: v2 (64-key blocks; the short ragged key sets of the cross-attention)
+// and v3 (128-key blocks; the default).  (Round 1's first kernel, single S buffer with P
+// through shared memory, is gone: every variant below supersedes it.)
 #include <stdlib.h>
 
 #include <type_traits>
@@ -56,241 +58,8 @@ struct AttnArgs {
   float scale_log2;     // softmax scale * log2(e)
 };
 
-__global__ void __launch_bounds__(AT_THREADS, 1)
-attention_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                  const __grid_constant__ CUtensorMap tmV, AttnArgs p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_OFF_BAR);
-  uint64_t* q_full = bars;                 // 1
-  uint64_t* kv_full = bars + 1;            // AT_STAGES
-  uint64_t* kv_empty = kv_full + AT_STAGES;
-  uint64_t* s_full = kv_empty + AT_STAGES; // 2
-  uint64_t* p_full = s_full + 2;           // 2
-  uint64_t* o_done = p_full + 2;           // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int head = blockIdx.y;
-  const int q0 = blockIdx.x * (2 * AT_BM);
-  const int nblk = (p.Lk + AT_BN - 1) / AT_BN;
-  const int col0 = head * AT_D;
-
-  if (warp == 0 && elect_one()) {
-    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
-  }
-  if (warp == 1 && elect_one()) {
-    mbar_init(q_full, 1);
-    for (int s = 0; s < AT_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int t = 0; t < 2; ++t) { mbar_init(&s_full[t], 1); mbar_init(&p_full[t], 4); mbar_init(&o_done[t], 1); }
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, 2 * AT_Q_BYTES);
-      for (int t = 0; t < 2; ++t)
-        for (int half = 0; half < 2; ++half)
-          tma_load_2d(smem + t * AT_Q_BYTES + half * (AT_Q_BYTES / 2), &tmQ, q_full, col0 + half * 64, q0 + t * AT_BM);
-    }
-    __syncwarp();
-    for (int j = 0; j < nblk; ++j) {
-      const int stage = j % AT_STAGES;
-      const uint32_t phase = (j / AT_STAGES) & 1;
-      mbar_wait(&kv_empty[stage], phase ^ 1);
-      if (elect_one()) {
-        uint8_t* kdst = smem + AT_OFF_KV + stage * AT_KV_BYTES;
-        uint8_t* vdst = kdst + AT_K_BYTES;
-        mbar_arrive_expect_tx(&kv_full[stage], AT_KV_BYTES);
-        for (int half = 0; half < 2; ++half) {
-          tma_load_2d(kdst + half * (AT_K_BYTES / 2), &tmK, &kv_full[stage], col0 + half * 64, j * AT_BN);
-          tma_load_2d(vdst + half * (AT_K_BYTES / 2), &tmV, &kv_full[stage], col0 + half * 64, j * AT_BN);
-        }
-      }
-      __syncwarp();
-    }
-  } else if (warp == 1) {
-    // -------------------------------------------------------------- MMA issuer
-    constexpr uint32_t idesc_s = umma_idesc(1, AT_BM, AT_BN, 0, 0);   // S = Q K^T : both K-major
-    constexpr uint32_t idesc_o = umma_idesc(1, AT_BM, AT_D, 0, 1);    // O += P V  : V is MN-major
-    const uint32_t q_addr = smem_u32(smem);
-    const uint32_t p_addr = smem_u32(smem + AT_OFF_P);
-    auto issue_s = [&](int t, int stage) {
-      const uint32_t k_addr = smem_u32(smem + AT_OFF_KV + stage * AT_KV_BYTES);
-#pragma unroll
-      for (int ks = 0; ks < AT_D / 16; ++ks) {
-        uint64_t da = umma_desc_sw128(q_addr + t * AT_Q_BYTES + (ks >> 2) * (AT_Q_BYTES / 2) + (ks & 3) * 32, 16, 1024);
-        uint64_t db = umma_desc_sw128(k_addr + (ks >> 2) * (AT_K_BYTES / 2) + (ks & 3) * 32, 16, 1024);
-        umma_f16_ss(tmem_base + AT_TMEM_S + t * AT_BN, da, db, idesc_s, ks != 0);
-      }
-      umma_commit(&s_full[t]);
-    };
-    auto issue_pv = [&](int t, int stage, int j) {
-      const uint32_t v_addr = smem_u32(smem + AT_OFF_KV + stage * AT_KV_BYTES + AT_K_BYTES);
-#pragma unroll
-      for (int ks = 0; ks < AT_BN / 16; ++ks) {
-        uint64_t da = umma_desc_sw128(p_addr + t * AT_P_BYTES + ks * 32, 16, 1024);
-        uint64_t db = umma_desc_sw128(v_addr + ks * 2048, AT_K_BYTES / 2, 1024);
-        umma_f16_ss(tmem_base + AT_TMEM_O + t * AT_D, da, db, idesc_o, (j | ks) != 0);
-      }
-      umma_commit(&o_done[t]);
-    };
-    mbar_wait(q_full, 0);
-    mbar_wait(&kv_full[0], 0);
-    tc_fence_after();
-    if (elect_one()) { issue_s(0, 0); issue_s(1, 0); }
-    __syncwarp();
-    for (int j = 0; j < nblk; ++j) {
-      const int stage = j % AT_STAGES;
-      const int nstage = (j + 1) % AT_STAGES;
-      const bool more = (j + 1 < nblk);
-      if (more) mbar_wait(&kv_full[nstage], ((j + 1) / AT_STAGES) & 1);
-      mbar_wait(&p_full[0], j & 1);
-      tc_fence_after();
-      if (elect_one()) {
-        issue_pv(0, stage, j);
-        if (more) issue_s(0, nstage);
-      }
-      __syncwarp();
-      mbar_wait(&p_full[1], j & 1);
-      tc_fence_after();
-      if (elect_one()) {
-        issue_pv(1, stage, j);
-        umma_commit(&kv_empty[stage]);      // both tiles have consumed this K/V block
-        if (more) issue_s(1, nstage);
-      }
-      __syncwarp();
-    }
-  } else if (warp >= 4) {
-    // ------------------------------------------------------------ softmax + epilogue
-    const int t = (warp - 4) >> 2;          // which query tile
-    const int qd = warp & 3;                // TMEM lane quarter
-    const int row = qd * 32 + lane_id();    // row within the tile
-    const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
-    const uint32_t s_tmem = tmem_base + lane_addr + AT_TMEM_S + t * AT_BN;
-    const uint32_t o_tmem = tmem_base + lane_addr + AT_TMEM_O + t * AT_D;
-    uint8_t* p_row = smem + AT_OFF_P + t * AT_P_BYTES + row * 128;
-    float m_ref = 0.f, l = 0.f;
-    for (int j = 0; j < nblk; ++j) {
-      mbar_wait(&s_full[t], j & 1);
-      tc_fence_after();
-      uint32_t r0[32], r1[32];
-      tmem_ld_32x32b_x32(s_tmem, r0);
-      tmem_ld_32x32b_x32(s_tmem + 32, r1);
-      tmem_ld_wait();
-      float s[64];
-      const int valid = p.Lk - j * AT_BN;   // keys of this block that exist
-#pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        s[c] = __uint_as_float(r0[c]) * p.scale_log2;
-        s[c + 32] = __uint_as_float(r1[c]) * p.scale_log2;
-      }
-      if (valid < AT_BN) {
-#pragma unroll
-        for (int c = 0; c < 64; ++c) if (c >= valid) s[c] = -INFINITY;
-      }
-      float m_blk = s[0];
-#pragma unroll
-      for (int c = 1; c < 64; ++c) m_blk = fmaxf(m_blk, s[c]);
-      float alpha = 1.0f;
-      bool grow = false;
-      if (j == 0) {
-        m_ref = m_blk;
-      } else if (m_blk - m_ref > AT_RESCALE_THRESHOLD) {
-        alpha = ex2(m_ref - m_blk);
-        m_ref = m_blk;
-        grow = true;
-      }
-      float sum = 0.f;
-      uint32_t pk[32];
-#pragma unroll
-      for (int c = 0; c < 64; c += 2) {
-        float e0 = ex2(s[c] - m_ref), e1 = ex2(s[c + 1] - m_ref);
-        sum += e0 + e1;
-        pk[c >> 1] = pack_bf16x2(e0, e1);
-      }
-      l = l * alpha + sum;
-      // P_t smem and O_t TMEM are free once PV_t(j-1) has retired
-      if (j > 0) {
-        mbar_wait(&o_done[t], (j - 1) & 1);
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, grow)) {
-#pragma unroll 1
-          for (int c = 0; c < AT_D; c += 32) {
-            uint32_t o[32];
-            tmem_ld_32x32b_x32(o_tmem + c, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x32b_x32(o_tmem + c, o);
-          }
-          tmem_st_wait();
-        }
-      }
-      // row-major 128-byte rows, 16-byte chunks XOR-swizzled by (row & 7): the SWIZZLE_128B K-major layout
-#pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        uint4 v = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
-        *reinterpret_cast<uint4*>(p_row + ((ch ^ (row & 7)) << 4)) = v;
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane_id() == 0) mbar_arrive(&p_full[t]);
-    }
-    // epilogue: O / l -> bf16 -> global
-    mbar_wait(&o_done[t], (nblk - 1) & 1);
-    tc_fence_after();
-    const int q = q0 + t * AT_BM + row;
-    const float inv_l = 1.0f / l;
-#pragma unroll 1
-    for (int c = 0; c < AT_D; c += 32) {
-      uint32_t o[32];
-      tmem_ld_32x32b_x32(o_tmem + c, o);
-      tmem_ld_wait();
-      if (q < p.Lq) {
-        bf16* dst = p.out + static_cast<size_t>(q) * p.ldo + col0 + c;
-        const bf16* add = p.add_in ? p.add_in + static_cast<size_t>(q) * p.ld_add + col0 + c : nullptr;
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          float w[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) w[u] = __uint_as_float(o[i + u]) * inv_l;
-          if (add) {
-            uint4 a = *reinterpret_cast<const uint4*>(add + i);
-            const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              float2 f = __bfloat1622float2(a2[u]);
-              w[2 * u] = __fadd_rn(bf16_round(w[2 * u]), f.x);
-              w[2 * u + 1] = __fadd_rn(bf16_round(w[2 * u + 1]), f.y);
-            }
-          }
-          uint4 v = make_uint4(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]), pack_bf16x2(w[4], w[5]),
-                               pack_bf16x2(w[6], w[7]));
-          *reinterpret_cast<uint4*>(dst + i) = v;
-        }
-      }
-    }
-    tc_fence_before();
-  }
-
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
-
 // =====================================================================================================================
-// v2: the same algorithm with (a) S double-buffered in TMEM so the tensor core computes S(j+1) for both tiles while the
+// v2: 64-key blocks with (a) S double-buffered in TMEM so the tensor core computes S(j+1) for both tiles while the
 // softmax warps still work on block j - the softmax never waits for the MMA and vice versa except through P;
 // (b) packed fp32x2 arithmetic (FFMA2 / FADD2), 3-input max (FMNMX3) and one fused multiply-add per score for
 // "scale, subtract the running maximum"; (c) optionally, every fourth pair of exponentials evaluated on the FMA pipe
@@ -901,7 +670,7 @@ static int attention_launch(const void* q, int ldq, const void* k, int ldk, cons
   if ((rc = mk(&tmQ, q, ldq, Lq, AT_BM))) return rc;
   if ((rc = mk(&tmK, k, ldk, Lk, AT_BN))) return rc;
   if ((rc = mk(&tmV, v, ldv, Lk, AT_BN))) return rc;
-  // WF_ATTN=1: v1 (single S buffer, P through smem); 2: v2 (double-buffered S, packed fp32x2 softmax, P through smem);
+  // WF_ATTN=2 (1 is an alias): v2 (double-buffered S, packed fp32x2 softmax, P through smem);
   // 3: v2 + polynomial ex2 offload; 4: v2 with P kept in TMEM as the A operand of the PV product; 5/6: 4 + polynomial ex2;
   // 7/8/9: v3 (128-key blocks, P handed over in halves) with 0 / 2 / 3 of every 8 exponential pairs on the FMA pipe.
   // Default 9: 26.0 M SM cycles per launch at the 480p shape against 31.9 M for variant 4 (tensor pipe 71 % vs 58 % active).
@@ -918,7 +687,6 @@ static int attention_launch(const void* q, int ldq, const void* k, int ldk, cons
     WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v3<0x00u>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM)));
     WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v3<0x88u>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM)));
     WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v3<0xa4u>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM)));
-    WF_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
     WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v2<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)));
     WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v2<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)));
     WF_CUDA_OK((cudaFuncSetAttribute(attention_tcgen05_v2<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)));
@@ -952,9 +720,7 @@ static int attention_launch(const void* q, int ldq, const void* k, int ldk, cons
     WF_LAUNCH_OK();
     return WF_OK;
   }
-  WF_REQUIRE(!(variant == 1 && n_peers > 0), "wf_attention_bf16_peers: variant 1 has no peer epilogue");
-  if (variant == 1) attention_tcgen05<<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);
-  else if (variant == 2) attention_tcgen05_v2<0, false><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);
+  if (variant <= 2) attention_tcgen05_v2<0, false><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);
   else if (variant == 3) attention_tcgen05_v2<1, false><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);
   else if (variant == 5) attention_tcgen05_v2<1, true><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);   // 4 + 25% polynomial ex2
   else if (variant == 6) attention_tcgen05_v2<2, true><<<grid, AT_THREADS, AT_SMEM, st>>>(tmQ, tmK, tmV, args);   // 4 + 50% polynomial ex2
