@@ -238,9 +238,11 @@ int wf_quantise_u8(const void* x, int is_bf16, unsigned char* out, long long n, 
 long long wf_farneback_workspace_bytes(int clips, int T, int H, int W);
 int wf_farneback_u8(const unsigned char* clips_u8, int clips, int T, int H, int W, int winsize, int iterations, float* flow,
                     void* workspace, void* stream);
-/* per channel: mean end-point error, mean outlier indicator (epe > 3 and epe > 0.05 |ref|), mean angular error in degrees
+/* per channel: mean end-point error, mean outlier indicator (epe > 3 AND epe > 0.05 |ref|; with outlier_or = 1 the two tests are
+ * OR-ed - LongCat's variant, longcat_video/modules/scheduling_flow_match_euler_discrete.py:226), mean angular error in degrees
  * between two flow fields [channels][per_channel][2]; out3: fp32 [channels][3]. */
-int wf_flow_metrics(const float* flow_ref, const float* flow_cand, float* out3, int channels, long long per_channel, void* stream);
+int wf_flow_metrics(const float* flow_ref, const float* flow_cand, float* out3, int channels, long long per_channel,
+                    int outlier_or, void* stream);
 /* LongCat CFG-zero + sign flip (pipeline_longcat_video.py:374-383, 875-888), fp32:
  * st = <cond,uncond>/(|uncond|^2 + 1e-8); out = -(uncond*st + scale*(cond - uncond*st)).  workspace: wf_dsg_workspace_bytes().
  * stats (device float[1] or NULL) receives st. */

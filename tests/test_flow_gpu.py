@@ -85,3 +85,26 @@ def test_selector_scores_device_vs_opencv(cuda, shape):
     np.testing.assert_allclose(s_dev, s_host, rtol=0, atol=2e-5)
     for step in (7, 12, 30):
         assert flf_select.selection_policy(s_dev, step) == flf_select.selection_policy(s_host, step)
+
+
+def test_longcat_selector_device_vs_opencv(cuda):
+    """LongCat's variant of the scoring (per-channel min-max, outliers by OR, weights 0.4 / 0.4 / 0.2;
+    scheduling_flow_match_euler_discrete.py:205-244, 286-379): device path vs OpenCV on host threads, same scores to 2e-5 and
+    the same channel choices at every policy stage."""
+    from worldforge_b200 import longcat_pipeline as wlp, lib
+    u8 = _clips(32, 13, (60, 104))
+    enc = torch.from_numpy(u8[:16].astype(np.float32) / 255.0).unsqueeze(0).to(cuda) * 3.0 - 1.0
+    pred = torch.from_numpy(u8[16:].astype(np.float32) / 255.0).unsqueeze(0).to(cuda) * 2.0 + 0.5
+    host, dev = wlp.LongCatChannelSelector(device_flow=False), wlp.LongCatChannelSelector(device_flow=True)
+    for step, distill in ((2, False), (8, False), (5, True)):
+        a = host.select(pred, enc, step, distill, 3)
+        b = dev.select(pred, enc, step, distill, 3)
+        np.testing.assert_allclose(dev.last_scores, host.last_scores, rtol=0, atol=2e-5)
+        assert a == b and len(a) >= 1
+    g = torch.Generator().manual_seed(3)
+    fa = torch.randn(3, 7, 20, 24, 2, generator=g) * 3
+    fb_ = fa + torch.randn(3, 7, 20, 24, 2, generator=g) * torch.tensor([0.1, 2.0, 6.0]).view(3, 1, 1, 1, 1)
+    m = lib.flow_metrics(fa.to(cuda), fb_.to(cuda), outlier_or=True).cpu()
+    for c in range(3):
+        want = wlp.flow_similarity(fa[c].permute(0, 3, 1, 2), fb_[c].permute(0, 3, 1, 2))
+        assert abs(wlp.similarity_from_means(float(m[c, 0]), float(m[c, 1]), float(m[c, 2])) - want) < 2e-6

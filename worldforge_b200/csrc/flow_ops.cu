@@ -264,7 +264,7 @@ __global__ void fb_box_solve_kernel(const double* __restrict__ V, float* __restr
 // flows [channels][pairs_per_channel][H][W][2] (dx, dy); out [channels][3] = mean EPE, mean outlier, mean angle (degrees)
 constexpr int FM_THREADS = 1024;
 __global__ void __launch_bounds__(FM_THREADS) flow_metrics_kernel(const float* __restrict__ ref, const float* __restrict__ cand,
-                                                                  float* __restrict__ out, long long per_channel) {
+                                                                  float* __restrict__ out, long long per_channel, int outlier_or) {
   __shared__ double red[3][FM_THREADS / 32];
   const float* r = ref + static_cast<size_t>(blockIdx.x) * per_channel * 2;
   const float* c = cand + static_cast<size_t>(blockIdx.x) * per_channel * 2;
@@ -281,7 +281,9 @@ __global__ void __launch_bounds__(FM_THREADS) flow_metrics_kernel(const float* _
     const float ang = __fdiv_rn(__fmul_rn(acosf(cosv), 180.0f), 3.14159265358979323846f);
     s_epe += epe;
     s_ang += ang;
-    s_out += (epe > 3.0f && epe > __fmul_rn(rn, 0.05f)) ? 1.0 : 0.0;
+    // Wan: epe > 3 AND epe > 0.05 |ref| (scheduling_unipc_multistep_clean.py:557); LongCat: OR (scheduling_flow_match_euler_discrete.py:226)
+    const bool a = epe > 3.0f, b = epe > __fmul_rn(rn, 0.05f);
+    s_out += (outlier_or ? (a || b) : (a && b)) ? 1.0 : 0.0;
   }
   double v[3] = {s_epe, s_out, s_ang};
 #pragma unroll
@@ -411,9 +413,9 @@ extern "C" int wf_farneback_u8(const unsigned char* clips_u8, int clips, int T, 
 }
 
 extern "C" int wf_flow_metrics(const float* flow_ref, const float* flow_cand, float* out3, int channels, long long per_channel,
-                               void* stream) {
+                               int outlier_or, void* stream) {
   WF_REQUIRE(flow_ref && flow_cand && out3 && channels > 0 && per_channel > 0, "wf_flow_metrics: bad arguments");
-  flow_metrics_kernel<<<channels, FM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(flow_ref, flow_cand, out3, per_channel);
+  flow_metrics_kernel<<<channels, FM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(flow_ref, flow_cand, out3, per_channel, outlier_or);
   WF_LAUNCH_OK();
   return WF_OK;
 }

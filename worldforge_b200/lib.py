@@ -69,7 +69,7 @@ _SIGNATURES = {
     "wf_qkv_norm_rope_scatter": [_vp, _i, _vp, _vp, _vp, _i, _i, _f, _vp, _i, _i, _i, _vp],
     "wf_attention_bf16_peers": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _f, _vp],
     "wf_farneback_u8": [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
-    "wf_flow_metrics": [_vp, _vp, _vp, _i, _ll, _vp],
+    "wf_flow_metrics": [_vp, _vp, _vp, _i, _ll, _i, _vp],
     "wf_peer_alloc": [_ll, _vp, _vp],
     "wf_peer_open": [_vp, _vp],
     "wf_peer_close": [_vp],
@@ -575,13 +575,14 @@ def farneback_u8(clips_u8, winsize: int = 15, iterations: int = 3):
     return flow
 
 
-def flow_metrics(flow_ref, flow_cand):
-    """[C, ..., 2] fp32 flow fields -> fp32 [C, 3]: mean EPE, mean outlier fraction, mean angular error (degrees) per channel."""
+def flow_metrics(flow_ref, flow_cand, outlier_or: bool = False):
+    """[C, ..., 2] fp32 flow fields -> fp32 [C, 3]: mean EPE, mean outlier fraction (Wan: AND of the two tests, LongCat: OR),
+    mean angular error (degrees) per channel."""
     assert flow_ref.shape == flow_cand.shape and flow_ref.dtype == flow_cand.dtype == torch.float32
     assert flow_ref.is_contiguous() and flow_cand.is_contiguous()
     C_ = flow_ref.shape[0]
     out = torch.empty(C_, 3, dtype=torch.float32, device=flow_ref.device)
-    _call("wf_flow_metrics", _p(flow_ref), _p(flow_cand), _p(out), C_, flow_ref.numel() // (2 * C_), _stream())
+    _call("wf_flow_metrics", _p(flow_ref), _p(flow_cand), _p(out), C_, flow_ref.numel() // (2 * C_), int(outlier_or), _stream())
     return out
 
 

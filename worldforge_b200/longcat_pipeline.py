@@ -66,11 +66,20 @@ def selection_policy(scores, step: int, use_distill: bool, max_replace_threshold
     return sorted(out)
 
 
+def similarity_from_means(epe: float, outlier: float, ang: float) -> float:
+    """LongCat's score from the three per-channel means (:229-244): weights 0.4 / 0.4 / 0.2."""
+    clamp = lambda v: min(max(v, 0.0), 1.0)
+    return clamp(1.0 - (0.4 * clamp(epe / 10.0) + 0.4 * clamp(outlier / 0.5) + 0.2 * clamp(ang / 30.0)))
+
+
 class LongCatChannelSelector:
-    def __init__(self, threads: int = 0):
+    def __init__(self, threads: int = 0, device_flow=None):
         self.threads = threads or min(32, os.cpu_count() or 8)
         self._pool = None
         self.last_scores = None
+        # Farneback + the flow metrics on the GPU (wf_farneback_u8 / wf_flow_metrics with the OR-ed outlier test) for frame
+        # sizes the device path covers; WF_FLF_GPU=0 keeps OpenCV on host threads
+        self.device_flow = (os.environ.get("WF_FLF_GPU", "1") == "1") if device_flow is None else bool(device_flow)
 
     def _flows(self, u8: np.ndarray) -> torch.Tensor:
         C, T = u8.shape[:2]
@@ -89,6 +98,12 @@ class LongCatChannelSelector:
         for c in range(C):                    # per-channel min-max (:329-336)
             lib.quantise_u8(enc[0, c], mode=1, out=q[0, c])
             lib.quantise_u8(pred_x0[0, c], mode=1, out=q[1, c])
+        from .flf_select import FlowChannelSelector
+        if self.device_flow and FlowChannelSelector.device_path_covers(*q.shape[-2:]):
+            flows = lib.farneback_u8(q.reshape((2 * C,) + tuple(q.shape[2:])))          # [2C, T-1, H, W, 2] on the device
+            means = lib.flow_metrics(flows[:C].contiguous(), flows[C:].contiguous(), outlier_or=True).cpu()
+            self.last_scores = [similarity_from_means(float(means[c, 0]), float(means[c, 1]), float(means[c, 2])) for c in range(C)]
+            return selection_policy(self.last_scores, step, use_distill, max_replace_threshold)
         both = q.cpu().numpy()
         ref_fl, pred_fl = self._flows(both[0]), self._flows(both[1])
         self.last_scores = [flow_similarity(ref_fl[c], pred_fl[c]) for c in range(C)]
