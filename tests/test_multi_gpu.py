@@ -31,3 +31,4 @@ def test_sharded_paths_on_real_ranks(cuda):
                  "cfg-parallel forwards equal to single-GPU: True",
                  "row-sharded VAE equal to single-GPU: encode True decode True", "rank-sharded FLF scores equal: True"):
         assert out.count(what) == n, (what, out[-4000:])
+    assert out.count("matches single-GPU: True") == n, out[-4000:]          # LongCat 2-D context parallel

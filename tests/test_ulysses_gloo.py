@@ -160,3 +160,56 @@ def test_cfg_parallel_layout(world):
     assert len(ret) == world
     for r in range(world):
         assert ret[r] == ([1.0], [11.0], 1), (r, ret[r])
+
+
+def _cp2d_worker(rank, world, store, split_hw, ret):
+    _init(rank, world, store)
+    try:
+        from worldforge_b200 import ulysses
+        g = torch.Generator().manual_seed(0)
+        T, Hp, Wp, H = 3, 4, 6, 4
+        qkv = torch.randn(T, Hp, Wp, 3 * H * 128, generator=g).to(torch.bfloat16)          # the whole clip's tokens on every rank
+        loc = ulysses.split_2d(qkv, (1, 2), split_hw, rank).reshape(-1, 3 * H * 128)          # this rank's block, (T, H', W') order
+        # split / gather round trip of a [C, T, H, W]-shaped tensor
+        full = torch.arange(2 * T * Hp * Wp, dtype=torch.float32).view(2, T, Hp, Wp)
+        parts = [torch.empty_like(ulysses.split_2d(full, (2, 3), split_hw, rank).contiguous()) for _ in range(world)]
+        dist.all_gather(parts, ulysses.split_2d(full, (2, 3), split_hw, rank).contiguous())
+        assert torch.equal(ulysses.gather_2d(parts, (2, 3), split_hw), full)
+        D = H * 128
+        sp = ulysses.GeneralSequenceParallel()
+        nq = loc.shape[0] // 3                                                               # "noise" queries: the last two frames' tokens
+        seen = {}
+        def attn(q, k, v, out, heads):
+            seen["shapes"] = (tuple(q.shape), tuple(k.shape), heads)
+            _cpu_attn(q, k, v, out, heads)
+        mine = sp.attention_qkv(loc[nq:, :D].contiguous(), loc[:, D:2 * D].contiguous(), loc[:, 2 * D:].contiguous(), H, attn)
+        assert seen["shapes"] == ((world * (loc.shape[0] - nq), D // world), (world * loc.shape[0], D // world), H // world)
+        outs = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(outs, mine)
+        if rank == 0:
+            ret["outs"] = [o.float() for o in outs]
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,split_hw", [(2, (1, 2)), (4, (2, 2))])
+def test_context_parallel_2d_exchange(world, split_hw):
+    """LongCat's 2-D context parallel (context_parallel_util.py:91-121, ulysses_wrapper.py:87-105) host logic: every rank
+    keeps one block of every frame; q (a subset of the local tokens) / k / v are exchanged heads-for-tokens and the result
+    equals single-rank attention of the same queries over ALL keys (dense attention does not depend on the key order)."""
+    from worldforge_b200 import ulysses
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_cp2d_worker, args=(world, _store_file(), split_hw, ret), nprocs=world, join=True)
+    g = torch.Generator().manual_seed(0)
+    T, Hp, Wp, H = 3, 4, 6, 4
+    D = H * 128
+    qkv = torch.randn(T, Hp, Wp, 3 * D, generator=g).to(torch.bfloat16)
+    flat = qkv.reshape(-1, 3 * D)
+    for r in range(world):
+        loc = ulysses.split_2d(qkv, (1, 2), split_hw, r).reshape(-1, 3 * D)
+        nq = loc.shape[0] // 3
+        want = torch.empty(loc.shape[0] - nq, D, dtype=torch.bfloat16)
+        _cpu_attn(loc[nq:, :D].contiguous(), flat[:, D:2 * D].contiguous(), flat[:, 2 * D:].contiguous(), want, H)
+        d = (ret["outs"][r] - want.float()).abs().max().item()
+        assert d <= 2 ** -6, (r, d)                              # same math, keys in another order: bf16 rounding flips only

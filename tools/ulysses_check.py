@@ -65,6 +65,27 @@ a, b = torch.randn(1, 16, 6, 30, 52, generator=g).to(dev), torch.randn(1, 16, 6,
 s1 = flf_select.FlowChannelSelector().scores(a, b)
 s2 = flf_select.FlowChannelSelector(group=dist.group.WORLD, world=world, rank=rank).scores(a, b)
 print(f"rank {rank}/{world}: rank-sharded FLF scores equal: {s1 == s2}", flush=True)
+# LongCat context parallel with the reference's 2-D split (context_parallel_util.py:91-121, 231-243): every rank keeps one
+# block of every frame, heads <-> tokens around self-attention, output blocks gathered - against the single-GPU forward (dense
+# attention: same math with the keys in rank-major order, so equal up to bf16 rounding flips, not bit for bit)
+from worldforge_b200 import longcat
+split = min(([i, world // i] for i in range(1, int(world ** 0.5) + 1) if world % i == 0), key=lambda f: abs(f[0] - f[1]))
+lheads = max(2, world)
+lcfg = longcat.LongCatConfig(hidden_size=128 * lheads, depth=2, num_heads=lheads, caption_channels=32, adaln_tembed_dim=32, frequency_embedding_size=32)
+lm = longcat.WfLongCatTransformer.random_init(lcfg, dev, seed=7)
+lx = torch.randn(1, 16, 3, 16, 32, generator=g).to(dev)
+lts = torch.tensor([[0.0, 700.0, 700.0]], device=dev)
+lctx = torch.randn(1, 1, 8, 32, generator=g).to(torch.bfloat16).to(dev)
+lmask = torch.ones(1, 8, dtype=torch.int64, device=dev); lmask[0, 6:] = 0
+l_single = lm(lx, lts, lctx, encoder_attention_mask=lmask, num_cond_latents=1).clone()
+lm.enable_context_parallel(dist.group.WORLD, split)
+l_cp = lm(lx, lts, lctx, encoder_attention_mask=lmask, num_cond_latents=1)
+torch.cuda.synchronize()
+l_rel = ((l_cp - l_single).norm() / l_single.norm()).item()
+same_everywhere = [torch.empty_like(l_cp) for _ in range(world)]
+dist.all_gather(same_everywhere, l_cp)
+l_ok = l_rel < 5e-3 and all(torch.equal(t_, l_cp) for t_ in same_everywhere)
+print(f"rank {rank}/{world}: LongCat context-parallel forward (split {split[0]}x{split[1]}) matches single-GPU: {l_ok} (rel {l_rel:.2e})", flush=True)
 dist.barrier()
 dist.destroy_process_group()
-sys.exit(0 if md < 1e-2 and vae_ok and s1 == s2 else 1)
+sys.exit(0 if md < 1e-2 and vae_ok and s1 == s2 and l_ok else 1)

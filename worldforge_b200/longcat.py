@@ -108,6 +108,7 @@ class WfLongCatTransformer:
         self.bsa_params = None          # the checkpoint's bsa_params (longcat_video_dit.py:32,56)
         self._bsa_on = False
         self.lora_dict, self.active_loras, self._lora_saved = {}, [], {}
+        self.cp = None                  # enable_context_parallel
 
     def to(self, *a, **k):
         return self
@@ -191,6 +192,27 @@ class WfLongCatTransformer:
         self._lora_saved = {}
         self.active_loras = []
 
+    # ---------------------------------------------------------------------------------- context parallel (2-D split)
+    def enable_context_parallel(self, group, split_hw):
+        """LongCat's context parallel (longcat_video_dit.py:329-332,361-362; context_parallel_util.py:91-121,180-243;
+        ulysses_wrapper.py:87-105): the patch grid of every frame is cut into split_h x split_w blocks, rank r = ih * split_w +
+        iw keeps block (ih, iw) of ALL frames; every token-local op runs on the block, self-attention exchanges heads for
+        tokens (one all-to-all per q / k / v and one back), and the gathered sequence is rank-major - P copies of a
+        (T, H/split_h, W/split_w) volume - which is the geometry the block-sparse attention chunks in (attention.py:60-66), so
+        its selections equal the reference's at the same split.  The final layer's output blocks are gathered back."""
+        import torch.distributed as dist
+        from . import ulysses
+        sh, sw = split_hw
+        world = dist.get_world_size(group)
+        if sh * sw != world:
+            raise lib.WfError(f"cp_split_hw {sh} x {sw} does not match the {world} ranks of the group")
+        if self.cfg.num_heads % world:
+            raise lib.WfError(f"{self.cfg.num_heads} heads do not split over {world} ranks")
+        self.cp = SimpleNamespace(group=group, world=world, rank=dist.get_rank(group), split_hw=(sh, sw),
+                                  sp=ulysses.GeneralSequenceParallel(group))
+        self.cp_split_hw = [sh, sw]
+        return self.cp
+
     # block-sparse self-attention of the 720p refine pass (longcat_video_dit.py:272-278, attention.py:56-67)
     def enable_bsa(self):
         if self.bsa_params is None:
@@ -202,9 +224,10 @@ class WfLongCatTransformer:
     def disable_bsa(self):
         self._bsa_on = False
 
-    def _self_attention(self, q, k, v, out, grid_q, grid_k, sparse: bool):
-        """One _process_attn call (attention.py:49-103): dense, or gating + block-sparse when BSA is enabled."""
-        Hn = self.cfg.num_heads
+    def _self_attention(self, q, k, v, out, grid_q, grid_k, sparse: bool, heads: int = None):
+        """One _process_attn call (attention.py:49-103): dense, or gating + block-sparse when BSA is enabled.  ``heads``: the
+        heads present in q / k / v (all of them, or this rank's share under context parallel)."""
+        Hn = self.cfg.num_heads if heads is None else heads
         if not sparse:
             return lib.attention_bf16(q, k, v, out, Hn)
         bp = self.bsa_params
@@ -385,24 +408,44 @@ class WfLongCatTransformer:
         C, Hn, Fd = c.hidden_size, c.num_heads, c.ffn_dim
         xb = x.to(BF).contiguous()
         _, T, H, W = xb.shape
-        grid = (T, H // 2, W // 2)
+        full_grid = (T, H // 2, W // 2)
+        cp = self.cp
+        if cp is not None:
+            if kv_cache is not None or return_kv:
+                raise lib.WfError("context parallel together with the KV cache is not supported")
+            from . import ulysses
+            sh, sw = cp.split_hw
+            if full_grid[1] % sh or full_grid[2] % sw:
+                raise lib.WfError(f"patch grid {full_grid[1]} x {full_grid[2]} is not a multiple of cp_split_hw {sh} x {sw}")
+            grid = (T, full_grid[1] // sh, full_grid[2] // sw)          # this rank's block of every frame
+        else:
+            grid = full_grid
         per = grid[1] * grid[2]
         N = T * per
         nc = num_cond * per
         Nn = N - nc
         Bf = self._buffers(N, Nn, T)
-        rgrid = (T + cached_frames, grid[1], grid[2])           # RoPE runs over [cached | own] frames (attention.py:171)
-        if rgrid not in self._rope:
-            self._rope[rgrid] = rope_table(rgrid).to(self.device)
+        rgrid = (T + cached_frames, full_grid[1], full_grid[2])  # RoPE runs over [cached | own] frames (attention.py:171)
+        rkey = rgrid if cp is None else (rgrid, cp.split_hw, cp.rank)
+        if rkey not in self._rope:
+            tab = rope_table(rgrid)
+            if cp is not None:                                  # global positions of this rank's block (rope_3d.py:79-86)
+                tab = ulysses.split_2d(tab.view(rgrid[0], rgrid[1], rgrid[2], 64, 2), (1, 2), cp.split_hw, cp.rank).reshape(-1, 64, 2).contiguous()
+            self._rope[rkey] = tab.to(self.device)
         Nc = cached_frames * per                                # cached condition tokens in front of this call's tokens
-        rope_all = self._rope[rgrid]
+        rope_all = self._rope[rkey]
         rope = rope_all[Nc:]
         kv_ret = {}
         if kv_cache is not None:
             kfull = torch.empty(Nc + N, C, dtype=BF, device=self.device)
             vfull = torch.empty(Nc + N, C, dtype=BF, device=self.device)
 
-        lib.patchify(xb, Bf.cols)
+        if cp is None:
+            lib.patchify(xb, Bf.cols)
+        else:                                                   # patch columns of the whole clip, then this rank's block
+            cols_full = torch.empty(full_grid[0] * full_grid[1] * full_grid[2], Bf.cols.shape[1], dtype=BF, device=self.device)
+            lib.patchify(xb, cols_full)
+            Bf.cols.copy_(ulysses.split_2d(cols_full.view(*full_grid, -1), (1, 2), cp.split_hw, cp.rank).reshape(N, -1))
         lib.gemm_bf16(Bf.cols, self.patch_w, self.patch_b, Bf.x, lib.EPI_BF16)
         # per-frame timestep embedding and ALL adaLN tables in fp32: timestep.to(bf16).float() as the reference does (:307,:313)
         ts = timestep.to(BF).to(F32).contiguous()
@@ -431,7 +474,19 @@ class WfLongCatTransformer:
             # in the reference BSA is skipped for single-frame inputs as a whole (shape[0] > 1, attention.py:56)
             sparse = self._bsa_on and T > 1
             gq = lambda t: (t, grid[1], grid[2])
-            if kv_cache is not None:
+            if cp is not None:
+                # Ulysses (ulysses_wrapper.py:87-105): heads <-> tokens; the gathered sequence is P copies of the local volume
+                P = cp.world
+                gP = lambda t: (P * t, grid[1], grid[2])
+                def exchange(qv, kv_, vv, outv, tq, tk):
+                    fn = lambda qf, kf, vf, of, hl: self._self_attention(qf, kf, vf, of, gP(tq), gP(tk), sparse, heads=hl)
+                    outv.copy_(cp.sp.attention_qkv(qv.contiguous(), kv_.contiguous(), vv.contiguous(), Hn, fn))
+                if nc > 0:
+                    exchange(q[:nc], k[:nc], v[:nc], Bf.att[:nc], num_cond, num_cond)
+                    exchange(q[nc:], k, v, Bf.att[nc:], T - num_cond, T)
+                else:
+                    exchange(q, k, v, Bf.att, T, T)
+            elif kv_cache is not None:
                 self._self_attention(q, kfull, vfull, Bf.att, gq(T), gq(T + cached_frames), sparse)
             elif nc > 0:      # condition tokens see only condition tokens; noise tokens see everything (attention.py:124-135)
                 self._self_attention(q[:nc], k[:nc], v[:nc], Bf.att[:nc], gq(num_cond), gq(num_cond), sparse)
@@ -454,6 +509,11 @@ class WfLongCatTransformer:
             lib.gemm_bf16(Bf.ff, b.w2, None, Bf.x, lib.EPI_RESID_BF16, gate=tab[5], gate_rows=per)
 
         shift, scale = mod[6 * c.depth], mod[6 * c.depth + 1]
-        out = torch.empty(c.out_channels, T, H, W, dtype=F32, device=self.device)
+        out = torch.empty(c.out_channels, T, 2 * grid[1], 2 * grid[2], dtype=F32, device=self.device)
         lib.dit_head(Bf.x, scale, shift, self.final_w, self.final_b, out, grid, 1e-6, rows_per_group=per, round_bf16=True)
+        if cp is not None:                                      # gather_cp_2d (longcat_video_dit.py:361-362)
+            import torch.distributed as dist
+            parts = [torch.empty_like(out) for _ in range(cp.world)]
+            dist.all_gather(parts, out, group=cp.group)
+            out = ulysses.gather_2d(parts, (2, 3), cp.split_hw).contiguous()
         return (out, kv_ret) if return_kv else out

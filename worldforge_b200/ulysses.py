@@ -75,6 +75,52 @@ class SequenceParallel:
         return tokens_to_heads_layout(back)
 
 
+def split_2d(x: torch.Tensor, dim_hw, split_hw, rank: int) -> torch.Tensor:
+    """split_tensor_in_cp_2d (longcat_video/context_parallel/context_parallel_util.py:91-121): the ``rank``-th block of ``x``
+    cut into split_h x split_w blocks along dims ``dim_hw``, blocks numbered row-major (h outer, w inner)."""
+    (dh, dw), (sh, sw) = dim_hw, split_hw
+    if x.shape[dh] % sh or x.shape[dw] % sw:
+        raise RuntimeError(f"sizes {x.shape[dh]} x {x.shape[dw]} are not multiples of the split {sh} x {sw}")
+    bh, bw = x.shape[dh] // sh, x.shape[dw] // sw
+    ih, iw = rank // sw, rank % sw
+    return x.narrow(dh, ih * bh, bh).narrow(dw, iw * bw, bw)
+
+
+def gather_2d(parts, dim_hw, split_hw) -> torch.Tensor:
+    """Inverse of split_2d over the list of every rank's block (gather_cp_2d, context_parallel_util.py:180-235)."""
+    (dh, dw), (sh, sw) = dim_hw, split_hw
+    rows = [torch.cat(parts[ih * sw:(ih + 1) * sw], dim=dw) for ih in range(sh)]
+    return torch.cat(rows, dim=dh)
+
+
+class GeneralSequenceParallel(SequenceParallel):
+    """Ulysses exchange for q, k, v of different lengths (LongCat: the noise tokens attend to all tokens, attention.py:124-135)
+    and any local token set: rank r's tokens land at rows [r * Ll, (r+1) * Ll) of the gathered sequence - the rank-major
+    order LongCat's context parallel produces and its block-sparse attention chunks in (attention.py:60-66)."""
+
+    def _scatter_heads(self, x: torch.Tensor) -> torch.Tensor:
+        """[Ll, H*128] (local tokens, all heads) -> [P*Ll, (H/P)*128] (all ranks' tokens rank-major, this rank's heads)."""
+        P = self.world
+        Ll, W = x.shape
+        send = x.reshape(Ll, P, W // P).permute(1, 0, 2).contiguous()            # block d = heads of rank d
+        return self.all_to_all(send).reshape(P * Ll, W // P)
+
+    def _gather_heads(self, x: torch.Tensor) -> torch.Tensor:
+        """[P*Ll, (H/P)*128] -> [Ll, H*128]."""
+        P = self.world
+        Ll = x.shape[0] // P
+        back = self.all_to_all(x.reshape(P, Ll, x.shape[1]).contiguous())      # block d = token shard of rank d
+        return back.permute(1, 0, 2).reshape(Ll, P * x.shape[1])
+
+    def attention_qkv(self, q, k, v, heads: int, attn_fn) -> torch.Tensor:
+        """q [Lq_l, H*128], k / v [Lk_l, H*128] (norm + RoPE applied) -> [Lq_l, H*128]; attn_fn(q, k, v, out, heads_local)."""
+        hl = heads // self.world
+        qf, kf, vf = self._scatter_heads(q), self._scatter_heads(k), self._scatter_heads(v)
+        out = torch.empty_like(qf)
+        attn_fn(qf, kf, vf, out, hl)
+        return self._gather_heads(out)
+
+
 class PeerSetupError(RuntimeError):
     """Raised on EVERY rank when any rank could not build the peer-memory exchange."""
 
