@@ -57,17 +57,20 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--height", type=int, default=480)
-    ap.add_argument("--width", type=int, default=832)
+    ap.add_argument("--height", type=int, default=None, help="default 480 (704 for longcat-refine)")
+    ap.add_argument("--width", type=int, default=None, help="default 832 (1280 for longcat-refine)")
     ap.add_argument("--frames", type=int, default=None, help="default 81 (wan) / 93 (longcat)")
-    ap.add_argument("--model", default="wan", choices=["wan", "longcat"],
+    ap.add_argument("--model", default="wan", choices=["wan", "longcat", "longcat-refine"],
                     help="wan: Wan2.1-I2V-14B guided sampling (BASELINE configs[1], the headline); longcat: LongCat-Video distilled "
-                         "16-step guided i2v (configs[3]; 93 frames unless --frames is given)")
+                         "16-step guided i2v (configs[3]; 93 frames unless --frames is given); longcat-refine: the 480p->720p refine "
+                         "pass with block-sparse attention (configs[4]; 16 latent frames of 704x1280, context parallel under torchrun)")
     ap.add_argument("--layers", type=int, default=None, help="DiT depth (default: 40 for Wan2.1-14B, 48 for LongCat; smaller only for dry runs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the PyTorch + flash-attn comparator leg (N=1 only)")
     a = ap.parse_args()
+    a.height = a.height if a.height is not None else (704 if a.model == "longcat-refine" else 480)
+    a.width = a.width if a.width is not None else (1280 if a.model == "longcat-refine" else 832)
     a.frames = a.frames if a.frames is not None else (81 if a.model == "wan" else 93)
     a.layers = a.layers if a.layers is not None else (40 if a.model == "wan" else 48)
     return a
@@ -482,6 +485,7 @@ def run_longcat(args):
         if rank == 0:
             for k, (n, t_ms) in sorted(summ.items(), key=lambda kv: -kv[1][1]):
                 print(f"[trace] {k:28s} {n:4d} calls {t_ms:10.1f} ms  ({t_ms / ms * 100:5.1f} % of the timed region)", file=sys.stderr, flush=True)
+    rank = 0
     launches = lib.launches
     fwd = dit.calls - calls0 - 2 * W
     attn = list(lib.timed_attention or [])
@@ -512,10 +516,129 @@ def run_longcat(args):
         "flops_per_forward": dit.flops_per_forward(N, (h // 2) * (w // 2), 64), "cpu_baseline": None})
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# LongCat-Video refine pass (BASELINE configs[4]): 480p -> 720p, block-sparse attention, context parallel over the ranks
+# ----------------------------------------------------------------------------------------------------------------
+
+def run_longcat_refine(args):
+    """K steps of generate_refine's loop (pipeline_longcat_video.py:1467-1498) on the engine: one DiT forward with block-sparse
+    self-attention (chunks 4x4x8, sparsity 0.9375) and an Euler step per timestep; no CFG / IRR / FLF / DSG in this pass.
+    16 latent frames (4 clean condition + 12 noise, the BSA padding of :1406-1421) of 704x1280 -> 56 320 tokens (SURVEY.md
+    §8a row a12).  Under torchrun the DiT runs LongCat's 2-D context parallel (`cp_split_hw`, every rank a block of every
+    frame).  e2e: the latents go to pinned host memory and back every step."""
+    import torch
+    import torch.distributed as dist
+    from worldforge_b200 import lib, longcat, longcat_pipeline as wlp
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib.load()
+    cfg = longcat.LongCatConfig(depth=args.layers)
+    dit = longcat.WfLongCatTransformer.random_init(cfg, dev, seed=1234)
+    dit.bsa_params = dict(sparsity=0.9375, cdf_threshold=None, chunk_3d_shape_q=[4, 4, 8], chunk_3d_shape_k=[4, 4, 8])
+    dit.enable_bsa()
+    T, h, w, ncl = 16, args.height // 8, args.width // 8, 4
+    split = [1, 1]
+    if world > 1:
+        split = min(([i, world // i] for i in range(1, int(world ** 0.5) + 1) if world % i == 0), key=lambda f: abs(f[0] - f[1]))
+        if (h // 2) % (4 * split[0]) or (w // 2) % (8 * split[1]):
+            if rank == 0:
+                emit({"metric": "refine_steps_per_sec_longcat_video_720p_bsa", "unavailable": f"{h // 2}x{w // 2} patch grid does not split into "
+                      f"{split[0]}x{split[1]} blocks of whole 4x8 BSA chunks (the reference switches resolution buckets with cp: bukcet_config.py:82-109)"})
+            return
+        dit.enable_context_parallel(dist.group.WORLD, split)
+    N = T * (h // 2) * (w // 2)
+    K, W = args.steps, args.warmup
+    total = W + K
+    g = torch.Generator().manual_seed(42)
+    lat0 = torch.randn(1, 16, T, h, w, generator=g)
+    pe = torch.randn(1, 1, 512, 4096, generator=g).to(torch.bfloat16)
+    pm = torch.zeros(1, 512, dtype=torch.int64); pm[:, :64] = 1
+    host = {k: v.contiguous().pin_memory() for k, v in dict(latents=lat0, pe=pe, pm=pm).items()}
+    devt = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    lat_host = torch.empty_like(host["latents"]).pin_memory()
+    clocks = ClockSampler(local)
+
+    def run(from_host: bool):
+        sched = wlp.WfFlowMatchEulerScheduler(shift=1.0)
+        ts = wlp.refine_schedule(sched, 50, 0.5, device=dev)
+        assert total <= len(ts), f"the refine schedule has {len(ts)} steps"
+        ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+        cnt = dict(h2d=0, d2h=0)
+        latents = devt["latents"].clone()
+
+        def on_step(i, lat):
+            if i == W - 1:
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                lib.launches = 0
+                if not from_host:
+                    clocks.start()
+                ev[0].record()
+            if from_host:
+                lat_host.copy_(lat, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                if i >= W:
+                    cnt["d2h"] += lat_host.numel() * 4
+                if i < total - 1:
+                    lat.copy_(lat_host, non_blocking=True)
+                    devt["pe"].copy_(host["pe"], non_blocking=True); devt["pm"].copy_(host["pm"], non_blocking=True)
+                    if i >= W - 1:
+                        cnt["h2d"] += lat_host.numel() * 4 + host["pe"].numel() * 2 + host["pm"].numel() * 8
+            if i == total - 1:
+                ev[1].record()
+        wlp.refine_loop(dit, sched, latents, devt["pe"], devt["pm"], ncl, ts[:total], on_step=on_step)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = ev[0].elapsed_time(ev[1])
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, cnt["h2d"] // max(K, 1), cnt["d2h"] // max(K, 1)
+
+    ms, _, _ = run(False)
+    clk = clocks.stop()
+    launches = lib.launches
+    e2e = None
+    if not args.no_e2e:
+        ms_e, h2d, d2h = run(True)
+        e2e = {"value": K / (ms_e / 1000.0), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+    if rank != 0:
+        return
+    pk = peaks()
+    C, Fd, per = cfg.hidden_size, cfg.ffn_dim, (h // 2) * (w // 2)
+    Nn, ctx = N - ncl * per, 64
+    n_sel = int((1 - 0.9375) * (N // 128))
+    # algorithmic FLOPs of one forward: token-side GEMMs, cross-attention, and the SELECTED blocks of the sparse self-attention
+    gemm = cfg.depth * (2 * N * (4 * C * C + 3 * C * Fd) + 2 * Nn * 2 * C * C + 2 * ctx * 2 * C * C + 4 * Nn * ctx * C)
+    sparse = cfg.depth * 4.0 * C * 128 * 128 * n_sel * (N // 128)
+    step_ms = ms / K
+    ach = (gemm + sparse) / world / (step_ms / 1000.0) / 1e12
+    emit({
+        "metric": "refine_steps_per_sec_longcat_video_720p_16lf_bsa", "value": K / (ms / 1000.0), "unit": UNIT, "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"LongCat-Video 13.6B refine pass {args.height}x{args.width}, 16 latent frames (4 condition + 12 noise), block-sparse "
+                               f"self-attention (4x4x8 chunks, sparsity 0.9375: {n_sel} of {N // 128} key chunks per query chunk), Euler steps from t = 0.5",
+                   "tokens": N, "dit_layers": cfg.depth, "parallelism": "single GPU" if world == 1 else f"context parallel cp_split_hw {split[0]}x{split[1]} (NCCL all-to-all)",
+                   "l2_policy": "inputs larger than L2 (27 GB of weights streamed per forward)"},
+        "clocks": clk, "gpu_launches": launches, "e2e": e2e,
+        "roofline": {"kernel": "DiT forward (tcgen05 GEMMs + block-sparse attention), whole step", "bound": "tensor", "achieved": ach, "peak": pk["bf16"],
+                     "unit": "TFLOP/s", "frac": ach / pk["bf16"], "traffic": None, "peak_source": pk["src"] + " sustained cuBLAS bf16",
+                     "flops_per_forward": gemm + sparse},
+        "cpu_baseline": None})
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.model == "longcat-refine":
+        run_longcat_refine(args)
     elif args.model == "longcat":
         run_longcat(args)
     else:
