@@ -415,7 +415,7 @@ def run_longcat(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world != 1:
         if int(os.environ.get("RANK", "0")) == 0:
-            emit({"metric": "denoising_steps_per_sec_longcat_video", "unavailable": "LongCat context parallelism is not wired (DESIGN.md §7): run with --gpus 1"})
+            emit({"metric": "denoising_steps_per_sec_longcat_video", "unavailable": "the guided LongCat i2v loop is benchmarked on one GPU (run with --gpus 1); its context parallel is measured with --model longcat-refine"})
         return
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
