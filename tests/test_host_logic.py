@@ -275,3 +275,21 @@ def test_longcat_lora_surface_folds_and_restores():
     with pytest.raises(Exception):
         m.load_lora(lora_for({"blocks.0.attn.q_norm": (128, 128, 1)}, 7), "bad", lora_network_dim=r)
         m.enable_loras(["bad"])
+
+
+def test_longcat_continuation_schedule_host():
+    """generate_vc's timestep surgery (pipeline_longcat_video.py:1151-1164, enhance_hf): engine scheduler vs oracle scheduler on
+    the host - the head of the standard schedule above t = 500, then ten uniform steps 500 -> 50, sigmas = t / 1000 + a final 0."""
+    import torch
+    from oracle import longcat_sched as ols
+    from worldforge_b200 import longcat_pipeline as lp
+    so, sw = ols.OracleEuler(1000, 1.0), lp.WfFlowMatchEulerScheduler(1000, 1.0)
+    for n in (12, 50):
+        a, b = ols.vc_timesteps(so, n, enhance_hf=True), lp.vc_timesteps(sw, n, enhance_hf=True)
+        assert torch.equal(a, b) and torch.equal(so.sigmas, sw.sigmas)
+        assert a[-10:].tolist() == [500.0, 450.0, 400.0, 350.0, 300.0, 250.0, 200.0, 150.0, 100.0, 50.0] and bool((a[:-10] > 500).all())
+        assert float(sw.sigmas[-1]) == 0.0 and len(sw.sigmas) == len(b) + 1
+    a, b = ols.vc_timesteps(so, 16, use_distill=True, enhance_hf=False), lp.vc_timesteps(sw, 16, use_distill=True, enhance_hf=False)
+    assert torch.equal(a, b) and len(a) == 16
+    with pytest.raises(Exception):
+        lp.vc_timesteps(sw, 16, use_distill=True, enhance_hf=True)
