@@ -134,6 +134,63 @@ def ref_generate_i2v(distill: bool):
     return dict(prepared=prepared[0], dit_inputs=torch.stack(seen), final=final.clone(), flf=[len(c) for _, c in getattr(sched, "flf_log", [])])
 
 
+VC_OUT = os.path.join(os.path.dirname(OUT), "longcat_vc_golden.pt")
+VC_STEPS = 12
+
+
+def ref_generate_vc(use_kv_cache: bool):
+    """LongCatVideoPipeline.generate_vc of the reference (pipeline_longcat_video.py:1010-1270), UNMODIFIED, over the oracle DiT /
+    VAE and the reference's scheduler: 9 frames of which 5 condition (2 clean latent frames + 1 noise frame), CFG-zero,
+    enhance_hf schedule (6 steps above t = 500 of the 12-step schedule + the 10-step uniform tail), with and without the KV
+    cache.  Handed in as for generate_i2v: prompt embeddings, the 64 x 96 size; the VAE adapter's posterior sample is its mode
+    and it evaluates in fp32 (the pipeline hands it a bf16 clip)."""
+    from oracle import adapters, longcat_dit, make_golden as mg, ref_shim, wan_vae
+    pm_mod = ref_shim.load_longcat_pipeline_module()
+    sm = ref_shim.load_longcat_scheduler_module()
+    cfg, vcfg = longcat_dit.LongCatConfig(**mg.LC_SCHED_DIT), wan_vae.VaeConfig(dim=8)
+    P, PV = longcat_dit.init_params(cfg, 3), wan_vae.init_params(vcfg, 2)
+    inp, pe, pmask = mg.longcat_sched_inputs()
+    table = {"neg": (pe[0, 0], int(pmask[0].sum())), "pos": (pe[1, 0], int(pmask[1].sum()))}
+    enc = ref_shim.FixedTextEncoder(table, pe.shape[2], pe.shape[3])
+    vae = adapters.OracleVAE(PV, vcfg)
+    vae.config.scale_factor_temporal, vae.config.scale_factor_spatial = 4, 8
+    enc_fn = vae.encode
+    def encode(x):
+        o = enc_fn(x.float())
+        o.latent_dist.sample = lambda generator=None: o.latent_dist.mode()
+        return o
+    vae.encode = encode
+    dit = adapters.OracleLongCatDit(P, cfg, amp=True)
+    seen = []
+    call = dit.__call__
+    class Rec:
+        dtype, config, cp_split_hw = dit.dtype, dit.config, dit.cp_split_hw
+        def __call__(self, hidden_states, **kw):
+            seen.append(hidden_states[-1].clone())
+            return call(hidden_states=hidden_states, **kw)
+    sched = sm.FlowMatchEulerDiscreteScheduler(num_train_timesteps=1000, shift=1.0)
+    pipe = pm_mod.LongCatVideoPipeline(tokenizer=enc.tokenizer, text_encoder=enc, vae=vae, scheduler=sched, dit=Rec())
+    pipe.device = "cpu"
+    pipe.get_condition_shape = lambda video, resolution, scale_factor_spatial=32: (64, 96)
+    prepared = []
+    prep = pipe.prepare_latents
+    def prepare_latents(**kw):
+        out = prep(**kw)
+        prepared.append(out.clone())
+        return out
+    pipe.prepare_latents = prepare_latents
+    video = inp.video_ref * 2 - 1                                       # [1,3,9,64,96] in [-1,1]
+    final = pipe.generate_vc(video=video, prompt="pos", negative_prompt="neg", num_frames=9, num_cond_frames=5,
+                             num_inference_steps=VC_STEPS, guidance_scale=4.0, generator=torch.Generator().manual_seed(42),
+                             output_type="latent", max_sequence_length=pe.shape[2], use_kv_cache=use_kv_cache, enhance_hf=True)
+    return dict(prepared=prepared[0], dit_inputs=[t.clone() for t in seen], final=final.clone(), timesteps=sched.timesteps.clone(),
+                sigmas=sched.sigmas.clone())
+
+
+if __name__ == "__main__" and len(__import__("sys").argv) > 1 and __import__("sys").argv[1] == "vc":
+    torch.save({"kv": ref_generate_vc(True), "nokv": ref_generate_vc(False)}, VC_OUT)
+    print("wrote", VC_OUT, os.path.getsize(VC_OUT), "bytes")
+
 if __name__ == "__main__" and len(__import__("sys").argv) > 1 and __import__("sys").argv[1] == "i2v":
     torch.save({"standard": ref_generate_i2v(False), "distill": ref_generate_i2v(True)}, I2V_OUT)
     print("wrote", I2V_OUT, os.path.getsize(I2V_OUT), "bytes")

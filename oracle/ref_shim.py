@@ -405,6 +405,13 @@ class _VideoProcessor:
             raise NotImplementedError("shim VideoProcessor: pass a [B,3,H,W] tensor in [-1,1] of the target size")
         return image
 
+    def preprocess_video(self, video, height=None, width=None):
+        """[B,3,F,H,W] float tensor already in [-1,1] at the target size (what diffusers returns for such an input)."""
+        if not (isinstance(video, torch.Tensor) and video.dim() == 5 and video.shape[-2:] == (height, width)
+                and float(video.min()) < 0 and float(video.abs().max()) <= 1):
+            raise NotImplementedError("shim VideoProcessor: pass a [B,3,F,H,W] tensor in [-1,1] of the target size")
+        return video
+
     def postprocess_video(self, video, output_type="np"):
         raise NotImplementedError("shim VideoProcessor: run the pinned pipelines with output_type='latent'")
 
