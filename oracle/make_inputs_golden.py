@@ -187,6 +187,67 @@ def ref_generate_vc(use_kv_cache: bool):
                 sigmas=sched.sigmas.clone())
 
 
+REFINE_OUT = os.path.join(os.path.dirname(OUT), "longcat_refine_call_golden.pt")
+
+
+def refine_inputs():
+    g = torch.Generator().manual_seed(31)
+    stage1 = torch.randint(0, 256, (17, 40, 40, 3), generator=g, dtype=torch.uint8)        # 17 low-resolution frames
+    image = torch.rand(1, 3, 128, 128, generator=g) * 2 - 1                                 # first frame at the target size
+    return stage1, image
+
+
+def ref_generate_refine():
+    """LongCatVideoPipeline.generate_refine of the reference (pipeline_longcat_video.py:1271-1511), UNMODIFIED, over the oracle
+    DiT (block-sparse attention on) / VAE and the reference's scheduler: upsampling chain, BSA padding (1 condition frame ->
+    4 condition latents, 16 noise frames -> 4 noise latents), VAE encode, noising to t = 0.6, Euler steps from there.  Handed in: the
+    prompt embeddings and the 128 x 128 target size; the VAE adapter evaluates in fp32 and its posterior sample is its mode."""
+    from oracle import adapters, longcat_dit, make_golden as mg, ref_shim, wan_vae
+    pm_mod = ref_shim.load_longcat_pipeline_module()
+    pm_mod.torch_gc = lambda: None                 # the module's helper empties the CUDA cache (:24-28); there is no CUDA here
+    sm = ref_shim.load_longcat_scheduler_module()
+    cfg, vcfg = longcat_dit.LongCatConfig(**mg.LC_SCHED_DIT), wan_vae.VaeConfig(dim=8)
+    P, PV = longcat_dit.init_params(cfg, 3), wan_vae.init_params(vcfg, 2)
+    _, pe, pmask = mg.longcat_sched_inputs()
+    enc = ref_shim.FixedTextEncoder({"pos": (pe[1, 0], int(pmask[1].sum()))}, pe.shape[2], pe.shape[3])
+    vae = adapters.OracleVAE(PV, vcfg)
+    vae.config.scale_factor_temporal, vae.config.scale_factor_spatial = 4, 8
+    enc_fn = vae.encode
+    def encode(x):
+        o = enc_fn(x.float())
+        o.latent_dist.sample = lambda generator=None: o.latent_dist.mode()
+        return o
+    vae.encode = encode
+    dit = adapters.OracleLongCatDit(P, cfg, amp=True, bsa=dict(mg.LC_BSA))
+    seen = []
+    call = dit.__call__
+    class Rec:
+        dtype, config, cp_split_hw = dit.dtype, dit.config, dit.cp_split_hw
+        def __call__(self, hidden_states, **kw):
+            seen.append(hidden_states[-1].clone())
+            return call(hidden_states=hidden_states, **kw)
+    sched = sm.FlowMatchEulerDiscreteScheduler(num_train_timesteps=1000, shift=1.0)
+    pipe = pm_mod.LongCatVideoPipeline(tokenizer=enc.tokenizer, text_encoder=enc, vae=vae, scheduler=sched, dit=Rec())
+    pipe.device = "cpu"
+    pipe.get_condition_shape = lambda video, resolution, scale_factor_spatial=32: (128, 128)
+    prepared = []
+    prep = pipe.prepare_latents
+    def prepare_latents(**kw):
+        out = prep(**kw)
+        prepared.append(out.clone())
+        return out
+    pipe.prepare_latents = prepare_latents
+    stage1, image = refine_inputs()
+    final = pipe.generate_refine(image=image, prompt="pos", stage1_video=list(stage1.numpy()), num_cond_frames=1, num_inference_steps=10,
+                                 generator=torch.Generator().manual_seed(42), output_type="latent", max_sequence_length=pe.shape[2],
+                                 t_thresh=0.6, spatial_refine_only=True)
+    return dict(prepared=prepared[0], dit_inputs=[t.clone() for t in seen], final=final.clone(), timesteps=sched.timesteps.clone())
+
+
+if __name__ == "__main__" and len(__import__("sys").argv) > 1 and __import__("sys").argv[1] == "refine":
+    torch.save(ref_generate_refine(), REFINE_OUT)
+    print("wrote", REFINE_OUT, os.path.getsize(REFINE_OUT), "bytes")
+
 if __name__ == "__main__" and len(__import__("sys").argv) > 1 and __import__("sys").argv[1] == "vc":
     torch.save({"kv": ref_generate_vc(True), "nokv": ref_generate_vc(False)}, VC_OUT)
     print("wrote", VC_OUT, os.path.getsize(VC_OUT), "bytes")
