@@ -96,3 +96,39 @@ def select_channels(pred_x0: torch.Tensor, fused: torch.Tensor, step: int) -> Li
     if step < 2:                       # :364
         return []
     return policy(channel_scores(pred_x0, fused), step)
+
+
+def presize_guidance(video_ref: torch.Tensor, mask: torch.Tensor, target_shape):
+    """Bring the warped clip [b,3,F,h,w] and its mask [b,c,F,h,w] to the decoded clip's shape (:1297-1371): batch
+    repeated, the clip resized in the plane with bilinear taps (align_corners=False, every frame of every channel on its
+    own, :1316-1324), the mask reduced to its first channel (:1342-1343) and resized with nearest taps (:1354-1361).  A
+    frame-count mismatch reaches ``F.interpolate`` with a 4-D tensor and a 3-element size (:1326-1334, :1363-1370), which
+    torch rejects with a ValueError - the reference cannot resample in time either, so neither does this."""
+    import torch.nn.functional as F
+    B, C, T, H, W = (int(v) for v in target_shape)
+    if tuple(video_ref.shape) == (B, C, T, H, W) and tuple(mask.shape[-2:]) != (H, W):
+        # the reference imports F inside the clip branch only (:1301): a mask that needs resizing next to a clip that does not
+        # dies with UnboundLocalError at :1356
+        raise ValueError("mask needs a spatial resize but video_ref does not: the reference fails here (F is bound at :1301 only)")
+    if tuple(video_ref.shape) != (B, C, T, H, W):
+        if video_ref.shape[0] != B:
+            video_ref = video_ref.repeat(B, 1, 1, 1, 1)
+        b, c, f, h, w = video_ref.shape
+        if (h, w) != (H, W):
+            video_ref = F.interpolate(video_ref.reshape(b * c * f, h, w).unsqueeze(1), size=(H, W), mode="bilinear",
+                                      align_corners=False).squeeze(1).reshape(b, c, f, H, W)
+        if f != T:
+            raise ValueError(f"video_ref has {f} frames, the decoded clip {T}: the reference's temporal branch "
+                             "(:1326-1334) calls F.interpolate with a 4-D input and a 3-D size and raises")
+    if tuple(mask.shape) != (B, 1, T, H, W):
+        if mask.shape[0] != B:
+            mask = mask.repeat(B, 1, 1, 1, 1)
+        if mask.shape[1] != 1:
+            mask = mask[:, 0:1]
+        b, c, f, h, w = mask.shape
+        if (h, w) != (H, W):
+            mask = F.interpolate(mask.reshape(b * c * f, h, w).unsqueeze(1), size=(H, W), mode="nearest").squeeze(1) \
+                .reshape(b, c, f, H, W)
+        if f != T:
+            raise ValueError(f"mask has {f} frames, the decoded clip {T}: the reference's temporal branch (:1363-1370) raises")
+    return video_ref, mask

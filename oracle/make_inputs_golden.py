@@ -259,3 +259,62 @@ if __name__ == "__main__" and len(__import__("sys").argv) > 1 and __import__("sy
 if __name__ == "__main__" and len(__import__("sys").argv) > 1 and __import__("sys").argv[1] == "kv":
     torch.save(ref_kv(), KV_OUT)
     print("wrote", KV_OUT, os.path.getsize(KV_OUT), "bytes")
+
+
+# ---- fuse_latents with a mis-sized clip / mask (scheduling_unipc_multistep_clean.py:1297-1371) -----------------------
+PRESIZE_OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "presize_golden.pt")
+
+
+class RecordingVAE:
+    """decode() hands back a fixed clip, encode() records the fused clip it is given: isolates the reference's resize +
+    blend from the networks."""
+
+    def __init__(self, decoded, z_dim=16):
+        from types import SimpleNamespace
+        from oracle import wan_vae
+        self.decoded, self.fused = decoded, None
+        self.config = SimpleNamespace(z_dim=z_dim, latents_mean=list(wan_vae.LATENTS_MEAN[:z_dim]), latents_std=list(wan_vae.LATENTS_STD[:z_dim]))
+
+    def decode(self, z, return_dict=False):
+        return (self.decoded.clone(),)
+
+    def encode(self, x):
+        from types import SimpleNamespace
+        self.fused = x.clone()
+        lat = torch.zeros(1, self.config.z_dim, (x.shape[2] - 1) // 4 + 1, x.shape[3] // 8, x.shape[4] // 8)
+        return SimpleNamespace(latent_dist=SimpleNamespace(mode=lambda: lat))
+
+
+def presize_inputs():
+    g = torch.Generator().manual_seed(77)
+    dec = torch.rand(1, 3, 5, 32, 48, generator=g) * 2 - 1
+    x0 = torch.randn(1, 16, 2, 4, 6, generator=g)
+    cases = {
+        "up": (torch.rand(1, 3, 5, 20, 30, generator=g), (torch.rand(1, 1, 5, 20, 30, generator=g) > 0.5).float()),
+        "down_odd": (torch.rand(1, 3, 5, 45, 67, generator=g), torch.rand(1, 1, 5, 45, 67, generator=g)),
+        "mask_3ch": (torch.rand(1, 3, 5, 32, 48, generator=g), torch.rand(1, 3, 5, 32, 48, generator=g)),
+        "both_mask_3ch": (torch.rand(1, 3, 5, 24, 40, generator=g), torch.rand(1, 3, 5, 16, 24, generator=g)),
+        "clip_only": (torch.rand(1, 3, 5, 64, 96, generator=g), torch.rand(1, 1, 5, 32, 48, generator=g)),
+    }
+    return dec, x0, cases
+
+
+def ref_presize():
+    """The reference scheduler's own fuse_latents on clips / masks that do not match the decoded clip: what it hands to
+    vae.encode (the resized clip blended with the decoded one)."""
+    from oracle import ref_shim
+    sm = ref_shim.load_scheduler_module()
+    s = sm.UniPCMultistepScheduler(num_train_timesteps=1000, solver_order=2, prediction_type="flow_prediction",
+                                   use_flow_sigmas=True, flow_shift=3.0)
+    dec, x0, cases = presize_inputs()
+    out = {}
+    for name, (clip, mask) in cases.items():
+        vae = RecordingVAE(dec)
+        s.fuse_latents(x0, clip, mask, vae=vae)
+        out[name] = vae.fused
+    return out
+
+
+if __name__ == "__main__" and len(__import__("sys").argv) > 1 and __import__("sys").argv[1] == "presize":
+    torch.save(ref_presize(), PRESIZE_OUT)
+    print("wrote", PRESIZE_OUT, os.path.getsize(PRESIZE_OUT), "bytes")

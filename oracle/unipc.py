@@ -179,8 +179,7 @@ class OracleUniPC:
         lat = (pred_x0 / inv_std + mean).to(torch.float32)
         dec = vae.decode(lat, return_dict=False)[0]
         if video_ref.shape != dec.shape or mask.shape != (dec.shape[0], 1) + tuple(dec.shape[2:]):
-            raise ValueError("oracle: reference/mask must be pre-sized to the decoded clip "
-                             "(the reference's interpolate branch :1300-1371 is out of scope)")
+            video_ref, mask = _flf.presize_guidance(video_ref, mask, dec.shape)       # :1300-1371
         ref = video_ref.to(dec.device, dec.dtype)
         m = mask.to(dec.device, dec.dtype)
         ref = 2.0 * ref - 1.0

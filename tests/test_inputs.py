@@ -71,3 +71,79 @@ def test_device_frame_stacking(cuda):
     assert torch.equal(got.cpu(), torch.from_numpy(oin.stack_frames(frames.numpy())))
     want = torch.stack([torch.tensor(np.array(f)).permute(2, 0, 1).float() / 255.0 for f in frames.numpy()]).unsqueeze(0).permute(0, 2, 1, 3, 4)
     assert torch.equal(got.cpu(), want)                              # the reference's own expression (:232-238)
+
+
+# ---- fuse_latents' resize branch (scheduling_unipc_multistep_clean.py:1297-1371) ----------------------------------------------
+PRESIZE = torch.load(os.path.join(os.path.dirname(__file__), "golden", "presize_golden.pt"), weights_only=False)
+
+
+def _oracle_fused(clip, mask):
+    from oracle import unipc
+    dec, x0, _ = mig.presize_inputs()
+    vae = mig.RecordingVAE(dec)
+    unipc.OracleUniPC(flow_shift=3.0).fuse_latents(x0, clip, mask, vae=vae)
+    return vae.fused
+
+
+def test_oracle_resize_branch_matches_reference_fixture():
+    """What the reference's own fuse_latents hands to vae.encode when the warped clip / mask are not the decoded clip's size
+    (bilinear clip, nearest mask, first mask channel), bit for bit."""
+    _, _, cases = mig.presize_inputs()
+    assert set(cases) == set(PRESIZE)
+    for name, (clip, mask) in cases.items():
+        assert torch.equal(_oracle_fused(clip, mask), PRESIZE[name]), name
+
+
+@pytest.mark.skipif(not os.path.exists(mig.REF), reason="/root/reference is not mounted")
+def test_oracle_resize_branch_matches_live_reference_and_fails_where_it_fails():
+    live = mig.ref_presize()
+    for name, want in PRESIZE.items():
+        assert torch.equal(live[name], want), name
+    from oracle import ref_shim
+    sm = ref_shim.load_scheduler_module()
+    s = sm.UniPCMultistepScheduler(num_train_timesteps=1000, solver_order=2, prediction_type="flow_prediction",
+                                   use_flow_sigmas=True, flow_shift=3.0)
+    dec, x0, _ = mig.presize_inputs()
+    bad = {"frames": (torch.rand(1, 3, 3, 32, 48), torch.rand(1, 1, 3, 32, 48)),          # temporal branch: F.interpolate rejects it
+           "mask_only": (torch.rand(1, 3, 5, 32, 48), torch.rand(1, 1, 5, 16, 24))}       # F unbound outside the clip branch
+    for name, (clip, mask) in bad.items():
+        with pytest.raises((ValueError, UnboundLocalError)):
+            s.fuse_latents(x0, clip, mask, vae=mig.RecordingVAE(dec))
+        with pytest.raises(ValueError):
+            _oracle_fused(clip, mask)
+
+
+def test_engine_presize_equals_oracle_and_scheduler_keeps_the_resized_pair(monkeypatch):
+    """worldforge_b200.inputs.presize_guidance against the oracle; WfUniPCScheduler.fuse_latents' host path (kernels stood in
+    for by their torch expressions) reproduces the reference fixture and resizes a given pair once."""
+    import contextlib
+    from oracle import flf
+    from worldforge_b200 import inputs, lib, scheduler as wsched
+    dec, x0, cases = mig.presize_inputs()
+    for name, (clip, mask) in cases.items():
+        a, b = inputs.presize_guidance(clip, mask, dec.shape)
+        c, d = flf.presize_guidance(clip, mask, dec.shape)
+        assert torch.equal(a, c) and torch.equal(b, d) and a.shape == dec.shape and b.shape == (1, 1) + dec.shape[2:], name
+    for clip, mask in ((torch.rand(1, 3, 3, 32, 48), torch.rand(1, 1, 3, 32, 48)), (torch.rand(1, 3, 5, 32, 48), torch.rand(1, 1, 5, 16, 24))):
+        with pytest.raises(ValueError):
+            inputs.presize_guidance(clip, mask, dec.shape)
+
+    calls = []
+    real = inputs.presize_guidance
+    monkeypatch.setattr(inputs, "presize_guidance", lambda *a: (calls.append(1), real(*a))[1])
+    monkeypatch.setattr(lib, "latent_denorm", lambda x, m, s: x.float())
+    monkeypatch.setattr(lib, "flf_blend", lambda d, r, m: (2.0 * r - 1.0) * m + d * (1 - m))
+    monkeypatch.setattr(lib, "latent_norm_replace", lambda enc, x, m, s, ch: enc)
+    monkeypatch.setattr(lib, "phase", lambda name: contextlib.nullcontext())
+    s = wsched.WfUniPCScheduler(flow_shift=3.0)
+    s.set_timesteps(4)
+    for name, (clip, mask) in cases.items():
+        vae = mig.RecordingVAE(dec)
+        n = len(calls)
+        for _ in range(3):
+            s.fuse_latents(x0, clip, mask, vae=vae)
+            assert torch.equal(vae.fused, PRESIZE[name]), name
+        assert len(calls) == n + 1, name                       # resized on the first call only
+        mask.add_(0.0)                                          # an in-place edit of a source invalidates the kept pair
+        s.fuse_latents(x0, clip, mask, vae=vae)
+        assert len(calls) == n + 2

@@ -75,3 +75,39 @@ def prepare_mask(masks_u8: torch.Tensor, soften: bool = True, transition_distanc
     """uint8 [F,H,W] -> mask [1,1,F,H,W] fp32 (:244-251)."""
     m = soften_mask(masks_u8, transition_distance, decay_type) if soften else mask_from_u8(masks_u8)
     return m.unsqueeze(0).unsqueeze(0)
+
+
+def presize_guidance(video_ref: torch.Tensor, mask: torch.Tensor, target_shape):
+    """The resize branch of ``fuse_latents`` (utils/scheduling_unipc_multistep_clean.py:1297-1371): a warped clip
+    [b,3,F,h,w] / mask [b,c,F,h,w] whose size is not the decoded clip's is brought to it - batch repeated, the clip
+    resampled in the plane with bilinear taps (align_corners=False), the mask cut to its first channel and resampled with
+    nearest taps.  Runs once per clip (the scheduler keeps the result), on whatever device the tensors live on, with
+    torch's own resampling - the op the reference calls, so the values are the reference's.  As in the reference, a
+    different frame count is an error (its temporal branch hands ``F.interpolate`` a 4-D tensor with a 3-element size,
+    :1326-1334), and so is a mask that needs resampling next to a clip that does not (``F`` is bound at :1301 only)."""
+    import torch.nn.functional as F
+    B, C, T, H, W = (int(v) for v in target_shape)
+    if video_ref.dim() != 5 or mask.dim() != 5:
+        raise ValueError(f"video_ref / mask must be 5-D, got {tuple(video_ref.shape)} / {tuple(mask.shape)}")
+    if tuple(video_ref.shape) == (B, C, T, H, W) and tuple(mask.shape[-2:]) != (H, W):
+        raise ValueError(f"mask {tuple(mask.shape)} needs a spatial resize to {(H, W)} but video_ref does not: "
+                         "the reference fails on this input (scheduling…:1301, :1356)")
+    if video_ref.shape[2] != T or mask.shape[2] != T:
+        raise ValueError(f"video_ref / mask have {video_ref.shape[2]} / {mask.shape[2]} frames, the decoded clip {T}: "
+                         "the reference cannot resample in time (scheduling…:1326-1334, :1363-1370 raise)")
+    if tuple(video_ref.shape) != (B, C, T, H, W):
+        if video_ref.shape[0] != B:
+            video_ref = video_ref.repeat(B, 1, 1, 1, 1)
+        b, c, f, h, w = video_ref.shape
+        if (h, w) != (H, W):
+            video_ref = F.interpolate(video_ref.reshape(b * c * f, 1, h, w), size=(H, W), mode="bilinear",
+                                      align_corners=False).reshape(b, c, f, H, W)
+    if tuple(mask.shape) != (B, 1, T, H, W):
+        if mask.shape[0] != B:
+            mask = mask.repeat(B, 1, 1, 1, 1)
+        if mask.shape[1] != 1:
+            mask = mask[:, 0:1]
+        b, c, f, h, w = mask.shape
+        if (h, w) != (H, W):
+            mask = F.interpolate(mask.reshape(b * c * f, 1, h, w), size=(H, W), mode="nearest").reshape(b, c, f, H, W)
+    return video_ref.contiguous(), mask.contiguous()

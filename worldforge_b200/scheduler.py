@@ -145,6 +145,7 @@ class WfUniPCScheduler:
         self.flf_log = []                 # (step, channels) per FLF selection, for parity tests
         self.fuse_calls = 0
         self._selector = None
+        self._presized = None             # (key, clip, mask, (resized clip, resized mask)) of the last mis-sized guidance pair
 
     @classmethod
     def from_config(cls, config, **kw):
@@ -182,6 +183,7 @@ class WfUniPCScheduler:
         self._step_index = None
         self._begin_index = None
         self._selector = None
+        self._presized = None
         self.resample_sigmas = self.sigmas[:-1].clone()
         self.resample_timesteps = torch.floor(self.resample_sigmas * n_train).to(torch.int64)
         self._resample_timesteps_dev = self.resample_timesteps.to(device) if device is not None else self.resample_timesteps
@@ -257,8 +259,13 @@ class WfUniPCScheduler:
         with lib.phase("flf.vae_decode"):
             dec = vae.decode(z, return_dict=False)[0]
         if tuple(video_latents.shape) != tuple(dec.shape) or tuple(mask.shape) != (dec.shape[0], 1) + tuple(dec.shape[2:]):
-            raise ValueError("video_ref / mask must be pre-sized to the decoded clip "
-                             f"(got {tuple(video_latents.shape)}, {tuple(mask.shape)}, decoded {tuple(dec.shape)})")
+            # the reference resizes a mis-sized clip / mask on every call (:1300-1371); here once per (clip, mask) pair
+            key = (video_latents.data_ptr(), video_latents._version, mask.data_ptr(), mask._version, tuple(dec.shape))
+            if self._presized is None or self._presized[0] != key:
+                from . import inputs
+                sized = inputs.presize_guidance(video_latents.to(dec.device), mask.to(dec.device), dec.shape)
+                self._presized = (key, video_latents, mask, sized)       # the sources are held: their addresses stay theirs
+            video_latents, mask = self._presized[3]
         ref = video_latents if video_latents.dtype == torch.float32 else video_latents.to(torch.float32)
         m = mask if mask.dtype == torch.float32 else mask.to(torch.float32)
         fused = lib.flf_blend(dec.contiguous(), ref.contiguous(), m.contiguous())
