@@ -52,7 +52,7 @@ class _StandIn(wvae.WfWanVAE):
 
 
 @pytest.mark.parametrize("seg,h_in,out_scale", [(ENC, 96, 1), (DEC, 12, 8)])
-@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
 def test_row_slabs_reproduce_the_full_evaluation(seg, h_in, out_scale, world):
     """A rank's slab - the rows need[0] with zero padding at the slab edges (what the conv kernels do), re-cut before
     every resampling layer - yields the rank's output rows exactly."""
@@ -130,7 +130,7 @@ class _StagedStandIn(_StandIn):
 
 
 @pytest.mark.parametrize("cuts", [False, True])
-@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
 def test_encode_stages_rows_frames_rows(world, cuts, monkeypatch):
     """sharded_stages('enc'): [rows | frames | rows] with a gather between stages reproduces the unsharded evaluation;
     with ``level_cuts`` the row stages additionally end after every downsampling layer (one stage per resolution level)."""

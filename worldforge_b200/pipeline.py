@@ -192,7 +192,8 @@ class WfWanI2VPipeline:
                  guide_steps: int = 20, omega: float = 1.8, omega_resample: float = 1.0, resample_round: int = 20,
                  use_pca_channel_selection: bool = False, static: bool = False, on_step=None, device="cuda"):
         if prompt_embeds is None or image_embeds is None:
-            raise ValueError("pass prompt_embeds / negative_prompt_embeds / image_embeds (the encoders are outside the hot path)")
+            raise ValueError("pass prompt_embeds / negative_prompt_embeds / image_embeds: tokenisation and CLIP preprocessing stay with the "
+                             "caller; worldforge_b200.encoders.t5_prompt_embeds / WfCLIPVisionEncoder compute the embeddings from token ids / pixels")
         if num_frames % 4 != 1:
             num_frames = max(num_frames // 4 * 4 + 1, 1)
         dev = torch.device(device)
