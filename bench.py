@@ -51,6 +51,27 @@ def metric_name(args):
 UNIT = "steps/s"
 
 
+def guided_of(K: int) -> int:
+    """How many of K timed steps are guided: the 15:35 mix of the 50-step run."""
+    return round(0.3 * K)
+
+
+def wan_config(args, world: int) -> dict:
+    """The `config` object of the line - the workload, identical for both arms (`--impl reference` measures the same
+    configuration on the host cores and says how in `cpu_baseline.sample`)."""
+    f, h, w = (args.frames - 1) // 4 + 1, args.height // 8, args.width // 8
+    K, kg = args.steps, guided_of(args.steps)
+    cfg_layout = world > 1 and world % 2 == 0 and os.environ.get("WF_LAYOUT", "cfg") != "ulysses"
+    sp_world = world // 2 if cfg_layout else world
+    par = "single GPU" if world == 1 else ("cfg2 x " if cfg_layout else "") + \
+        f"ulysses{sp_world} (DiT tokens, {os.environ.get('WF_ULYSSES', 'peer')} exchange) + vae-rows{world} + flf-channels{world}"
+    return {"workload": f"Wan2.1-I2V-14B {args.height}x{args.width} {args.frames}f guided sampling (IRR+FLF+DSG), "
+                        f"{kg} guided + {K - kg} plain timed steps (the 15:35 mix of the 50-step run)",
+            "tokens": f * (h // 2) * (w // 2), "dit_layers": args.layers, "dit_forwards_timed": 4 * kg + 2 * (K - kg),
+            "vae": "fp32 storage, tf32 tensor-core convs", "parallelism": par,
+            "l2_policy": "inputs larger than L2 (33 GB of weights, 0.67 GB activations streamed per GEMM)"}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -169,8 +190,9 @@ def cpu_baseline(args, reps: int = int(os.environ.get("WF_CPU_REPS", "2"))):
         ts_vae = timed(lambda: wan_vae.encode_mode(PV, vcfg, wan_vae.decode(PV, vcfg, z)))
     t_vs, sp_vae = _median_spread(ts_vae)
     t_vae = t_vs * (args.frames * args.height * args.width) / (Fs * Hs * Ws)
-    # 50-step mix: 15 guided steps (4 forwards + 2 VAE round trips) and 35 plain steps (2 forwards)
-    t_step = (15 * (4 * t_fwd + 2 * t_vae) + 35 * 2 * t_fwd) / 50
+    # the timed steps of this configuration: kg guided steps (4 forwards + 2 VAE round trips) and K - kg plain steps (2 forwards)
+    K, kg = max(args.steps, 1), guided_of(args.steps)
+    t_step = (kg * (4 * t_fwd + 2 * t_vae) + (K - kg) * 2 * t_fwd) / K
     return {"value": 1.0 / t_step, "unit": UNIT, "cores": cores, "kind": "port",
             "reps": reps, "spread": {"block": round(sp_blk, 4), "attention": round(sp_att, 4), "vae": round(sp_vae, 4)},
             "block_s": t_blk, "attention_s": t_att, "vae_round_trip_s": t_vs,
@@ -178,7 +200,7 @@ def cpu_baseline(args, reps: int = int(os.environ.get("WF_CPU_REPS", "2"))):
                       f"Wan-14B-width DiT block at L={Ls} tokens ({t_blk:.2f}s, spread {sp_blk:.1%}; its self-attention "
                       f"{t_att:.2f}s, spread {sp_att:.1%}) and one VAE decode+encode of {Fs}x{Hs}x{Ws} ({t_vs:.2f}s, spread "
                       f"{sp_vae:.1%}), extrapolated to L={L} tokens x 40 blocks / {args.frames}x{args.height}x{args.width} and "
-                      f"the 15:35 guided:plain step mix"}
+                      f"the {kg}:{K - kg} guided:plain mix of the {K} timed steps"}
 
 
 def run_reference(args):
@@ -189,13 +211,11 @@ def run_reference(args):
         return
     base = cpu_baseline(args, reps=int(os.environ.get("WF_CPU_REPS_REF", max(5, min(args.steps, 7)))))
     v = base["value"]
-    f, h, w = (args.frames - 1) // 4 + 1, args.height // 8, args.width // 8
     emit({
         "impl": "reference", "metric": metric_name(args), "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"Wan2.1-I2V-14B {args.height}x{args.width} {args.frames}f, IRR+FLF+DSG, guided:plain 3:7 "
-                               "(CPU port of the reference, bounded sample extrapolated)", "tokens": f * (h // 2) * (w // 2)},
+        "config": wan_config(args, int(os.environ.get("WORLD_SIZE", "1"))),     # the same configuration object as our arm's
         "cpu_baseline": base,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
@@ -205,7 +225,8 @@ def gpu_reference(args, tr, dev, devt, n_guided: int = 2, n_plain: int = 2):
     §3, kind port-gpu): oracle/gpu_path.py = the vendored WanModel op sequence on cuBLAS bf16 GEMMs + eager fp32 torch ops +
     flash_attn_varlen_func (flash-attn 2.8.3), the chunked / cached WanVAE_ schedule on cuDNN (tf32), the reference loop
     and scheduler, OpenCV FLF scoring on the host - on the SAME weights, inputs, GPU.  One guided warm-up step, then
-    ``n_guided`` guided + ``n_plain`` plain steps timed with CUDA events; steps/s for the 15:35 mix of the 50-step run."""
+    ``n_guided`` guided + ``n_plain`` plain steps timed with CUDA events; steps/s for the guided:plain mix of the timed steps of
+    our arm (``guided_of``: 15:35 of the 50-step run)."""
     import torch
     from oracle import gpu_path, pipeline as opipe, unipc, wan_vae
     torch.cuda.empty_cache()
@@ -224,14 +245,15 @@ def gpu_reference(args, tr, dev, devt, n_guided: int = 2, n_plain: int = 2):
     torch.cuda.synchronize()
     ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(total)]
     g_ms, p_ms = statistics.mean(ms[warm:guide]), statistics.mean(ms[guide:])
-    t_step = (15 * g_ms + 35 * p_ms) / 50
+    K, kg = max(args.steps, 1), guided_of(args.steps)
+    t_step = (kg * g_ms + (K - kg) * p_ms) / K           # the guided:plain mix of our arm's timed steps (15:35 for K = 20)
     del ref_tr, ref_vae
     torch.cuda.empty_cache()
     import flash_attn
     return {"value": 1000.0 / t_step, "unit": UNIT, "kind": "port-gpu", "guided_step_ms": g_ms, "plain_step_ms": p_ms,
             "dit_forward_ms": p_ms / 2, "step_ms": ms,
             "sample": f"oracle/gpu_path.py on the same GPU, weights and inputs: {warm} guided warm-up step, then {n_guided} guided + "
-                      f"{n_plain} plain steps (CUDA events), weighted 15:35; cuBLAS bf16 Linears, eager fp32 norms / complex128 "
+                      f"{n_plain} plain steps (CUDA events), weighted {kg}:{K - kg} like the {K} timed steps of this run; cuBLAS bf16 Linears, eager fp32 norms / complex128 "
                       f"RoPE, flash-attn {flash_attn.__version__} varlen, chunked cuDNN tf32 VAE, OpenCV FLF scoring on the host "
                       "(the timed guided steps have step index < 6, where the reference's selector returns without scoring)"}
 
@@ -278,7 +300,7 @@ def run_ours(args):
     L = f * (h // 2) * (w // 2)
 
     K, W = args.steps, args.warmup
-    k_guided = round(0.3 * K)
+    k_guided = guided_of(K)
     total = W + K
     guide = W + k_guided
     knobs = dict(guidance_scale=4.0, guided=True, resample_steps=2, guide_steps=guide, omega=4.0, omega_resample=4.0,
@@ -376,11 +398,7 @@ def run_ours(args):
     line = {
         "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"Wan2.1-I2V-14B {args.height}x{args.width} {args.frames}f guided sampling (IRR+FLF+DSG), "
-                               f"{k_guided} guided + {K - k_guided} plain timed steps (the 15:35 mix of the 50-step run)",
-                   "tokens": L, "dit_layers": args.layers, "dit_forwards_timed": fwd - 4 * W,
-                   "vae": "fp32 storage, tf32 tensor-core convs", "parallelism": "single GPU" if world == 1 else (f"cfg2 x " if cfgp is not None else "") + f"ulysses{sp_world} (DiT tokens, {os.environ.get('WF_ULYSSES', 'peer')} exchange) + vae-rows{world} + flf-channels{world}",
-                   "l2_policy": "inputs larger than L2 (33 GB of weights, 0.67 GB activations streamed per GEMM)"},
+        "config": dict(wan_config(args, world), dit_forwards_timed=fwd - 4 * W),
         "clocks": clk, "gpu_launches": launches, "e2e": e2e, "roofline": roof,
         "dit_forwards_per_sec": (fwd - 4 * W) / (ms / 1000.0),
     }

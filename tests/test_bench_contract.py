@@ -20,6 +20,15 @@ def test_reference_arm_prints_one_json_line():
     assert d["metric"] == "denoising_steps_per_sec_wan2.1_i2v_14b_480p_81f_irr_flf_dsg"
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # the reference arm runs on OUR arm's configuration object: both arms build it with wan_config()
+    assert d["config"] == {"workload": "Wan2.1-I2V-14B 480x832 81f guided sampling (IRR+FLF+DSG), 0 guided + 1 plain timed steps "
+                                       "(the 15:35 mix of the 50-step run)",
+                           "tokens": 32760, "dit_layers": 40, "dit_forwards_timed": 2, "vae": "fp32 storage, tf32 tensor-core convs",
+                           "parallelism": "single GPU",
+                           "l2_policy": "inputs larger than L2 (33 GB of weights, 0.67 GB activations streamed per GEMM)"}
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert '"config": dict(wan_config(args, world), dit_forwards_timed=fwd - 4 * W)' in src       # run_ours
+    assert '"config": wan_config(args, int(os.environ.get("WORLD_SIZE", "1")))' in src            # run_reference
 
 
 def test_non_zero_ranks_of_the_reference_arm_stay_silent():
