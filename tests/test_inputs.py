@@ -147,3 +147,71 @@ def test_engine_presize_equals_oracle_and_scheduler_keeps_the_resized_pair(monke
         mask.add_(0.0)                                          # an in-place edit of a source invalidates the kept pair
         s.fuse_latents(x0, clip, mask, vae=vae)
         assert len(calls) == n + 2
+
+
+# ---- the on-disk contract: a warp folder of frames and mask_* images (infer_worldforge.py:65-102, :208-251) --------------------
+def _write_case(tmp_path, n_frames=5, n_masks=3, size=(50, 36)):
+    from PIL import Image
+    rng = np.random.default_rng(11)
+    for i in range(n_frames):
+        ext = "jpg" if i == 1 else "png"                     # mixed extensions sort by the whole path, as in the reference
+        Image.fromarray(rng.integers(0, 256, (size[1], size[0], 3), dtype=np.uint8)).save(tmp_path / f"warp_{i:03d}.{ext}")
+    for i in range(n_masks):
+        m = np.zeros((size[1], size[0]), np.uint8)
+        m[5 + i:25, 8:30 + i] = 255
+        Image.fromarray(m).save(tmp_path / f"mask_{i:03d}.png")
+    (tmp_path / "notes.txt").write_text("not an image")
+    return str(tmp_path)
+
+
+def test_case_folder_listing_and_mask_padding(tmp_path):
+    from worldforge_b200 import inputs
+    d = _write_case(tmp_path)
+    frames, masks = inputs.list_case_folder(d)
+    assert [os.path.basename(f) for f in frames] == ["warp_000.png", "warp_001.jpg", "warp_002.png", "warp_003.png", "warp_004.png"]
+    assert [os.path.basename(f) for f in masks] == ["mask_000.png", "mask_001.png", "mask_002.png"]
+    fr, mk, first = inputs.read_case_folder(d)
+    assert len(fr) == len(mk) == 5 and first is fr[0] and fr[0].mode == "RGB" and mk[0].mode == "L"
+    assert mk[3] is mk[2] and mk[4] is mk[2]                 # fewer masks than frames: the last one repeated (:95-97)
+    with pytest.raises(ValueError):
+        inputs.list_case_folder(str(tmp_path / "missing"))
+    assert inputs.target_size(1280, 720, 480 * 832) == (832, 464) and inputs.target_size(960, 512, 480 * 832) == (864, 448)
+    assert inputs.target_size(1280, 720, 720 * 1280) == (1280, 720) and inputs.target_size(832, 480) == (832, 480)
+
+
+@pytest.mark.skipif(not os.path.exists(mig.REF), reason="/root/reference is not mounted")
+def test_case_folder_matches_the_reference_entry_script(tmp_path):
+    """read_frames_from_directory and the size statements of infer_worldforge.py, taken from its source, against the engine's
+    loader - on a synthetic folder (mixed extensions, fewer masks than frames, no masks, more masks) and on the reference's
+    own truck case; then the whole of :225-251 (PIL resize, stacking, softening) against load_case's composition."""
+    from worldforge_b200 import inputs
+    ref_read = oin.reference_read_frames(mig.REF)
+    same = lambda a, b: len(a) == len(b) and all(x.size == y.size and x.mode == y.mode and x.tobytes() == y.tobytes() for x, y in zip(a, b))
+    for k, (nf, nm) in enumerate(((5, 3), (4, 0), (3, 6))):
+        sub = tmp_path / f"case{k}"
+        sub.mkdir()
+        d = _write_case(sub, nf, nm)
+        (f0, m0, first0), (f1, m1, first1) = ref_read(d), inputs.read_case_folder(d)
+        assert same(f0, f1) and same(m0, m1) and same([first0], [first1]) and len(m1) == nf
+    truck = os.path.join(os.path.dirname(os.path.dirname(mig.REF)), "test_case", "truck", "imgs")
+    fr, mk = inputs.list_case_folder(truck)
+    assert len(fr) == len(mk) == 49
+    rng = np.random.default_rng(3)
+    for w, h in [(1280, 720), (960, 512), (720, 1280), (1000, 1000), (641, 479)] + [tuple(int(v) for v in rng.integers(200, 2000, 2)) for _ in range(20)]:
+        for area in (480 * 832, 720 * 1280):
+            assert inputs.target_size(w, h, area) == oin.reference_target_size(mig.REF, w, h, area), (w, h, area)
+
+    d = _write_case(tmp_path / "case0", 5, 3, size=(100, 60))
+    got = inputs.load_case(d, max_area=64 * 96, transition_distance=6, decay_type="sine",
+                           _to_clip=lambda u8: torch.from_numpy(oin.stack_frames(u8.numpy())),
+                           _to_mask=lambda u8: torch.from_numpy(oin.soften_mask(oin.stack_masks(u8.numpy()), 6, "sine"))[None, None])
+    frames, masks, first = ref_read(d)
+    width, height = oin.reference_target_size(mig.REF, first.width, first.height, 64 * 96)
+    assert (got["width"], got["height"], got["num_frames"]) == (width, height, 5) and got["image"].size == (width, height)
+    resized = [f.resize((width, height)) for f in frames]                                                      # :231
+    video = torch.stack([torch.tensor(np.array(f)).permute(2, 0, 1).float() / 255.0 for f in resized])         # :232-235
+    assert torch.equal(got["video_ref"], video.unsqueeze(0).permute(0, 2, 1, 3, 4))                            # :236
+    marr = np.stack([np.array(m.resize((width, height))) / 255.0 for m in masks])                              # :245-246
+    marr = oin.reference_soften_mask(mig.REF)(marr, 6, "sine")                                                 # :248-249
+    assert torch.equal(got["mask"], torch.from_numpy(marr).unsqueeze(0).unsqueeze(0))                          # :251
+    assert got["image"].tobytes() == first.resize((width, height)).tobytes()                                   # :222

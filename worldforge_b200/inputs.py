@@ -111,3 +111,70 @@ def presize_guidance(video_ref: torch.Tensor, mask: torch.Tensor, target_shape):
         if (h, w) != (H, W):
             mask = F.interpolate(mask.reshape(b * c * f, 1, h, w), size=(H, W), mode="nearest").reshape(b, c, f, H, W)
     return video_ref.contiguous(), mask.contiguous()
+
+
+# ---- the on-disk contract of the warping stages: a folder of warped frames and ``mask_*`` images -----------------------------
+_IMAGE_PATTERNS = ("*.jpg", "*.jpeg", "*.png", "*.bmp", "*.tiff")
+
+
+def list_case_folder(directory: str):
+    """(frame files, mask files) of a warp folder in the reference's order (infer_worldforge.py:65-86;
+    run_longcat_worldforge_single.py:56-79): every image file of the five extensions, sorted by full path, split by the
+    ``mask_`` prefix of the file name."""
+    import glob
+    import os
+    files = []
+    for pat in _IMAGE_PATTERNS:
+        files.extend(glob.glob(os.path.join(directory, pat)))
+    files = sorted(files)
+    if not files:
+        raise ValueError(f"No image files found in directory {directory}")
+    masks = [f for f in files if os.path.basename(f).startswith("mask_")]
+    frames = [f for f in files if not os.path.basename(f).startswith("mask_")]
+    return frames, masks
+
+
+def read_case_folder(directory: str):
+    """``read_frames_from_directory`` (infer_worldforge.py:65-102): (RGB frames, L masks, first frame) as PIL images; no mask
+    files -> all-zero masks, fewer masks than frames -> the last one repeated, more -> cut (:92-99)."""
+    from PIL import Image
+    frame_files, mask_files = list_case_folder(directory)
+    frames = [Image.open(f).convert("RGB") for f in frame_files]
+    masks = [Image.open(f).convert("L") for f in mask_files]
+    if not masks and frames:
+        masks = [Image.new("L", frames[0].size, 0) for _ in frames]
+    while len(masks) < len(frames):
+        masks.append(masks[-1] if masks else Image.new("L", frames[0].size, 0))
+    masks = masks[:len(frames)]
+    return frames, masks, (frames[0] if frames else None)
+
+
+def target_size(image_width: int, image_height: int, max_area: int = 480 * 832, mod_value: int = 16):
+    """(width, height) the entry script resizes everything to (:218-221): the area budget at the first frame's aspect
+    ratio, rounded, then cut to a multiple of vae_scale_factor_spatial * patch_size = 16."""
+    aspect_ratio = image_height / image_width
+    height = round(np.sqrt(max_area * aspect_ratio)) // mod_value * mod_value
+    width = round(np.sqrt(max_area / aspect_ratio)) // mod_value * mod_value
+    return int(width), int(height)
+
+
+def load_case(directory: str, max_area: int = 480 * 832, mod_value: int = 16, soften: bool = True, transition_distance=15,
+              decay_type: str = "sine", device="cuda", image=None, _to_clip=None, _to_mask=None):
+    """A warp folder -> what the pipeline call takes (infer_worldforge.py:156, :208-251): ``image`` (PIL, resized),
+    ``video_ref`` [1,3,F,H,W] fp32 in [0,1] and ``mask`` [1,1,F,H,W] fp32 on ``device``, plus ``width`` / ``height``.
+    PIL decodes and resizes the 8-bit images on the host exactly as the script does (its default filter); the uint8 stacks
+    are uploaded once and turned into the fp32 clip / softened mask by the device kernels above.
+    (``_to_clip`` / ``_to_mask`` replace those two device steps - the CPU tests check the composition with the oracle's.)"""
+    frames, masks, first = read_case_folder(directory)
+    image = first if image is None else image
+    if image is None:
+        raise ValueError("Cannot get first frame as input image, please specify an image")
+    width, height = target_size(image.width, image.height, max_area, mod_value)
+    image = image.resize((width, height))
+    frames_u8 = torch.from_numpy(np.stack([np.array(f.resize((width, height))) for f in frames]))          # [F,H,W,3]
+    masks_u8 = torch.from_numpy(np.stack([np.array(m.resize((width, height))) for m in masks]))            # [F,H,W]
+    to_clip = _to_clip if _to_clip is not None else (lambda u8: clip_from_frames(u8.to(device)))
+    to_mask = _to_mask if _to_mask is not None else \
+        (lambda u8: prepare_mask(u8.to(device), soften=soften, transition_distance=transition_distance, decay_type=decay_type))
+    return dict(image=image, video_ref=to_clip(frames_u8), mask=to_mask(masks_u8), width=width, height=height,
+                num_frames=len(frames))
