@@ -114,7 +114,10 @@ def ref_sched():
         log.append((k.get("current_step"), list(r)))
         return r
     sm.VideoMotionPCASelector.select_motion_related_channels = spy
-    hist = run_sched(s)
+    with ref_shim.no_silent_fallbacks(sm.VideoMotionPCASelector) as events:
+        hist = run_sched(s)
+    sm.VideoMotionPCASelector.select_motion_related_channels = orig
+    assert not events, f"the reference took a silent fallback: {events}"
     s50 = sm.UniPCMultistepScheduler(num_train_timesteps=1000, solver_order=2, prediction_type="flow_prediction",
                                      use_flow_sigmas=True, flow_shift=3.0)
     s50.set_timesteps(50)
@@ -170,10 +173,12 @@ def ref_pipeline_call():
     def on_step(p, i, t, kw):
         hist.append(kw["latents"].clone())
         return {}
-    out = pipe(image=image, height=64, width=96, num_frames=9, num_inference_steps=PIPE_STEPS, guidance_scale=4.0,
-               generator=torch.Generator().manual_seed(42), latents=inp.latents.clone(), prompt_embeds=inp.prompt_embeds,
-               negative_prompt_embeds=inp.negative_prompt_embeds, output_type="latent", return_dict=False,
-               callback_on_step_end=on_step, video_ref=inp.video_ref, mask=inp.mask, **PIPE_KNOBS)[0]
+    with ref_shim.no_silent_fallbacks(sm.VideoMotionPCASelector) as events:
+        out = pipe(image=image, height=64, width=96, num_frames=9, num_inference_steps=PIPE_STEPS, guidance_scale=4.0,
+                   generator=torch.Generator().manual_seed(42), latents=inp.latents.clone(), prompt_embeds=inp.prompt_embeds,
+                   negative_prompt_embeds=inp.negative_prompt_embeds, output_type="latent", return_dict=False,
+                   callback_on_step_end=on_step, video_ref=inp.video_ref, mask=inp.mask, **PIPE_KNOBS)[0]
+    assert not events, f"the reference took a silent fallback: {events}"
     assert torch.equal(out, hist[-1])
     return dict(condition=conds[0], latents=[h.clone() for h in hist], dtypes=[str(h.dtype) for h in hist])
 
@@ -239,8 +244,10 @@ def ref_longcat_sched():
             log.append((k.get("current_step"), list(r)))
             return r
         sm.VideoMotionChannelSelector.select_motion_related_channels = spy
-        hist = run_longcat_sched(sm.FlowMatchEulerDiscreteScheduler(num_train_timesteps=1000, shift=1.0), distill)
+        with ref_shim.no_silent_fallbacks(sm.VideoMotionChannelSelector) as events:
+            hist = run_longcat_sched(sm.FlowMatchEulerDiscreteScheduler(num_train_timesteps=1000, shift=1.0), distill)
         sm.VideoMotionChannelSelector.select_motion_related_channels = orig
+        assert not events, f"the reference took a silent fallback: {events}"
         out["distill" if distill else "standard"] = dict(latents=torch.stack(hist), flf=log)
     return out
 

@@ -128,9 +128,11 @@ def ref_generate_i2v(distill: bool):
     pipe.prepare_latents = prepare_latents
     image = inp.video_ref[:, :, 0] * 2 - 1
     knobs = dict(mg.LC_KNOBS)
-    final = pipe.generate_i2v(image=image, prompt="pos", negative_prompt="neg", num_frames=9, num_inference_steps=I2V_STEPS,
-                              use_distill=distill, generator=torch.Generator().manual_seed(42), output_type="latent",
-                              max_sequence_length=pe.shape[2], video_ref=inp.video_ref, mask=inp.mask, **knobs)
+    with ref_shim.no_silent_fallbacks(sm.VideoMotionChannelSelector) as events:
+        final = pipe.generate_i2v(image=image, prompt="pos", negative_prompt="neg", num_frames=9, num_inference_steps=I2V_STEPS,
+                                  use_distill=distill, generator=torch.Generator().manual_seed(42), output_type="latent",
+                                  max_sequence_length=pe.shape[2], video_ref=inp.video_ref, mask=inp.mask, **knobs)
+    assert not events, f"the reference took a silent fallback: {events}"
     return dict(prepared=prepared[0], dit_inputs=torch.stack(seen), final=final.clone(), flf=[len(c) for _, c in getattr(sched, "flf_log", [])])
 
 

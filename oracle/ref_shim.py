@@ -534,3 +534,66 @@ class FixedImageEncoder:
 
     def encoder(self, pixel_values=None, output_hidden_states=True):
         return types.SimpleNamespace(hidden_states=[None, self.embeds, None])
+
+
+# ---- "a parity harness must assert these fallbacks were not taken" ------------------------------------------------
+class no_silent_fallbacks:
+    """The reference schedulers swallow failures and carry on with a different computation (fuse_latents returns the unfused
+    prediction, the selectors drop from Farneback flow to temporal differences / gradients, a failed metric scores 0.0 - all
+    inside bare ``except`` blocks: scheduling_unipc_multistep_clean.py:111, :225, :390, :477, :492, :606, :1286, :1414, :1419;
+    scheduling_flow_match_euler_discrete.py:142, :161, :242, :301, :322, :885, :1215, :1224).  A fixture generated through one
+    of them would pin the wrong computation.  Inside this context every such path leaves a trace in ``events``; the golden
+    generators assert the list stays empty."""
+
+    FALLBACK_METHODS = ("_extract_multiscale_motion", "_extract_temporal_difference")
+
+    def __init__(self, selector_cls):
+        self.cls, self.events, self._undo = selector_cls, [], []
+
+    def _patch(self, obj, name, fn):
+        self._undo.append((obj, name, getattr(obj, name)))
+        setattr(obj, name, fn)
+
+    def __enter__(self):
+        import logging
+        import cv2
+        ev = self.events
+        for name in self.FALLBACK_METHODS:
+            if hasattr(self.cls, name):
+                orig = getattr(self.cls, name)
+                def spy(self_, *a, _orig=orig, _name=name, **k):
+                    ev.append(("fallback method", _name))
+                    return _orig(self_, *a, **k)
+                self._patch(self.cls, name, spy)
+        if hasattr(self.cls, "_compute_flow_metrics"):
+            orig = self.cls._compute_flow_metrics
+            def metrics(self_, *a, _orig=orig, **k):
+                r = _orig(self_, *a, **k)
+                if r == 0.0:                       # the value its ``except`` returns; a genuine score of exactly 0 is not expected
+                    ev.append(("metric 0.0", None))
+                return r
+            self._patch(self.cls, "_compute_flow_metrics", metrics)
+        orig_fb = cv2.calcOpticalFlowFarneback
+        def farneback(*a, **k):
+            try:
+                return orig_fb(*a, **k)
+            except Exception as ex:
+                ev.append(("cv2.calcOpticalFlowFarneback raised", repr(ex)))
+                raise
+        self._patch(cv2, "calcOpticalFlowFarneback", farneback)
+
+        class Handler(logging.Handler):
+            def emit(self_, record):
+                if record.levelno >= logging.WARNING:
+                    ev.append(("log", record.getMessage()))
+        self._handler = Handler()
+        logging.getLogger().addHandler(self._handler)
+        return self.events
+
+    def __exit__(self, *a):
+        import logging
+        logging.getLogger().removeHandler(self._handler)
+        for obj, name, orig in reversed(self._undo):
+            setattr(obj, name, orig)
+        self._undo = []
+        return False
