@@ -57,3 +57,32 @@ def test_argument_validation_without_gpu():
     assert h.wf_gemm_bf16(p, 8, p, 8, None, p, 8, None, 0, 4, 33, 8, 0, None) == -1      # N not a multiple of 32
     assert h.wf_cfg_combine(p, p, p, 1, 1.0, 6, None) == -1                             # not a multiple of 4
     assert h.wf_rms_norm_rope(p, 8, p, p, 1, 72, 1e-6, None) == -1                      # RoPE needs head_dim 128
+
+
+def test_binding_argument_types_are_the_header_prototypes():
+    """Every ctypes prototype in worldforge_b200/lib.py has the argument list of its declaration in include/wf_b200.h
+    (pointers -> c_void_p, int / float / long long / unsigned by value).  The .cu files include the same header, so the
+    compiler holds the definitions to it; this holds the Python side to it."""
+    import ctypes as C
+    from worldforge_b200 import lib
+    src = open(os.path.join(ROOT, "include", "wf_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    protos = re.findall(r"\b([A-Za-z_][A-Za-z0-9_ \*]*?)\b(wf_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src)
+    assert sorted(n for _, n, _ in protos) == declared()
+    scalar = {"int": C.c_int, "float": C.c_float, "long long": C.c_longlong, "unsigned": C.c_uint, "unsigned int": C.c_uint}
+
+    def ctype(param):
+        param = param.strip()
+        if param in ("void", ""):
+            return None
+        if "*" in param:
+            return C.c_void_p
+        return scalar[re.sub(r"\bconst\b", "", re.sub(r"\b[A-Za-z_][A-Za-z0-9_]*$", "", param)).strip()]
+
+    for ret, name, args in protos:
+        got = [t for t in (ctype(a) for a in args.split(",")) if t is not None]
+        want = lib._SIGNATURES[name] if name in lib._SIGNATURES else lib._PLAIN[name][1]
+        assert got == want, (name, [t.__name__ for t in got], [t.__name__ for t in want])
+        if name in lib._SIGNATURES:
+            assert ret.strip() == "int", name                    # error code
