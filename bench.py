@@ -213,6 +213,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.model != "wan":      # the CPU arm times the headline configuration only (BASELINE.json configs[1] / [2] shapes)
+        emit({"impl": "reference", "unavailable": f"the CPU arm covers --model wan (the metric's configuration), not {args.model}"})
+        return
     base = cpu_baseline(args, reps=int(os.environ.get("WF_CPU_REPS_REF", max(5, min(args.steps, 7)))))
     v = base["value"]
     emit({
