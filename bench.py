@@ -207,6 +207,79 @@ def cpu_baseline(args, reps: int = int(os.environ.get("WF_CPU_REPS", "2"))):
                       f"the {kg}:{K - kg} guided:plain mix of the {K} timed steps"}
 
 
+def cpu_baseline_longcat(args, refine: bool, reps: int = int(os.environ.get("WF_CPU_REPS", "2"))):
+    """The LongCat lines' CPU baseline, same recipe as ``cpu_baseline``: ONE full-width LongCat-13.6B block of the oracle
+    (oracle/longcat_dit.py, bf16 autocast arithmetic) at a bounded token count, its self-attention alone, and (guided i2v
+    only) one VAE decode + encode of a 9 x 128 x 192 clip; medians after a warm-up; attention scaled with L^2, the rest
+    with L, x 48 blocks.  i2v (distilled, configs[3]): a guided step is 2 forwards + 1 VAE round trip, a plain step 1
+    forward, mixed like the timed steps.  Refine pass (configs[4]): 1 forward per step with block-sparse attention - the
+    attention term is scaled by the selected fraction (1 - sparsity) of the dense cost; chunk gating is not timed."""
+    import torch
+    from oracle import longcat_dit, wan_vae
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = longcat_dit.LongCatConfig(depth=1)
+    P = longcat_dit.init_params(cfg, 3)
+    T = 16 if refine else (args.frames - 1) // 4 + 1
+    h, w = args.height // 8, args.width // 8
+    L = T * (h // 2) * (w // 2)
+    grid_s = tuple(int(v) for v in os.environ.get("WF_CPU_GRID", "3x30x52").split("x"))
+    Ls = grid_s[0] * grid_s[1] * grid_s[2]
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(Ls, cfg.hidden_size, generator=g).to(torch.bfloat16)
+    y = torch.randn(64, cfg.hidden_size, generator=g).to(torch.bfloat16)
+    t = torch.randn(grid_s[0], cfg.adaln_tembed_dim, generator=g)
+    q = torch.randn(Ls, cfg.num_heads, cfg.head_dim, generator=g).to(torch.bfloat16)
+
+    def timed(fn, n=reps):
+        fn()
+        ts = []
+        for _ in range(max(n, 1)):
+            t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+        return ts
+
+    with torch.no_grad():
+        ts_blk = timed(lambda: longcat_dit.block_forward(P, cfg, 0, x, y, t, grid_s, 1, True))
+        ts_att = timed(lambda: longcat_dit.attention(q, q, q, True), 2 * reps + 1)
+    (t_blk, sp_blk), (t_att, sp_att) = _median_spread(ts_blk), _median_spread(ts_att)
+    t_lin = max(t_blk - t_att, 1e-6)
+    keep = (1.0 - 0.9375) if refine else 1.0
+    t_fwd = 48 * (t_lin * L / Ls + keep * t_att * (L / Ls) ** 2)
+    K = max(args.steps, 1)
+    if refine:
+        t_step, t_vs, sp_vae, mix = t_fwd, None, None, "1 forward per step (block-sparse attention: 1/16 of the dense cost)"
+    else:
+        vcfg = wan_vae.VaeConfig()
+        PV = wan_vae.init_params(vcfg, 4)
+        Fs, Hs, Ws = (9, 128, 192) if "WF_CPU_GRID" not in os.environ else (5, 32, 48)
+        with torch.no_grad():
+            z = torch.randn(16, (Fs - 1) // 4 + 1, Hs // 8, Ws // 8, generator=g)
+            ts_vae = timed(lambda: wan_vae.encode_mode(PV, vcfg, wan_vae.decode(PV, vcfg, z)))
+        t_vs, sp_vae = _median_spread(ts_vae)
+        t_vae = t_vs * (args.frames * args.height * args.width) / (Fs * Hs * Ws)
+        kg = round(0.625 * args.steps)
+        t_step = (kg * (2 * t_fwd + t_vae) + (K - kg) * t_fwd) / K
+        mix = f"{kg}:{K - kg} guided:plain mix of the {K} timed steps (guided: 2 forwards + 1 VAE round trip of {Fs}x{Hs}x{Ws} scaled by pixels x frames)"
+    return {"value": 1.0 / t_step, "unit": UNIT, "cores": cores, "kind": "port", "reps": reps,
+            "spread": {"block": round(sp_blk, 4), "attention": round(sp_att, 4), "vae": None if sp_vae is None else round(sp_vae, 4)},
+            "block_s": t_blk, "attention_s": t_att, "vae_round_trip_s": t_vs,
+            "sample": f"oracle (CPU port of the reference) on {cores} threads, fixed seeds, median of {reps} after a warm-up: one "
+                      f"LongCat-13.6B-width block at L={Ls} tokens ({t_blk:.2f}s, spread {sp_blk:.1%}; its self-attention {t_att:.2f}s, "
+                      f"spread {sp_att:.1%}), extrapolated to L={L} tokens x 48 blocks; {mix}"}
+
+
+def guarded_baseline(fn, args, *a):
+    """A reported baseline never fails (or delays past the deadline) the bench line it rides on."""
+    if args.no_cpu_baseline:
+        return None
+    if time.time() - T_START > EXTRAS_DEADLINE_S:
+        return {"skipped": f"the run was older than {EXTRAS_DEADLINE_S:.0f} s (WF_BENCH_EXTRAS_DEADLINE_S) when this leg was due"}
+    try:
+        return fn(args, *a)
+    except Exception as ex:  # noqa: BLE001
+        return {"error": f"{type(ex).__name__}: {ex}"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path = the oracle port on all host cores (the Python reference itself cannot
     travel to the GPU box and has no compiled component).  One bounded sample, every piece timed >= 5 times, medians."""
@@ -544,7 +617,8 @@ def run_longcat(args):
                    "tokens": N, "dit_layers": cfg.depth, "dit_forwards_timed": fwd, "vae": "fp32 storage, tf32 tensor-core convs",
                    "parallelism": "single GPU", "l2_policy": "inputs larger than L2 (27 GB of weights streamed per forward)"},
         "clocks": clk, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "dit_forwards_per_sec": fwd / (ms / 1000.0),
-        "flops_per_forward": dit.flops_per_forward(N, (h // 2) * (w // 2), 64), "cpu_baseline": None})
+        "flops_per_forward": dit.flops_per_forward(N, (h // 2) * (w // 2), 64),
+        "cpu_baseline": guarded_baseline(cpu_baseline_longcat, args, False)})
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -661,7 +735,7 @@ def run_longcat_refine(args):
         "roofline": {"kernel": "DiT forward (tcgen05 GEMMs + block-sparse attention), whole step", "bound": "tensor", "achieved": ach, "peak": pk["bf16"],
                      "unit": "TFLOP/s", "frac": ach / pk["bf16"], "traffic": None, "peak_source": pk["src"] + " sustained cuBLAS bf16",
                      "flops_per_forward": gemm + sparse},
-        "cpu_baseline": None})
+        "cpu_baseline": guarded_baseline(cpu_baseline_longcat, args, True) if world == 1 else None})
 
 
 def main():

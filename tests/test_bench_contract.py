@@ -36,3 +36,30 @@ def test_non_zero_ranks_of_the_reference_arm_stay_silent():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_longcat_cpu_baselines_on_a_tiny_sample():
+    """The LongCat lines' cpu_baseline (oracle LongCat block + VAE, extrapolated) - run in a child process on a tiny sample,
+    because importing bench.py re-points file descriptor 1."""
+    code = (
+        "import importlib.util, json, sys, types\n"
+        f"spec = importlib.util.spec_from_file_location('bench_mod', {os.path.join(ROOT, 'bench.py')!r})\n"
+        "b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)\n"
+        "out = {}\n"
+        "for refine, (h, w) in ((False, (480, 832)), (True, (704, 1280))):\n"
+        "    a = types.SimpleNamespace(frames=93, height=h, width=w, steps=8, no_cpu_baseline=False)\n"
+        "    out['refine' if refine else 'i2v'] = b.guarded_baseline(b.cpu_baseline_longcat, a, refine)\n"
+        "a.no_cpu_baseline = True\n"
+        "out['off'] = b.guarded_baseline(b.cpu_baseline_longcat, a, True)\n"
+        "out['err'] = b.guarded_baseline(lambda args: 1 / 0, a.__class__(no_cpu_baseline=False))\n"
+        "sys.stderr.write('RESULT ' + json.dumps(out) + '\\n')\n")
+    env = dict(os.environ, WF_CPU_GRID="2x10x13", WF_CPU_REPS="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(next(l for l in r.stderr.splitlines() if l.startswith("RESULT "))[7:])
+    for k, tokens in (("i2v", 37440), ("refine", 56320)):
+        d = out[k]
+        assert d["kind"] == "port" and d["unit"] == "steps/s" and d["value"] > 0 and d["cores"] >= 1, d
+        assert f"L={tokens} tokens x 48 blocks" in d["sample"], d["sample"]
+    assert "5:3 guided:plain" in out["i2v"]["sample"] and out["i2v"]["vae_round_trip_s"] > 0 and out["refine"]["vae_round_trip_s"] is None
+    assert out["off"] is None and out["err"]["error"].startswith("ZeroDivisionError")
