@@ -90,6 +90,8 @@ def parse():
                          "16-step guided i2v (configs[3]; 93 frames unless --frames is given); longcat-refine: the 480p->720p refine "
                          "pass with block-sparse attention (configs[4]; 16 latent frames of 704x1280, context parallel under torchrun)")
     ap.add_argument("--layers", type=int, default=None, help="DiT depth (default: 40 for Wan2.1-14B, 48 for LongCat; smaller only for dry runs)")
+    ap.add_argument("--bsa-chunk", default="4x4x8", help="longcat-refine: BSA chunk (t x h x w latent tokens). 4x4x8 = the code default "
+                    "(bsa_interface.py:619-622); 4x4x4 with --height 768 is what the reference's cp = 8 resolution bucket needs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the PyTorch + flash-attn comparator leg (N=1 only)")
@@ -642,16 +644,21 @@ def run_longcat_refine(args):
     lib.load()
     cfg = longcat.LongCatConfig(depth=args.layers)
     dit = longcat.WfLongCatTransformer.random_init(cfg, dev, seed=1234)
-    dit.bsa_params = dict(sparsity=0.9375, cdf_threshold=None, chunk_3d_shape_q=[4, 4, 8], chunk_3d_shape_k=[4, 4, 8])
+    ck = [int(v) for v in args.bsa_chunk.split("x")]
+    assert len(ck) == 3 and ck[0] * ck[1] * ck[2] in (64, 128), "--bsa-chunk: 64- or 128-token chunks (t x h x w)"
+    ct = ck[0] * ck[1] * ck[2]
+    dit.bsa_params = dict(sparsity=0.9375, cdf_threshold=None, chunk_3d_shape_q=list(ck), chunk_3d_shape_k=list(ck))
     dit.enable_bsa()
     T, h, w, ncl = 16, args.height // 8, args.width // 8, 4
     split = [1, 1]
     if world > 1:
         split = min(([i, world // i] for i in range(1, int(world ** 0.5) + 1) if world % i == 0), key=lambda f: abs(f[0] - f[1]))
-        if (h // 2) % (4 * split[0]) or (w // 2) % (8 * split[1]):
+        if (h // 2) % (ck[1] * split[0]) or (w // 2) % (ck[2] * split[1]):
             if rank == 0:
                 emit({"metric": "refine_steps_per_sec_longcat_video_720p_bsa", "unavailable": f"{h // 2}x{w // 2} patch grid does not split into "
-                      f"{split[0]}x{split[1]} blocks of whole 4x8 BSA chunks (the reference switches resolution buckets with cp: bukcet_config.py:82-109)"})
+                      f"{split[0]}x{split[1]} blocks of whole {ck[1]}x{ck[2]} BSA chunks - the reference's own assert (bsa_interface.py:638-639). It "
+                      "switches resolution buckets with cp (pipeline_longcat_video.py:1334-1337 -> bukcet_config.py:82-109: 768x1280 at cp = 8, "
+                      "whose 24x20 blocks need the checkpoint's 4x4x4 chunks): --height 768 --width 1280 --bsa-chunk 4x4x4"})
             return
         dit.enable_context_parallel(dist.group.WORLD, split)
     N = T * (h // 2) * (w // 2)
@@ -718,17 +725,17 @@ def run_longcat_refine(args):
     pk = peaks()
     C, Fd, per = cfg.hidden_size, cfg.ffn_dim, (h // 2) * (w // 2)
     Nn, ctx = N - ncl * per, 64
-    n_sel = int((1 - 0.9375) * (N // 128))
+    n_sel = int((1 - 0.9375) * (N // ct))
     # algorithmic FLOPs of one forward: token-side GEMMs, cross-attention, and the SELECTED blocks of the sparse self-attention
     gemm = cfg.depth * (2 * N * (4 * C * C + 3 * C * Fd) + 2 * Nn * 2 * C * C + 2 * ctx * 2 * C * C + 4 * Nn * ctx * C)
-    sparse = cfg.depth * 4.0 * C * 128 * 128 * n_sel * (N // 128)
+    sparse = cfg.depth * 4.0 * C * ct * ct * n_sel * (N // ct)
     step_ms = ms / K
     ach = (gemm + sparse) / world / (step_ms / 1000.0) / 1e12
     emit({
         "metric": "refine_steps_per_sec_longcat_video_720p_16lf_bsa", "value": K / (ms / 1000.0), "unit": UNIT, "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"LongCat-Video 13.6B refine pass {args.height}x{args.width}, 16 latent frames (4 condition + 12 noise), block-sparse "
-                               f"self-attention (4x4x8 chunks, sparsity 0.9375: {n_sel} of {N // 128} key chunks per query chunk), Euler steps from t = 0.5",
+                               f"self-attention ({args.bsa_chunk} chunks, sparsity 0.9375: {n_sel} of {N // ct} key chunks per query chunk), Euler steps from t = 0.5",
                    "tokens": N, "dit_layers": cfg.depth, "parallelism": "single GPU" if world == 1 else f"context parallel cp_split_hw {split[0]}x{split[1]} (NCCL all-to-all)",
                    "l2_policy": "inputs larger than L2 (27 GB of weights streamed per forward)"},
         "clocks": clk, "gpu_launches": launches, "e2e": e2e,
