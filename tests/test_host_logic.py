@@ -293,3 +293,33 @@ def test_longcat_continuation_schedule_host():
     assert torch.equal(a, b) and len(a) == 16
     with pytest.raises(Exception):
         lp.vc_timesteps(sw, 16, use_distill=True, enhance_hf=True)
+
+
+def test_2d_context_parallel_split_is_the_reference_split():
+    """ulysses.split_2d / gather_2d against the reference's own split_tensor_in_cp_2d (context_parallel_util.py:91-121) for every
+    rank of the 1x2, 2x2 and 2x4 (cp = 8) layouts, and the layout rule get_optimal_split (:238-243) bench.py restates."""
+    import importlib.util
+    import os
+    from worldforge_b200 import ulysses
+    x = torch.arange(2 * 3 * 8 * 12 * 5).reshape(2, 3, 8, 12, 5)
+    for split in ([1, 2], [2, 2], [2, 4], [4, 2]):
+        parts = [ulysses.split_2d(x, (2, 3), split, r) for r in range(split[0] * split[1])]
+        assert all(p.shape == (2, 3, 8 // split[0], 12 // split[1], 5) for p in parts)
+        assert torch.equal(ulysses.gather_2d(parts, (2, 3), split), x)
+        assert torch.equal(parts[1], x[:, :, :8 // split[0], 12 // split[1]:2 * (12 // split[1])])     # row-major: w inner
+    with pytest.raises(RuntimeError):
+        ulysses.split_2d(x, (2, 3), [3, 1], 0)
+    optimal = lambda n: min(([i, n // i] for i in range(1, int(n ** 0.5) + 1) if n % i == 0), key=lambda f: abs(f[0] - f[1]))
+    assert [optimal(n) for n in (1, 2, 4, 8)] == [[1, 1], [1, 2], [2, 2], [2, 4]]
+    ref = "/root/reference/longcat_for_worldforge/longcat_video/context_parallel/context_parallel_util.py"
+    if not os.path.exists(ref):
+        return
+    spec = importlib.util.spec_from_file_location("wf_ref_cp_util", ref)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    assert [m.get_optimal_split(n) for n in (1, 2, 4, 8)] == [optimal(n) for n in (1, 2, 4, 8)]
+    for split in ([1, 2], [2, 2], [2, 4], [4, 2]):
+        m.cp_size = split[0] * split[1]
+        for r in range(m.cp_size):
+            m.get_cp_rank = lambda r=r: r
+            assert torch.equal(m.split_tensor_in_cp_2d(x, (2, 3), split), ulysses.split_2d(x, (2, 3), split, r)), (split, r)
